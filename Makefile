@@ -1,0 +1,28 @@
+# Builds the product library (CUDA, sm_100a), the CPU oracle (test infrastructure) and the host-check shim.
+NVCC      ?= nvcc
+CXX       ?= g++
+NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 \
+             -Xcompiler -fPIC,-fvisibility=hidden --shared -Iinclude
+LIB       := aruco_b200/lib/libaruco_b200.so
+CSRC      := $(wildcard aruco_b200/csrc/*.cu aruco_b200/csrc/*.cuh) include/aruco_b200.h
+
+all: $(LIB) oracle hostcheck
+
+$(LIB): $(CSRC)
+	@mkdir -p aruco_b200/lib
+	$(NVCC) $(NVFLAGS) -Xptxas -v -o $@ aruco_b200/csrc/aruco_b200.cu 2> aruco_b200/lib/ptxas.log || (cat aruco_b200/lib/ptxas.log; false)
+
+oracle: oracle/_build/liboracle.so
+oracle/_build/liboracle.so: $(wildcard oracle/*.cpp oracle/*.h)
+	@mkdir -p oracle/_build
+	@if ls oracle/*.cpp >/dev/null 2>&1; then $(CXX) -O2 -fopenmp -ffp-contract=off -shared -fPIC -o $@ oracle/*.cpp; fi
+
+hostcheck: tests/_build/libhostcheck.so
+tests/_build/libhostcheck.so: tests/hostcheck/hostcheck.cpp $(wildcard aruco_b200/csrc/*.cuh)
+	@mkdir -p tests/_build
+	$(CXX) -O2 -ffp-contract=off -shared -fPIC -o $@ tests/hostcheck/hostcheck.cpp
+
+clean:
+	rm -rf aruco_b200/lib/*.so oracle/_build tests/_build
+
+.PHONY: all oracle hostcheck clean

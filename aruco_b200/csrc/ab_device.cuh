@@ -1,0 +1,104 @@
+// Device-side data layout of one batch (fixed-capacity SoA buffers, see DESIGN.md "Data layout in HBM").
+#pragma once
+#include <stdint.h>
+#include "../../include/aruco_b200.h"
+#include "ab_math.cuh"
+
+namespace ab {
+
+enum : unsigned {
+    ERR_STARTS_OVERFLOW = 1u,
+    ERR_CONTOURS_OVERFLOW = 2u,
+    ERR_POOL_OVERFLOW = 4u,
+    ERR_QUADS_OVERFLOW = 8u,
+    ERR_CANDS_OVERFLOW = 16u,
+};
+
+constexpr int MAX_QUADS = 1024;  // hard upper bound of quads per frame handled by the per-frame filter
+constexpr int MAX_CANDS = 512;   // hard upper bound of candidates per frame
+
+struct ContourRec {
+    uint32_t frame;
+    uint32_t off;  // first point in the pool
+    uint32_t n;    // number of points
+    uint32_t key;  // raster scan position of the Suzuki start (ordering = reverse discovery)
+};
+
+struct QuadRec {
+    short x[4], y[4];
+    uint32_t key;
+    uint32_t contour;
+};
+
+struct CandRec {
+    float c[8];        // corners entering warp (after the orientation swap), integer valued
+    float refined[8];  // corners after LINES / SUBPIX / HARRIS (== c when NONE)
+    uint32_t contour;
+    int32_t swapped;
+    int32_t id;
+    int32_t nrot;
+};
+
+// counters zeroed at the start of every batch
+struct Counters {
+    unsigned long long n_starts;
+    unsigned long long pool_used;
+    unsigned int n_contours;
+    unsigned int trace_work;
+    unsigned int err;
+    unsigned int pad;
+    unsigned long long n_quads_total, n_cands_total, n_markers_total;
+};
+
+struct HrmDict {
+    const uint64_t* bits;  // count rotation-0 bit strings
+    const uint32_t* ids;   // sorted folded ids (tree order) .. see k_decode
+    const uint32_t* ord_ids;
+    const int32_t* ord_pos;
+    const int32_t* tree;  // 2*count children
+    int root;
+    int count;
+    int n;
+    int correction;
+};
+
+struct Batch {
+    int W, H, B, wpr;
+    size_t bits_words;  // per frame
+    const uint8_t* grey;
+    size_t grey_row, grey_frame;
+    uint8_t* thres;   // [B][H][W]
+    uint32_t* bits;   // [B][bits_words]
+    uint32_t* bits2;  // scratch for erosion
+    uint2* starts;
+    unsigned long long cap_starts;
+    ContourRec* contours;
+    unsigned int cap_contours;
+    uint32_t* pool;
+    unsigned long long cap_pool;
+    QuadRec* quads;  // [B][cap_q]
+    int cap_q;
+    CandRec* cands;  // [B][cap_c]
+    int cap_c;
+    uint8_t* canon;  // [B][cap_c][S*S]
+    ab_marker* markers;  // [B][cap_c]
+    Counters* cnt;
+    unsigned int* n_quads;    // [B]
+    unsigned int* n_cands;    // [B]
+    unsigned int* n_markers;  // [B]
+    // parameters
+    int min_len, max_len;  // contour length limits (exclusive)
+    int S;                 // warp size
+    int decoder;
+    int corner_method;
+    int subpix_win;
+    int locked;
+    int set_y_perp;
+    int vx0, vy0, vx1, vy1;  // valid region of the border filter
+    float marker_size;
+    Camera cam;
+    HrmDict dict;
+    AB_HD BitImage bit_image(int f) const { return BitImage{bits + (size_t)f * bits_words, wpr, W, H}; }
+};
+
+}  // namespace ab

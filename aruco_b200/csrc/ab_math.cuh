@@ -1,0 +1,638 @@
+// Per-thread arithmetic used by the kernels: every function restates one OpenCV primitive the reference
+// calls on its hot path.  All f64 code here must not be contracted into FMAs
+// (the library is compiled with -fmad=false) so that results match the x86 evaluation order.
+#pragma once
+#include <math.h>
+#include <float.h>
+#include <stdint.h>
+#include "ab_trace.cuh"
+
+namespace ab {
+
+// ---------------------------------------------------------------------------------------------------
+// approxPolyDP pieces (reference call: src/markerdetector.cpp:522; OpenCV 4.13 semantics)
+// ---------------------------------------------------------------------------------------------------
+// squared distance of p to the SEGMENT s-e, f64 on integer coordinates
+AB_HD double seg_dist2(int px, int py, int sx, int sy, int ex, int ey) {
+    double dx = (double)(ex - sx), dy = (double)(ey - sy);
+    double qx = (double)(px - sx), qy = (double)(py - sy);
+    double dd = dx * dx + dy * dy;
+    double t = qx * dx + qy * dy;
+    if (t < 0) return qx * qx + qy * qy;
+    if (t > dd) {
+        double fx = (double)(px - ex), fy = (double)(py - ey);
+        return fx * fx + fy * fy;
+    }
+    double c = qx * dy - qy * dx;
+    return c * c / dd;
+}
+
+// final clean-up pass of approxPolyDP over the emitted closed polygon (in place). E = eps^2.
+AB_HD int dp_cleanup(int* px, int* py, int count, double E) {
+    int new_count = count;
+    if (count == 0) return 0;
+    int pos = count - 1;
+    int sx = px[pos], sy = py[pos];
+    if (++pos >= count) pos = 0;
+    int wpos = pos;
+    int tx = px[pos], ty = py[pos];
+    if (++pos >= count) pos = 0;
+    for (int i = 0; i < count && new_count > 2; i++) {
+        int ex = px[pos], ey = py[pos];
+        if (++pos >= count) pos = 0;
+        double dx = (double)(ex - sx), dy = (double)(ey - sy);
+        double dist = fabs((double)(tx - sx) * dy - (double)(ty - sy) * dx);
+        double sip = (double)((tx - sx) * (ex - tx) + (ty - sy) * (ey - ty));
+        if (dist * dist <= 0.5 * E * (dx * dx + dy * dy) && dx != 0 && dy != 0 && sip >= 0) {
+            new_count--;
+            px[wpos] = sx = ex;
+            py[wpos] = sy = ey;
+            if (++wpos >= count) wpos = 0;
+            tx = px[pos];
+            ty = py[pos];
+            if (++pos >= count) pos = 0;
+            i++;
+            continue;
+        }
+        px[wpos] = sx = tx;
+        py[wpos] = sy = ty;
+        if (++wpos >= count) wpos = 0;
+        tx = ex;
+        ty = ey;
+    }
+    return new_count;
+}
+
+// cv::isContourConvex on 4 integer points (src/markerdetector.cpp:535)
+AB_HD bool is_convex4(const int* x, const int* y) {
+    int px = x[2], py = y[2], cx = x[3], cy = y[3];
+    int dx0 = cx - px, dy0 = cy - py;
+    int orientation = 0;
+    for (int i = 0; i < 4; i++) {
+        px = cx;
+        py = cy;
+        cx = x[i];
+        cy = y[i];
+        int dx = cx - px, dy = cy - py;
+        long long dxdy0 = (long long)dx * dy0, dydx0 = (long long)dy * dx0;
+        orientation |= (dydx0 > dxdy0) ? 1 : ((dydx0 < dxdy0) ? 2 : 3);
+        if (orientation == 3) return false;
+        dx0 = dx;
+        dy0 = dy;
+    }
+    return true;
+}
+
+// aruco::perimeter (src/utils.h:37-44): f64 norms of f32 differences summed into an f32
+AB_HD float perimeter4(const float* c) {
+    float sum = 0.f;
+    for (int i = 0; i < 4; i++) {
+        int j = (i + 1) & 3;
+        float dx = c[2 * i] - c[2 * j], dy = c[2 * i + 1] - c[2 * j + 1];
+        sum = (float)((double)sum + sqrt((double)dx * (double)dx + (double)dy * (double)dy));
+    }
+    return sum;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// getPerspectiveTransform + warpPerspective(INTER_NEAREST) (src/markerdetector.cpp:684-697, A.5/A.6)
+// ---------------------------------------------------------------------------------------------------
+// Gaussian elimination with partial pivoting in the operation order of OpenCV's LUImpl<double>.
+AB_HD bool lu_solve8(double A[8][8], double b[8]) {
+    for (int i = 0; i < 8; i++) {
+        int k = i;
+        for (int j = i + 1; j < 8; j++)
+            if (fabs(A[j][i]) > fabs(A[k][i])) k = j;
+        if (fabs(A[k][i]) < DBL_EPSILON * 100) return false;
+        if (k != i) {
+            for (int j = i; j < 8; j++) {
+                double t = A[i][j];
+                A[i][j] = A[k][j];
+                A[k][j] = t;
+            }
+            double t = b[i];
+            b[i] = b[k];
+            b[k] = t;
+        }
+        double d = -1 / A[i][i];
+        for (int j = i + 1; j < 8; j++) {
+            double alpha = A[j][i] * d;
+            for (int c = i + 1; c < 8; c++) A[j][c] += alpha * A[i][c];
+            b[j] += alpha * b[i];
+        }
+    }
+    for (int i = 7; i >= 0; i--) {
+        double s = b[i];
+        for (int c = i + 1; c < 8; c++) s -= A[i][c] * b[c];
+        b[i] = s / A[i][i];
+    }
+    return true;
+}
+
+// M maps src quad -> dst quad (both 4x(x,y)); row-major 3x3 with M[8] = 1
+AB_HD bool perspective_transform(const float* src, const float* dst, double* M) {
+    double a[8][8], b[8];
+    for (int i = 0; i < 4; i++) {
+        float sx = src[2 * i], sy = src[2 * i + 1], dx = dst[2 * i], dy = dst[2 * i + 1];
+        a[i][0] = a[i + 4][3] = sx;
+        a[i][1] = a[i + 4][4] = sy;
+        a[i][2] = a[i + 4][5] = 1;
+        a[i][3] = a[i][4] = a[i][5] = a[i + 4][0] = a[i + 4][1] = a[i + 4][2] = 0;
+        a[i][6] = (double)(-sx * dx);
+        a[i][7] = (double)(-sy * dx);
+        a[i + 4][6] = (double)(-sx * dy);
+        a[i + 4][7] = (double)(-sy * dy);
+        b[i] = dx;
+        b[i + 4] = dy;
+    }
+    if (!lu_solve8(a, b)) return false;
+    for (int i = 0; i < 8; i++) M[i] = b[i];
+    M[8] = 1.0;
+    return true;
+}
+
+// closed-form 3x3 inverse as cv::invert does for 3x3 (adjugate * 1/det)
+AB_HD bool invert3(const double* m, double* t) {
+    double d = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+    if (d == 0.) return false;
+    d = 1. / d;
+    t[0] = (m[4] * m[8] - m[5] * m[7]) * d;
+    t[1] = (m[2] * m[7] - m[1] * m[8]) * d;
+    t[2] = (m[1] * m[5] - m[2] * m[4]) * d;
+    t[3] = (m[5] * m[6] - m[3] * m[8]) * d;
+    t[4] = (m[0] * m[8] - m[2] * m[6]) * d;
+    t[5] = (m[2] * m[3] - m[0] * m[5]) * d;
+    t[6] = (m[3] * m[7] - m[4] * m[6]) * d;
+    t[7] = (m[1] * m[6] - m[0] * m[7]) * d;
+    t[8] = (m[0] * m[4] - m[1] * m[3]) * d;
+    return true;
+}
+
+AB_HD double clamp_int_range(double v) { return v < -2147483648.0 ? -2147483648.0 : (v > 2147483647.0 ? 2147483647.0 : v); }
+
+// source pixel of destination pixel (x,y) under inverse map Mi; OpenCV processes the row in blocks of
+// `bw` columns whose origin bx enters the affine part first (block size rule of WarpPerspectiveInvoker).
+AB_HD void warp_src_coord(const double* Mi, int x, int y, int bw, int* sx, int* sy) {
+    int bx = (x / bw) * bw, x1 = x - bx;
+    double X0 = Mi[0] * bx + Mi[1] * y + Mi[2];
+    double Y0 = Mi[3] * bx + Mi[4] * y + Mi[5];
+    double W0 = Mi[6] * bx + Mi[7] * y + Mi[8];
+    double W = W0 + Mi[6] * x1;
+    W = W ? 1. / W : 0;
+    double fX = clamp_int_range((X0 + Mi[0] * x1) * W);
+    double fY = clamp_int_range((Y0 + Mi[3] * x1) * W);
+    *sx = (int)rint(fX);
+    *sy = (int)rint(fY);
+}
+
+AB_HD int warp_block_width(int S) {
+    int bh0 = 16 < S ? 16 : S;
+    int bw0 = (1024 / bh0) < S ? (1024 / bh0) : S;
+    return bw0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// threshold(BINARY|OTSU) threshold value from a 256-bin histogram of N samples
+// ---------------------------------------------------------------------------------------------------
+AB_HD int otsu_threshold(const int* h, int N) {
+    double mu = 0, scale = 1. / N;
+    for (int i = 0; i < 256; i++) mu += i * (double)h[i];
+    mu *= scale;
+    double mu1 = 0, q1 = 0, max_sigma = 0, max_val = 0;
+    for (int i = 0; i < 256; i++) {
+        double p_i = h[i] * scale;
+        mu1 *= q1;
+        q1 += p_i;
+        double q2 = 1. - q1;
+        double mn = q1 < q2 ? q1 : q2, mx = q1 < q2 ? q2 : q1;
+        if (mn < FLT_EPSILON || mx > 1. - FLT_EPSILON) continue;
+        mu1 = (mu1 + i * p_i) / q1;
+        double mu2 = (mu - q1 * mu1) / q2;
+        double sigma = q1 * q2 * (mu1 - mu2) * (mu1 - mu2);
+        if (sigma > max_sigma) {
+            max_sigma = sigma;
+            max_val = i;
+        }
+    }
+    return (int)max_val;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// FiducidalMarkers decode from the 7x7 cell majority bits (src/arucofidmarkers.cpp:100-137, 168-184)
+// cells[y*7+x] = 1 when the cell is white.  Returns id or -1; *nrot in 0..3.
+// ---------------------------------------------------------------------------------------------------
+AB_HD int fid_row_dist(int bits5) {
+    // words 10000 10111 01001 01110 (bit 4 = column 0)
+    const int w[4] = {0x10, 0x17, 0x09, 0x0E};
+    int best = 100000;
+    for (int p = 0; p < 4; p++) {
+#if defined(__CUDA_ARCH__)
+        int d = __popc((unsigned)(bits5 ^ w[p]));
+#else
+        int d = __builtin_popcount((unsigned)(bits5 ^ w[p]));
+#endif
+        if (d < best) best = d;
+    }
+    return best;
+}
+
+AB_HD int fid_decode(const uint8_t* cells, int* nrot) {
+    *nrot = 0;
+    for (int y = 0; y < 7; y++) {
+        int inc = (y == 0 || y == 6) ? 1 : 6;
+        for (int x = 0; x < 7; x += inc)
+            if (cells[y * 7 + x]) return -1;
+    }
+    uint8_t cur[25], nxt[25];
+    for (int y = 0; y < 5; y++)
+        for (int x = 0; x < 5; x++) cur[y * 5 + x] = cells[(y + 1) * 7 + x + 1];
+    int minDist = 1 << 30, bestRot = 0;
+    uint8_t best[25];
+    for (int r = 0; r < 4; r++) {
+        if (r > 0) {
+            for (int i = 0; i < 5; i++)
+                for (int j = 0; j < 5; j++) nxt[i * 5 + j] = cur[(5 - j - 1) * 5 + i];
+            for (int i = 0; i < 25; i++) cur[i] = nxt[i];
+        }
+        int dist = 0;
+        for (int y = 0; y < 5; y++) {
+            int v = 0;
+            for (int x = 0; x < 5; x++) v = (v << 1) | cur[y * 5 + x];
+            dist += fid_row_dist(v);
+        }
+        if (dist < minDist) {
+            minDist = dist;
+            bestRot = r;
+            for (int i = 0; i < 25; i++) best[i] = cur[i];
+        }
+    }
+    *nrot = bestRot;
+    if (minDist != 0) return -1;
+    int id = 0;
+    for (int y = 0; y < 5; y++) id |= ((best[y * 5 + 1] << 1) | best[y * 5 + 3]) << (2 * (4 - y));
+    return id;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// HRM: bit strings / folded ids of the 4 rotations (src/highlyreliablemarkers.cpp:149-180)
+// code[y*n+x] in {0,1}; bits[r] has bit pos set for rotation r; ids[r] = OR-fold with x86 shift semantics
+// ---------------------------------------------------------------------------------------------------
+AB_HD void hrm_rotations(const uint8_t* code, int n, uint64_t bits[4], uint32_t ids[4]) {
+    for (int r = 0; r < 4; r++) {
+        bits[r] = 0;
+        ids[r] = 0;
+    }
+    for (int y = 0; y < n; y++)
+        for (int x = 0; x < n; x++) {
+            if (!code[y * n + x]) continue;
+            for (int r = 0; r < 4; r++) {
+                int _x = x, _y = y;
+                if (r == 1) {
+                    _y = x;
+                    _x = n - y - 1;
+                } else if (r == 2) {
+                    _y = n - y - 1;
+                    _x = n - x - 1;
+                } else if (r == 3) {
+                    _y = n - x - 1;
+                    _x = y;
+                }
+                int pos = _y * n + _x;
+                bits[r] |= (uint64_t)1 << pos;
+                int sh = pos & 31;
+                ids[r] |= (sh == 31) ? 0u : (2u << sh);
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Camera model helpers (K, D arrive as f32 and are widened)
+// ---------------------------------------------------------------------------------------------------
+struct Camera {
+    double fx, fy, cx, cy;
+    double k1, k2, p1, p2, k3;
+    float fxf, fyf, cxf, cyf;
+    int has_K, has_D;
+};
+
+// cv::undistortPoints(src, K, D, R=I, P=K): 5 fixed-point iterations, result rounded to f32
+AB_HD void undistort_point_px(const Camera& c, float u, float v, float* ou, float* ov) {
+    double x0 = ((double)u - c.cx) / c.fx, y0 = ((double)v - c.cy) / c.fy;
+    double x = x0, y = y0;
+    for (int j = 0; j < 5; j++) {
+        double r2 = x * x + y * y;
+        double icdist = 1. / (1 + ((c.k3 * r2 + c.k2) * r2 + c.k1) * r2);
+        double deltaX = 2 * c.p1 * x * y + c.p2 * (r2 + 2 * x * x);
+        double deltaY = c.p1 * (r2 + 2 * y * y) + 2 * c.p2 * x * y;
+        x = (x0 - deltaX) * icdist;
+        y = (y0 - deltaY) * icdist;
+    }
+    *ou = (float)(x * c.fx + c.cx);
+    *ov = (float)(y * c.fy + c.cy);
+}
+
+// same iteration but returning normalised coordinates in f64 (used by the pose initialisation)
+AB_HD void undistort_point_norm(const Camera& c, double u, double v, double* ox, double* oy) {
+    double x0 = (u - c.cx) / c.fx, y0 = (v - c.cy) / c.fy;
+    double x = x0, y = y0;
+    for (int j = 0; j < 20; j++) {
+        double r2 = x * x + y * y;
+        double icdist = 1. / (1 + ((c.k3 * r2 + c.k2) * r2 + c.k1) * r2);
+        double deltaX = 2 * c.p1 * x * y + c.p2 * (r2 + 2 * x * x);
+        double deltaY = c.p1 * (r2 + 2 * y * y) + 2 * c.p2 * x * y;
+        x = (x0 - deltaX) * icdist;
+        y = (y0 - deltaY) * icdist;
+    }
+    *ox = x;
+    *oy = y;
+}
+
+// forward distortion of a normalised point, pixel output in f64
+AB_HD void distort_norm_to_px(const Camera& c, double x, double y, double* u, double* v) {
+    double r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+    double a1 = 2 * x * y, a2 = r2 + 2 * x * x, a3 = r2 + 2 * y * y;
+    double cdist = 1 + c.k1 * r2 + c.k2 * r4 + c.k3 * r6;
+    double xd = x * cdist + c.p1 * a1 + c.p2 * a2;
+    double yd = y * cdist + c.p1 * a3 + c.p2 * a1;
+    *u = xd * c.fx + c.cx;
+    *v = yd * c.fy + c.cy;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Pose: cv::solvePnP(SOLVEPNP_ITERATIVE) for 4 coplanar points (src/markerdetector.cpp:458, marker.cpp:118)
+// planar homography initialisation + Levenberg-Marquardt on the pixel reprojection error
+// ---------------------------------------------------------------------------------------------------
+AB_HD void rodrigues_to_mat(const double* r, double* R) {
+    double theta = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    if (theta < DBL_EPSILON) {
+        R[0] = R[4] = R[8] = 1;
+        R[1] = R[2] = R[3] = R[5] = R[6] = R[7] = 0;
+        return;
+    }
+    double c = cos(theta), s = sin(theta), c1 = 1. - c, it = 1. / theta;
+    double x = r[0] * it, y = r[1] * it, z = r[2] * it;
+    R[0] = c + c1 * x * x;
+    R[1] = c1 * x * y - s * z;
+    R[2] = c1 * x * z + s * y;
+    R[3] = c1 * x * y + s * z;
+    R[4] = c + c1 * y * y;
+    R[5] = c1 * y * z - s * x;
+    R[6] = c1 * x * z - s * y;
+    R[7] = c1 * y * z + s * x;
+    R[8] = c + c1 * z * z;
+}
+
+// rotation matrix (already orthonormal) -> Rodrigues vector, cv::Rodrigues conventions incl. theta ~ pi
+AB_HD void mat_to_rodrigues(const double* R, double* r) {
+    double rx = R[7] - R[5], ry = R[2] - R[6], rz = R[3] - R[1];
+    double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+    double c = (R[0] + R[4] + R[8] - 1) * 0.5;
+    c = c > 1. ? 1. : (c < -1. ? -1. : c);
+    double theta = acos(c);
+    if (s < 1e-5) {
+        if (c > 0) {
+            r[0] = r[1] = r[2] = 0;
+        } else {
+            double t = (R[0] + 1) * 0.5;
+            rx = sqrt(t > 0 ? t : 0);
+            t = (R[4] + 1) * 0.5;
+            ry = sqrt(t > 0 ? t : 0) * (R[1] < 0 ? -1. : 1.);
+            t = (R[8] + 1) * 0.5;
+            rz = sqrt(t > 0 ? t : 0) * (R[2] < 0 ? -1. : 1.);
+            if (fabs(rx) < fabs(ry) && fabs(rx) < fabs(rz) && (R[5] > 0) != (ry * rz > 0)) rz = -rz;
+            theta /= sqrt(rx * rx + ry * ry + rz * rz);
+            r[0] = rx * theta;
+            r[1] = ry * theta;
+            r[2] = rz * theta;
+        }
+    } else {
+        double vth = 1 / (2 * s);
+        vth *= theta;
+        r[0] = rx * vth;
+        r[1] = ry * vth;
+        r[2] = rz * vth;
+    }
+}
+
+AB_HD void mat3_inv_transpose(const double* m, double* o) {
+    // o = (m^-1)^T = cofactor(m) / det
+    double c0 = m[4] * m[8] - m[5] * m[7], c1 = m[5] * m[6] - m[3] * m[8], c2 = m[3] * m[7] - m[4] * m[6];
+    double det = m[0] * c0 + m[1] * c1 + m[2] * c2;
+    double id = 1. / det;
+    o[0] = c0 * id;
+    o[1] = c1 * id;
+    o[2] = c2 * id;
+    o[3] = (m[2] * m[7] - m[1] * m[8]) * id;
+    o[4] = (m[0] * m[8] - m[2] * m[6]) * id;
+    o[5] = (m[1] * m[6] - m[0] * m[7]) * id;
+    o[6] = (m[1] * m[5] - m[2] * m[4]) * id;
+    o[7] = (m[2] * m[3] - m[0] * m[5]) * id;
+    o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+}
+
+// nearest rotation (polar factor U*V^T of the SVD) by Newton iteration R <- (R + R^-T)/2
+AB_HD void orthonormalize3(double* R) {
+    for (int it = 0; it < 30; it++) {
+        double T[9], diff = 0;
+        mat3_inv_transpose(R, T);
+        for (int i = 0; i < 9; i++) {
+            double n = 0.5 * (R[i] + T[i]);
+            diff += fabs(n - R[i]);
+            R[i] = n;
+        }
+        if (diff < 1e-15) break;
+    }
+}
+
+AB_HD void project_marker(const Camera& cam, const double* p, const float* obj, double* uv) {
+    double R[9];
+    rodrigues_to_mat(p, R);
+    for (int i = 0; i < 4; i++) {
+        double X = obj[3 * i], Y = obj[3 * i + 1], Z = obj[3 * i + 2];
+        double x = R[0] * X + R[1] * Y + R[2] * Z + p[3];
+        double y = R[3] * X + R[4] * Y + R[5] * Z + p[4];
+        double z = R[6] * X + R[7] * Y + R[8] * Z + p[5];
+        z = z ? 1. / z : 1.;
+        x *= z;
+        y *= z;
+        distort_norm_to_px(cam, x, y, &uv[2 * i], &uv[2 * i + 1]);
+    }
+}
+
+AB_HD bool solve6(double A[6][6], double* b) {
+    for (int i = 0; i < 6; i++) {
+        int k = i;
+        for (int j = i + 1; j < 6; j++)
+            if (fabs(A[j][i]) > fabs(A[k][i])) k = j;
+        if (fabs(A[k][i]) < 1e-300) return false;
+        if (k != i) {
+            for (int j = 0; j < 6; j++) {
+                double t = A[i][j];
+                A[i][j] = A[k][j];
+                A[k][j] = t;
+            }
+            double t = b[i];
+            b[i] = b[k];
+            b[k] = t;
+        }
+        for (int j = i + 1; j < 6; j++) {
+            double f = A[j][i] / A[i][i];
+            for (int c = i; c < 6; c++) A[j][c] -= f * A[i][c];
+            b[j] -= f * b[i];
+        }
+    }
+    for (int i = 5; i >= 0; i--) {
+        double s = b[i];
+        for (int c = i + 1; c < 6; c++) s -= A[i][c] * b[c];
+        b[i] = s / A[i][i];
+    }
+    return true;
+}
+
+// corners: 4 x (u,v) f32 in the reference's order; size = marker side; out rvec/tvec f64.
+AB_HD bool solve_pnp_marker(const Camera& cam, const float* corners, float size, double* rvec, double* tvec) {
+    float h = size / 2.f;  // getObjectPoints, src/marker.cpp:91-108
+    float obj[12] = {-h, -h, 0, -h, h, 0, h, h, 0, h, -h, 0};
+    // 1. normalised image points
+    float nsrc[8], ndst[8];
+    double xn[8];
+    for (int i = 0; i < 4; i++) {
+        undistort_point_norm(cam, corners[2 * i], corners[2 * i + 1], &xn[2 * i], &xn[2 * i + 1]);
+        nsrc[2 * i] = obj[3 * i];
+        nsrc[2 * i + 1] = obj[3 * i + 1];
+    }
+    // 2. exact 4-point homography object plane -> normalised image (f64 system)
+    double a[8][8], b[8];
+    for (int i = 0; i < 4; i++) {
+        double sx = nsrc[2 * i], sy = nsrc[2 * i + 1], dx = xn[2 * i], dy = xn[2 * i + 1];
+        for (int c = 0; c < 8; c++) a[i][c] = a[i + 4][c] = 0;
+        a[i][0] = a[i + 4][3] = sx;
+        a[i][1] = a[i + 4][4] = sy;
+        a[i][2] = a[i + 4][5] = 1;
+        a[i][6] = -sx * dx;
+        a[i][7] = -sy * dx;
+        a[i + 4][6] = -sx * dy;
+        a[i + 4][7] = -sy * dy;
+        b[i] = dx;
+        b[i + 4] = dy;
+    }
+    (void)ndst;
+    if (!lu_solve8(a, b)) return false;
+    double h1[3] = {b[0], b[3], b[6]}, h2[3] = {b[1], b[4], b[7]}, h3[3] = {b[2], b[5], 1.0};
+    double n1 = sqrt(h1[0] * h1[0] + h1[1] * h1[1] + h1[2] * h1[2]);
+    double n2 = sqrt(h2[0] * h2[0] + h2[1] * h2[1] + h2[2] * h2[2]);
+    if (!(n1 > DBL_EPSILON) || !(n2 > DBL_EPSILON)) return false;
+    for (int i = 0; i < 3; i++) {
+        h1[i] /= n1;
+        h2[i] /= n2;
+    }
+    double sc = 2. / (n1 + n2);
+    double p[6];
+    p[3] = h3[0] * sc;
+    p[4] = h3[1] * sc;
+    p[5] = h3[2] * sc;
+    double c3[3] = {h1[1] * h2[2] - h1[2] * h2[1], h1[2] * h2[0] - h1[0] * h2[2], h1[0] * h2[1] - h1[1] * h2[0]};
+    double R[9] = {h1[0], h2[0], c3[0], h1[1], h2[1], c3[1], h1[2], h2[2], c3[2]};
+    orthonormalize3(R);
+    mat_to_rodrigues(R, p);
+    // 3. Levenberg-Marquardt (numeric central-difference Jacobian, run to convergence)
+    double m[8];
+    for (int i = 0; i < 8; i++) m[i] = corners[i];
+    double uv[8], res[8], lambda = 1e-3;
+    project_marker(cam, p, obj, uv);
+    double err = 0;
+    for (int i = 0; i < 8; i++) {
+        res[i] = uv[i] - m[i];
+        err += res[i] * res[i];
+    }
+    for (int it = 0; it < 100; it++) {
+        double J[8][6];
+        for (int k = 0; k < 6; k++) {
+            double hstep = 1e-6 * (fabs(p[k]) > 1. ? fabs(p[k]) : 1.);
+            double pp[6], up[8], um[8];
+            for (int i = 0; i < 6; i++) pp[i] = p[i];
+            pp[k] = p[k] + hstep;
+            project_marker(cam, pp, obj, up);
+            pp[k] = p[k] - hstep;
+            project_marker(cam, pp, obj, um);
+            for (int i = 0; i < 8; i++) J[i][k] = (up[i] - um[i]) / (2 * hstep);
+        }
+        double JtJ[6][6], Jtr[6];
+        for (int i = 0; i < 6; i++) {
+            Jtr[i] = 0;
+            for (int k = 0; k < 8; k++) Jtr[i] += J[k][i] * res[k];
+            for (int j = 0; j < 6; j++) {
+                double s = 0;
+                for (int k = 0; k < 8; k++) s += J[k][i] * J[k][j];
+                JtJ[i][j] = s;
+            }
+        }
+        bool improved = false;
+        double stepn = 0, pn = 0;
+        for (int tries = 0; tries < 30 && !improved; tries++) {
+            double A[6][6], d[6];
+            for (int i = 0; i < 6; i++) {
+                for (int j = 0; j < 6; j++) A[i][j] = JtJ[i][j];
+                A[i][i] += lambda * (JtJ[i][i] > 1e-300 ? JtJ[i][i] : 1e-300);
+                d[i] = -Jtr[i];
+            }
+            if (!solve6(A, d)) {
+                lambda *= 10;
+                continue;
+            }
+            double pp[6], nuv[8], nerr = 0;
+            for (int i = 0; i < 6; i++) pp[i] = p[i] + d[i];
+            project_marker(cam, pp, obj, nuv);
+            for (int i = 0; i < 8; i++) {
+                double e = nuv[i] - m[i];
+                nerr += e * e;
+            }
+            if (nerr <= err) {
+                stepn = 0;
+                pn = 0;
+                for (int i = 0; i < 6; i++) {
+                    stepn += d[i] * d[i];
+                    pn += pp[i] * pp[i];
+                    p[i] = pp[i];
+                }
+                for (int i = 0; i < 8; i++) res[i] = nuv[i] - m[i];
+                err = nerr;
+                lambda = lambda * 0.1 > 1e-12 ? lambda * 0.1 : 1e-12;
+                improved = true;
+            } else {
+                lambda *= 10;
+            }
+        }
+        if (!improved) break;
+        if (stepn <= 1e-26 * (pn > 1e-300 ? pn : 1e-300)) break;
+    }
+    for (int i = 0; i < 3; i++) {
+        rvec[i] = p[i];
+        tvec[i] = p[3 + i];
+    }
+    return true;
+}
+
+// aruco::rotateXAxis (src/utils.cpp:16-30): R(f32) = Rodrigues(rvec) * RX(90 deg) (f32), back to a vector
+AB_HD void rotate_x_axis(double* rvec) {
+    double Rd[9];
+    rodrigues_to_mat(rvec, Rd);
+    float R[9], RX[9] = {1, 0, 0, 0, 0, 0, 0, 0, 0}, O[9];
+    for (int i = 0; i < 9; i++) R[i] = (float)Rd[i];
+    float ang = (float)(3.14159265358979323846 / 2);
+    RX[4] = (float)cos((double)ang);
+    RX[5] = -(float)sin((double)ang);
+    RX[7] = (float)sin((double)ang);
+    RX[8] = (float)cos((double)ang);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            float s = 0;
+            for (int k = 0; k < 3; k++) s += R[i * 3 + k] * RX[k * 3 + j];
+            O[i * 3 + j] = s;
+        }
+    for (int i = 0; i < 9; i++) Rd[i] = O[i];
+    orthonormalize3(Rd);
+    mat_to_rodrigues(Rd, rvec);
+}
+
+}  // namespace ab

@@ -1,0 +1,135 @@
+// Border following as a cycle walk over (pixel, back-direction) states.
+//
+// Replaces cv::findContours(RETR_LIST, CHAIN_APPROX_NONE) at src/markerdetector.cpp:510-511 of the
+// reference.  OpenCV's Suzuki-Abe tracer is a serial raster scan that marks pixels so that every border
+// is started once; here every border is a cycle of a local successor function (the 3x3 neighbourhood
+// decides the next state), and the Suzuki start of a cycle is the trigger with the smallest raster scan
+// position that lies on it.  Only pixels that *can* be such a minimum are start candidates:
+//   outer border: foreground pixel whose W, NW, N, NE neighbours are background
+//                 (the raster-first pixel of an 8-connected component always is one)
+//   hole border:  background pixel h whose W and N neighbours are foreground (the raster-first pixel of a
+//                 4-connected hole always is one); the contour then starts at the pixel left of h.
+// A candidate walks its cycle and gives up as soon as it meets the start state of a candidate with a
+// smaller scan position; the survivor reproduces OpenCV's contour point for point.
+//
+// Directions (image y grows downwards):  0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AB_HD __host__ __device__ __forceinline__
+#else
+#define AB_HD inline
+#endif
+
+namespace ab {
+
+// Binary image packed 1 bit per pixel, LSB first, with one zero word left/right of every row and one zero
+// row above/below, so a 3x3 neighbourhood never needs a bounds test.
+struct BitImage {
+    const uint32_t* bits;  // points at the padded buffer
+    int wpr;               // words per padded row = ceil(W/32) + 2
+    int W, H;
+    AB_HD const uint32_t* row(int y) const { return bits + (size_t)(y + 1) * wpr; }
+};
+
+AB_HD int bit_words_per_row(int W) { return ((W + 31) >> 5) + 2; }
+AB_HD size_t bit_image_words(int W, int H) { return (size_t)bit_words_per_row(W) * (H + 2); }
+
+// bits of pixels x-1, x, x+1 of one padded row (bit0 = x-1)
+AB_HD uint32_t row3(const uint32_t* row, int x) {
+    int p = x + 31;  // pixel x-1 lives at padded bit x-1+32
+    uint32_t lo = row[p >> 5], hi = row[(p >> 5) + 1];
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, p & 31) & 7u;
+#else
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> (p & 31)) & 7u;
+#endif
+}
+
+// 8-neighbour mask of pixel (x,y): bit d set <=> neighbour in direction d is foreground
+AB_HD uint32_t neighbours8(const BitImage& im, int x, int y) {
+    uint32_t t = row3(im.row(y - 1), x), m = row3(im.row(y), x), b = row3(im.row(y + 1), x);
+    return ((m >> 2) & 1u) | (((t >> 2) & 1u) << 1) | (((t >> 1) & 1u) << 2) | ((t & 1u) << 3) | ((m & 1u) << 4) |
+           ((b & 1u) << 5) | (((b >> 1) & 1u) << 6) | (((b >> 2) & 1u) << 7);
+}
+
+AB_HD int dir_dx(int d) { return (d == 0 || d == 1 || d == 7) ? 1 : ((d >= 3 && d <= 5) ? -1 : 0); }
+AB_HD int dir_dy(int d) { return (d >= 1 && d <= 3) ? -1 : ((d >= 5) ? 1 : 0); }
+
+// first foreground neighbour going CLOCKWISE from direction `from` (exclusive), -1 if none
+AB_HD int first_clockwise(uint32_t nb, int from) {
+    for (int k = 1; k <= 8; k++) {
+        int d = (from - k) & 7;
+        if ((nb >> d) & 1u) return d;
+    }
+    return -1;
+}
+
+// successor: first foreground neighbour going COUNTER-CLOCKWISE from back-direction b (exclusive).
+// nb always has bit b set (we came from there), so this terminates.
+AB_HD int next_dir(uint32_t nb, int b) {
+    uint32_t r = ((nb >> (b + 1)) | (nb << (7 - b))) & 0xFFu;  // rotate right by b+1 within 8 bits
+#if defined(__CUDA_ARCH__)
+    int t = __ffs((int)r) - 1;
+#else
+    int t = __builtin_ffs((int)r) - 1;
+#endif
+    return (b + 1 + t) & 7;
+}
+
+AB_HD bool is_outer_candidate(uint32_t nb) { return (nb & 0x1Eu) == 0; }            // NE,N,NW,W all zero
+AB_HD bool is_hole_candidate_east(uint32_t nb) { return (nb & 1u) == 0 && (nb & 2u); }  // E zero, NE set
+
+enum TraceResult { TRACE_NOT_START = 0, TRACE_OK = 1, TRACE_TOO_LONG = 2, TRACE_ISOLATED = 3 };
+
+struct TraceStart {
+    int x, y;      // first contour point
+    int b;         // back-direction of the start state
+    int64_t key;   // raster scan position of the trigger
+};
+
+// Start state of a candidate. type 0: outer border starting at fg pixel (x,y); type 1: hole border whose
+// trigger is the bg pixel (x,y) -- the contour starts at (x-1,y).  Returns false for an isolated pixel.
+AB_HD bool make_start(const BitImage& im, int type, int x, int y, TraceStart& st) {
+    st.key = (int64_t)y * im.W + x;
+    if (type == 0) {
+        st.x = x;
+        st.y = y;
+        st.b = first_clockwise(neighbours8(im, x, y), 4);
+    } else {
+        st.x = x - 1;
+        st.y = y;
+        st.b = first_clockwise(neighbours8(im, x - 1, y), 0);
+    }
+    return st.b >= 0;
+}
+
+// Walks the cycle of `st`.  Returns TRACE_OK with the length in *len when `st` is the Suzuki start of its
+// border and the length is < max_len; TRACE_NOT_START when a smaller trigger lies on the cycle;
+// TRACE_TOO_LONG when max_len points were passed without closing.  When `emit` is non-null the points are
+// written as (x | y<<16).
+AB_HD int trace_cycle(const BitImage& im, const TraceStart& st, int max_len, int* len, uint32_t* emit) {
+    int x = st.x, y = st.y, b = st.b, n = 0;
+    for (;;) {
+        uint32_t nb = neighbours8(im, x, y);
+        if (n > 0) {
+            if (is_outer_candidate(nb) && (int64_t)y * im.W + x < st.key && b == first_clockwise(nb, 4))
+                return TRACE_NOT_START;
+            if (is_hole_candidate_east(nb) && (int64_t)y * im.W + x + 1 < st.key && b == first_clockwise(nb, 0))
+                return TRACE_NOT_START;
+        }
+        if (emit) emit[n] = (uint32_t)x | ((uint32_t)y << 16);
+        n++;
+        int s = next_dir(nb, b);
+        x += dir_dx(s);
+        y += dir_dy(s);
+        b = (s + 4) & 7;
+        if (x == st.x && y == st.y && b == st.b) break;
+        if (n >= max_len) return TRACE_TOO_LONG;
+    }
+    *len = n;
+    return TRACE_OK;
+}
+
+}  // namespace ab

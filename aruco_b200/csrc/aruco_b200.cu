@@ -1,0 +1,947 @@
+// libaruco_b200.so -- context management and the C ABI declared in include/aruco_b200.h.
+// Everything computational happens in the kernels of k_*.cuh on the device; this file only sizes buffers,
+// moves frames/results and launches.  There is deliberately no host implementation of any stage.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "ab_device.cuh"
+#include "k_threshold.cuh"
+#include "k_contours.cuh"
+#include "k_polygon.cuh"
+#include "k_decode.cuh"
+#include "k_refine.cuh"
+#include "k_finalize.cuh"
+
+using namespace ab;
+
+#define AB_VERSION "aruco_b200 0.1 (sm_100a)"
+
+struct ab_context {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    cudaStream_t copy_stream = nullptr;
+    ab_params params;
+    std::string err;
+    // reserved geometry
+    int W = 0, H = 0, maxB = 0, capQ = 0, capC = 0, S_alloc = 0;
+    long long capStartsPF = 0, capPoolPF = 0;
+    unsigned capContoursPF = 16384;
+    // device buffers
+    uint8_t* d_grey[2] = {nullptr, nullptr};
+    size_t grey_bytes = 0;
+    uint8_t* d_bgr = nullptr;
+    size_t bgr_bytes = 0;
+    uint8_t* d_thres = nullptr;
+    uint32_t *d_bits = nullptr, *d_bits2 = nullptr;
+    uint2* d_starts = nullptr;
+    ContourRec* d_contours = nullptr;
+    uint32_t* d_pool = nullptr;
+    QuadRec* d_quads = nullptr;
+    CandRec* d_cands = nullptr;
+    uint8_t* d_canon = nullptr;
+    ab_marker* d_markers = nullptr;
+    uint8_t* d_counters = nullptr;  // Counters + 3*maxB uints
+    size_t counters_bytes = 0;
+    // HRM dictionary
+    uint64_t* d_dict_bits = nullptr;
+    uint32_t* d_dict_ordids = nullptr;
+    int32_t* d_dict_ordpos = nullptr;
+    int32_t* d_dict_tree = nullptr;
+    HrmDict dict{};
+    bool have_dict = false;
+    // host callback decoder
+    ab_decoder_fn cb = nullptr;
+    void* cb_user = nullptr;
+    // pinned host staging
+    ab_marker* h_markers = nullptr;
+    size_t h_markers_bytes = 0;
+    uint8_t* h_counters = nullptr;
+    // last batch
+    Batch last{};
+    bool have_last = false;
+    int last_n = 0;
+    // timing
+    bool timing = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+};
+
+static int set_err(ab_context* c, int code, const char* fmt, ...) {
+    if (c) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return set_err(ctx, AB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+static void free_buffers(ab_context* c) {
+    auto F = [](auto*& p) {
+        if (p) cudaFree(p);
+        p = nullptr;
+    };
+    F(c->d_grey[0]);
+    F(c->d_grey[1]);
+    F(c->d_bgr);
+    F(c->d_thres);
+    F(c->d_bits);
+    F(c->d_bits2);
+    F(c->d_starts);
+    F(c->d_contours);
+    F(c->d_pool);
+    F(c->d_quads);
+    F(c->d_cands);
+    F(c->d_canon);
+    F(c->d_markers);
+    F(c->d_counters);
+    if (c->h_markers) cudaFreeHost(c->h_markers);
+    c->h_markers = nullptr;
+    c->h_markers_bytes = 0;
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    c->h_counters = nullptr;
+    c->grey_bytes = c->bgr_bytes = 0;
+    c->W = c->H = c->maxB = 0;
+    c->have_last = false;
+}
+
+extern "C" {
+
+const char* ab_version(void) { return AB_VERSION; }
+
+const char* ab_last_error(const ab_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int ab_default_params(ab_params* p) {
+    if (!p) return AB_E_INVALID;
+    memset(p, 0, sizeof(*p));
+    p->thres_method = AB_THRES_ADAPTIVE;
+    p->thres_param1 = 7;
+    p->thres_param2 = 7;
+    p->corner_method = AB_CORNER_LINES;
+    p->min_size = 0.04f;
+    p->max_size = 0.5f;
+    p->warp_size = 56;
+    p->border_dist = 0.025f;
+    p->locked_corners = 0;
+    p->erosion = 0;
+    p->decoder = AB_DECODER_FIDUCIDAL;
+    p->set_y_perpendicular = 0;
+    return AB_OK;
+}
+
+int ab_create(int device, ab_context** out) {
+    if (!out) return AB_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return AB_E_NO_DEVICE;
+    ab_context* ctx = new ab_context();
+    ctx->device = device;
+    ab_default_params(&ctx->params);
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete ctx;
+        return AB_E_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return AB_E_CUDA;
+    }
+    for (int i = 0; i < 6; i++) cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
+    }
+    *out = ctx;
+    return AB_OK;
+}
+
+void ab_destroy(ab_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    free_buffers(ctx);
+    auto F = [](auto*& p) {
+        if (p) cudaFree(p);
+        p = nullptr;
+    };
+    F(ctx->d_dict_bits);
+    F(ctx->d_dict_ordids);
+    F(ctx->d_dict_ordpos);
+    F(ctx->d_dict_tree);
+    for (int i = 0; i < 6; i++)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    }
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+int ab_set_params(ab_context* ctx, const ab_params* p) {
+    if (!ctx || !p) return AB_E_INVALID;
+    // the reference's CV_Asserts: setMinMaxSize (cpp:1031-1038), setWarpSize (cpp:1047-1051)
+    if (!(p->min_size > 0 && p->min_size <= 1) || !(p->max_size > 0 && p->max_size <= 1) || !(p->min_size < p->max_size))
+        return set_err(ctx, AB_E_INVALID, "setMinMaxSize: need 0 < min < max <= 1");
+    if (p->warp_size < 10 || p->warp_size > MAX_WARP_SIZE)
+        return set_err(ctx, AB_E_INVALID, "setWarpSize: need 10 <= size <= %d", MAX_WARP_SIZE);
+    if (p->thres_method < 0 || p->thres_method > 2) return set_err(ctx, AB_E_INVALID, "bad threshold method");
+    if (p->corner_method < 0 || p->corner_method > 3) return set_err(ctx, AB_E_INVALID, "bad corner refinement method");
+    if (p->decoder < 0 || p->decoder > 2) return set_err(ctx, AB_E_INVALID, "bad decoder kind");
+    ctx->params = *p;
+    return AB_OK;
+}
+
+int ab_get_params(const ab_context* ctx, ab_params* p) {
+    if (!ctx || !p) return AB_E_INVALID;
+    *p = ctx->params;
+    return AB_OK;
+}
+
+int ab_set_stream(ab_context* ctx, void* s) {
+    if (!ctx) return AB_E_INVALID;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream && ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    if (s == nullptr) {
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    } else {
+        ctx->stream = (cudaStream_t)s;
+        ctx->own_stream = false;
+    }
+    return AB_OK;
+}
+
+int ab_set_decoder_callback(ab_context* ctx, ab_decoder_fn fn, void* user) {
+    if (!ctx) return AB_E_INVALID;
+    ctx->cb = fn;
+    ctx->cb_user = user;
+    return AB_OK;
+}
+
+int ab_enable_timing(ab_context* ctx, int enable) {
+    if (!ctx) return AB_E_INVALID;
+    ctx->timing = enable != 0;
+    return AB_OK;
+}
+
+int ab_load_hrm_dictionary(ab_context* ctx, int n, int count, const uint8_t* bits, int tau0, float rate) {
+    if (!ctx || !bits || n < 1 || n > 8 || count < 1 || count > 16383) return set_err(ctx, AB_E_INVALID, "bad dictionary");
+    cudaSetDevice(ctx->device);
+    std::vector<uint64_t> b0(count);
+    std::vector<uint32_t> id0(count);
+    for (int i = 0; i < count; i++) {
+        uint64_t rb[4];
+        uint32_t ids[4];
+        hrm_rotations(bits + (size_t)i * n * n, n, rb, ids);
+        b0[i] = rb[0];
+        id0[i] = ids[0];
+    }
+    // BalancedBinaryTree::loadDictionary (highlyreliablemarkers.cpp:387-476): the search structure is data,
+    // built once on the host; the lookups run on the device (k_decode.cuh hrm_decode).
+    std::vector<std::pair<uint32_t, uint32_t>> order(count);
+    for (int i = 0; i < count; i++) order[i] = {id0[i], (uint32_t)i};
+    std::sort(order.begin(), order.end());
+    unsigned sz = (unsigned)count, levels = 0;
+    while (powf(2.f, (float)levels) <= (float)sz) levels++;
+    std::vector<char> visited(sz, 0);
+    unsigned root = sz / 2;
+    visited[root] = 1;
+    std::vector<std::pair<unsigned, unsigned>> intervals;
+    intervals.push_back({0u, root});
+    intervals.push_back({root, sz});
+    std::vector<int32_t> tree(2 * (size_t)sz, 0);
+    tree[2 * root] = !visited[(0 + root) / 2] ? (int)((0 + root) / 2) : -1;
+    tree[2 * root + 1] = !visited[(root + sz) / 2] ? (int)((root + sz) / 2) : -1;
+    for (unsigned lv = 1; lv < levels; lv++) {
+        size_t nint = intervals.size();
+        for (size_t j = 0; j < nint; j++) {
+            unsigned lo = intervals.back().first, hi = intervals.back().second;
+            intervals.pop_back();
+            unsigned center = (hi + lo) / 2;
+            if (!visited[center]) visited[center] = 1;
+            else continue;
+            unsigned lc = (lo + center) / 2, hc = (center + hi) / 2;
+            if (!visited[lc]) {
+                intervals.insert(intervals.begin(), {lo, center});
+                tree[2 * center] = (int)lc;
+            } else tree[2 * center] = -1;
+            if (!visited[hc]) {
+                intervals.insert(intervals.begin(), {center, hi});
+                tree[2 * center + 1] = (int)hc;
+            } else tree[2 * center + 1] = -1;
+        }
+    }
+    std::vector<uint32_t> ordids(count);
+    std::vector<int32_t> ordpos(count);
+    for (int i = 0; i < count; i++) {
+        ordids[i] = order[i].first;
+        ordpos[i] = (int32_t)order[i].second;
+    }
+    auto F = [](auto*& p) {
+        if (p) cudaFree(p);
+        p = nullptr;
+    };
+    F(ctx->d_dict_bits);
+    F(ctx->d_dict_ordids);
+    F(ctx->d_dict_ordpos);
+    F(ctx->d_dict_tree);
+    CK(cudaMalloc(&ctx->d_dict_bits, sizeof(uint64_t) * count));
+    CK(cudaMalloc(&ctx->d_dict_ordids, sizeof(uint32_t) * count));
+    CK(cudaMalloc(&ctx->d_dict_ordpos, sizeof(int32_t) * count));
+    CK(cudaMalloc(&ctx->d_dict_tree, sizeof(int32_t) * 2 * count));
+    CK(cudaMemcpy(ctx->d_dict_bits, b0.data(), sizeof(uint64_t) * count, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_dict_ordids, ordids.data(), sizeof(uint32_t) * count, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_dict_ordpos, ordpos.data(), sizeof(int32_t) * count, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_dict_tree, tree.data(), sizeof(int32_t) * 2 * count, cudaMemcpyHostToDevice));
+    ctx->dict.bits = ctx->d_dict_bits;
+    ctx->dict.ids = nullptr;
+    ctx->dict.ord_ids = ctx->d_dict_ordids;
+    ctx->dict.ord_pos = ctx->d_dict_ordpos;
+    ctx->dict.tree = ctx->d_dict_tree;
+    ctx->dict.root = (int)root;
+    ctx->dict.count = count;
+    ctx->dict.n = n;
+    ctx->dict.correction = (int)(rate * (float)((tau0 - 1) / 2));  // highlyreliablemarkers.cpp:318
+    ctx->have_dict = true;
+    return AB_OK;
+}
+
+int ab_reserve(ab_context* ctx, int width, int height, int max_batch, int max_quads, int max_cands,
+               int64_t max_starts_pf, int64_t max_points_pf) {
+    if (!ctx || width < 8 || height < 8 || width > 16384 || height > 16384 || max_batch < 1)
+        return set_err(ctx, AB_E_INVALID, "ab_reserve: bad geometry %dx%d x%d", width, height, max_batch);
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    free_buffers(ctx);
+    int capQ = max_quads > 0 ? std::min(max_quads, MAX_QUADS) : MAX_QUADS;
+    int capC = max_cands > 0 ? std::min(max_cands, MAX_CANDS) : 256;
+    long long px = (long long)width * height;
+    long long capS = max_starts_pf > 0 ? max_starts_pf : std::max(px / 8, 65536LL);
+    long long capP = max_points_pf > 0 ? max_points_pf : std::max(px / 4, 65536LL);
+    if (capP * max_batch > 0xFFFFFFF0LL) capP = 0xFFFFFFF0LL / max_batch;
+    ctx->W = width;
+    ctx->H = height;
+    ctx->maxB = max_batch;
+    ctx->capQ = capQ;
+    ctx->capC = capC;
+    ctx->capStartsPF = capS;
+    ctx->capPoolPF = capP;
+    ctx->S_alloc = std::max(ctx->params.warp_size, 56);
+    size_t B = (size_t)max_batch;
+    size_t bw = bit_image_words(width, height);
+    CK(cudaMalloc(&ctx->d_thres, B * px));
+    CK(cudaMalloc(&ctx->d_bits, B * bw * 4));
+    CK(cudaMalloc(&ctx->d_bits2, B * bw * 4));
+    CK(cudaMemset(ctx->d_bits, 0, B * bw * 4));
+    CK(cudaMemset(ctx->d_bits2, 0, B * bw * 4));
+    CK(cudaMalloc(&ctx->d_starts, B * capS * sizeof(uint2)));
+    CK(cudaMalloc(&ctx->d_contours, B * ctx->capContoursPF * sizeof(ContourRec)));
+    CK(cudaMalloc(&ctx->d_pool, B * capP * 4));
+    CK(cudaMalloc(&ctx->d_quads, B * capQ * sizeof(QuadRec)));
+    CK(cudaMalloc(&ctx->d_cands, B * capC * sizeof(CandRec)));
+    CK(cudaMalloc(&ctx->d_canon, B * capC * (size_t)ctx->S_alloc * ctx->S_alloc));
+    CK(cudaMalloc(&ctx->d_markers, B * capC * sizeof(ab_marker)));
+    ctx->counters_bytes = sizeof(Counters) + 3 * B * sizeof(unsigned);
+    CK(cudaMalloc(&ctx->d_counters, ctx->counters_bytes));
+    CK(cudaMallocHost(&ctx->h_counters, ctx->counters_bytes));
+    return AB_OK;
+}
+
+static int ensure_reserved(ab_context* ctx, int W, int H, int nB) {
+    if (ctx->W == W && ctx->H == H && ctx->maxB >= nB && ctx->S_alloc >= ctx->params.warp_size) return AB_OK;
+    int B = (ctx->W == W && ctx->H == H) ? std::max(ctx->maxB, nB) : nB;
+    return ab_reserve(ctx, W, H, B, ctx->capQ, ctx->capC, 0, 0);
+}
+
+static Camera make_camera(const float* K, const float* D) {
+    Camera c;
+    memset(&c, 0, sizeof(c));
+    if (K) {
+        c.has_K = 1;
+        c.fxf = K[0];
+        c.cxf = K[2];
+        c.fyf = K[4];
+        c.cyf = K[5];
+        c.fx = K[0];
+        c.cx = K[2];
+        c.fy = K[4];
+        c.cy = K[5];
+    }
+    if (D) {
+        c.has_D = 1;
+        c.k1 = D[0];
+        c.k2 = D[1];
+        c.p1 = D[2];
+        c.p2 = D[3];
+        c.k3 = D[4];
+    }
+    return c;
+}
+
+static int launch_threshold(ab_context* ctx, const Batch& b, int method, double p1, double p2) {
+    cudaStream_t st = ctx->stream;
+    if (method == AB_THRES_ADAPTIVE) {
+        // thresHold: ensure an odd block size >= 3 (src/markerdetector.cpp:657-660)
+        if (p1 < 3) p1 = 3;
+        else if (((int)p1) % 2 != 1) p1 = (int)(p1 + 1);
+        int k = (int)p1;
+        if (k > 63) return set_err(ctx, AB_E_INVALID, "adaptive threshold block size %d > 63 not supported", k);
+        double fl = floor(p2);
+        int idelta = (int)std::max(-300.0, std::min(300.0, fl));
+        ThrArgs a;
+        a.grey = b.grey;
+        a.grey_row = b.grey_row;
+        a.grey_frame = b.grey_frame;
+        a.thres = b.thres;
+        a.bits = b.bits;
+        a.bits_words = b.bits_words;
+        a.W = b.W;
+        a.H = b.H;
+        a.wpr = b.wpr;
+        a.k = k;
+        a.idelta = idelta;
+        a.TWo = 480;
+        a.RH = k <= 9 ? 64 : 128;
+        int r = k / 2;
+        a.R4 = (r + 3) & ~3;
+        a.aligned4 = ((((uintptr_t)b.grey) | b.grey_row | b.grey_frame) & 3) == 0;
+        int nth = (a.TWo + 2 * a.R4) / 4;
+        nth = (nth + 31) & ~31;
+        size_t SPAN = 4 * (size_t)nth;
+        size_t smem = (((size_t)k * SPAN + 15) & ~(size_t)15) + 4 * SPAN + nth;
+        dim3 grid((b.W + a.TWo - 1) / a.TWo, (b.H + a.RH - 1) / a.RH, b.B);
+        k_threshold_adaptive<<<grid, nth, smem, st>>>(a);
+    } else if (method == AB_THRES_FIXED) {
+        int thr = (int)floor(p1);
+        k_threshold_fixed<<<ctx->sm_count * 8, 256, 0, st>>>(b.grey, b.grey_row, b.grey_frame, b.thres, b.bits, b.bits_words,
+                                                              b.W, b.H, b.wpr, thr, 0, b.B);
+    } else {
+        return set_err(ctx, AB_E_INVALID, "ThresholdMethods::CANNY is not implemented on the device path");
+    }
+    CK(cudaGetLastError());
+    return AB_OK;
+}
+
+__global__ void k_set_ids(Batch b, const int2* idrot) {
+    int f = blockIdx.y, ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= (int)b.n_cands[f]) return;
+    int2 v = idrot[(size_t)f * b.cap_c + ci];
+    b.cands[(size_t)f * b.cap_c + ci].id = v.x;
+    b.cands[(size_t)f * b.cap_c + ci].nrot = v.y;
+}
+
+// cvtColor(BGR2GRAY) of OpenCV 4.x: (3735 B + 19235 G + 9798 R + 16384) >> 15   
+__global__ void k_bgr2grey(const uint8_t* bgr, size_t row, size_t frame, uint8_t* grey, int W, int H, int B) {
+    size_t total = (size_t)W * H * B;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int x = (int)(i % W);
+        int y = (int)((i / W) % H);
+        int f = (int)(i / ((size_t)W * H));
+        const uint8_t* p = bgr + (size_t)f * frame + (size_t)y * row + 3 * (size_t)x;
+        grey[i] = (uint8_t)((3735 * p[0] + 19235 * p[1] + 9798 * p[2] + 16384) >> 15);
+    }
+}
+
+static int fill_batch(ab_context* ctx, Batch& b, const uint8_t* dgrey, size_t row, size_t frame, int n, const float* K,
+                      const float* D, float marker_size) {
+    const ab_params& P = ctx->params;
+    memset(&b, 0, sizeof(b));
+    b.W = ctx->W;
+    b.H = ctx->H;
+    b.B = n;
+    b.wpr = bit_words_per_row(ctx->W);
+    b.bits_words = bit_image_words(ctx->W, ctx->H);
+    b.grey = dgrey;
+    b.grey_row = row;
+    b.grey_frame = frame;
+    b.thres = ctx->d_thres;
+    b.bits = ctx->d_bits;
+    b.bits2 = ctx->d_bits2;
+    b.starts = ctx->d_starts;
+    b.cap_starts = (unsigned long long)ctx->capStartsPF * n;
+    b.contours = ctx->d_contours;
+    b.cap_contours = ctx->capContoursPF * (unsigned)n;
+    b.pool = ctx->d_pool;
+    b.cap_pool = (unsigned long long)ctx->capPoolPF * n;
+    b.quads = ctx->d_quads;
+    b.cap_q = ctx->capQ;
+    b.cands = ctx->d_cands;
+    b.cap_c = ctx->capC;
+    b.canon = ctx->d_canon;
+    b.markers = ctx->d_markers;
+    b.cnt = (Counters*)ctx->d_counters;
+    b.n_quads = (unsigned*)(ctx->d_counters + sizeof(Counters));
+    b.n_cands = b.n_quads + ctx->maxB;
+    b.n_markers = b.n_cands + ctx->maxB;
+    // contour length limits (src/markerdetector.cpp:500-501): f32 product truncated to int
+    int mx = std::max(ctx->W, ctx->H);
+    b.min_len = (int)(P.min_size * (float)mx * 4.f);
+    b.max_len = (int)(P.max_size * (float)mx * 4.f);
+    b.S = P.warp_size;
+    b.decoder = P.decoder;
+    b.corner_method = P.corner_method;
+    b.subpix_win = (int)P.thres_param1;
+    b.locked = P.locked_corners;
+    b.set_y_perp = P.set_y_perpendicular;
+    // valid region (src/markerdetector.cpp:433-434): Point*float rounds half-to-even
+    float bd = P.border_dist, ob = 1.0f - bd;
+    int x0 = (int)lrintf((float)ctx->W * bd), y0 = (int)lrintf((float)ctx->H * bd);
+    int x1 = (int)lrintf((float)ctx->W * ob), y1 = (int)lrintf((float)ctx->H * ob);
+    b.vx0 = std::min(x0, x1);
+    b.vy0 = std::min(y0, y1);
+    b.vx1 = std::max(x0, x1);
+    b.vy1 = std::max(y0, y1);
+    b.marker_size = marker_size;
+    b.cam = make_camera(K, D);
+    b.dict = ctx->dict;
+    return AB_OK;
+}
+
+// launches the whole path for frames resident at `dgrey`
+static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t frame, int n, const float* K,
+                     const float* D, float marker_size) {
+    const ab_params& P = ctx->params;
+    if (P.decoder == AB_DECODER_HRM && !ctx->have_dict)
+        return set_err(ctx, AB_E_STATE, "HRM decoder selected but no dictionary loaded (ab_load_hrm_dictionary)");
+    if (P.decoder == AB_DECODER_HOST_CALLBACK && !ctx->cb)
+        return set_err(ctx, AB_E_STATE, "host-callback decoder selected but no callback set");
+    if (P.decoder == AB_DECODER_HRM && (ctx->dict.n + 2) > P.warp_size)
+        return set_err(ctx, AB_E_INVALID, "warp size too small for the dictionary");
+    if (P.corner_method == AB_CORNER_SUBPIX && ((int)P.thres_param1 < 1 || (int)P.thres_param1 > 24))
+        return set_err(ctx, AB_E_INVALID, "SUBPIX window %d outside 1..24", (int)P.thres_param1);
+    if (P.corner_method == AB_CORNER_HARRIS || P.locked_corners)
+        return set_err(ctx, AB_E_INVALID, "HARRIS refinement / locked corners are not implemented yet");
+    Batch b;
+    fill_batch(ctx, b, dgrey, row, frame, n, K, D, marker_size);
+    cudaStream_t st = ctx->stream;
+    const int sms = ctx->sm_count;
+    if (ctx->timing) cudaEventRecord(ctx->ev[0], st);
+    CK(cudaMemsetAsync(ctx->d_counters, 0, ctx->counters_bytes, st));
+    int rc = launch_threshold(ctx, b, P.thres_method, P.thres_param1, P.thres_param2);
+    if (rc) return rc;
+    if (P.erosion) {
+        k_erode<<<sms * 8, 256, 0, st>>>(b.bits, b.bits2, b.thres, b.bits_words, b.W, b.H, b.wpr, b.B);
+        std::swap(b.bits, b.bits2);
+    }
+    if (ctx->timing) cudaEventRecord(ctx->ev[1], st);
+    k_scan_starts<<<sms * 8, 256, 0, st>>>(b);
+    k_trace<<<sms * 8, 128, 0, st>>>(b);
+    k_polygon<<<sms * 4, 128, 0, st>>>(b);
+    k_frame_filter<<<n, 256, 0, st>>>(b);
+    CK(cudaGetLastError());
+    if (ctx->timing) cudaEventRecord(ctx->ev[2], st);
+    dim3 gcand(b.cap_c, n);
+    if (P.decoder == AB_DECODER_HOST_CALLBACK) {
+        k_decode<<<gcand, 128, 0, st>>>(b, 1);
+        CK(cudaGetLastError());
+        // MarkerdetectorFunc plugin hook (markerdetector.h:78,243): canonical images go to the host, the
+        // user function runs per candidate in the reference's order, ids/rotations come back.
+        std::vector<unsigned> ncand(n);
+        CK(cudaMemcpyAsync(ncand.data(), b.n_cands, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        size_t ss = (size_t)b.S * b.S;
+        std::vector<uint8_t> canon((size_t)n * b.cap_c * ss);
+        CK(cudaMemcpyAsync(canon.data(), b.canon, canon.size(), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        std::vector<int2> idrot((size_t)n * b.cap_c, make_int2(-1, 0));
+        for (int f = 0; f < n; f++)
+            for (unsigned c = 0; c < std::min<unsigned>(ncand[f], b.cap_c); c++) {
+                int nrot = 0;
+                int id = ctx->cb(canon.data() + ((size_t)f * b.cap_c + c) * ss, b.S, &nrot, ctx->cb_user);
+                idrot[(size_t)f * b.cap_c + c] = make_int2(id, nrot);
+            }
+        int2* d_idrot = nullptr;
+        CK(cudaMalloc(&d_idrot, idrot.size() * sizeof(int2)));
+        CK(cudaMemcpyAsync(d_idrot, idrot.data(), idrot.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+        k_set_ids<<<dim3((b.cap_c + 127) / 128, n), 128, 0, st>>>(b, d_idrot);
+        CK(cudaStreamSynchronize(st));
+        cudaFree(d_idrot);
+    } else {
+        k_decode<<<gcand, 128, 0, st>>>(b, 0);
+        CK(cudaGetLastError());
+    }
+    if (ctx->timing) cudaEventRecord(ctx->ev[3], st);
+    if (P.corner_method == AB_CORNER_LINES) {
+        k_refine_lines<<<gcand, 128, 0, st>>>(b);
+    } else if (P.corner_method == AB_CORNER_SUBPIX) {
+        int w = b.subpix_win, pw = 2 * w + 3;
+        size_t smem = (size_t)4 * pw * pw * sizeof(float);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_refine_subpix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_refine_subpix<<<dim3(b.cap_c, n), 128, smem, st>>>(b);
+    }
+    CK(cudaGetLastError());
+    if (ctx->timing) cudaEventRecord(ctx->ev[4], st);
+    k_finalize<<<n, 128, 0, st>>>(b);
+    CK(cudaGetLastError());
+    if (ctx->timing) cudaEventRecord(ctx->ev[5], st);
+    ctx->last = b;
+    ctx->have_last = true;
+    ctx->last_n = n;
+    return AB_OK;
+}
+
+static int check_device_errors(ab_context* ctx, const Counters* c) {
+    if (!c->err) return AB_OK;
+    std::string what;
+    if (c->err & ERR_STARTS_OVERFLOW) what += " start-candidates(max_start_candidates_per_frame)";
+    if (c->err & ERR_CONTOURS_OVERFLOW) what += " contours";
+    if (c->err & ERR_POOL_OVERFLOW) what += " contour-points(max_contour_points_per_frame)";
+    if (c->err & ERR_QUADS_OVERFLOW) what += " quads(max_quads_per_frame)";
+    if (c->err & ERR_CANDS_OVERFLOW) what += " candidates(max_candidates_per_frame)";
+    return set_err(ctx, AB_E_CAPACITY, "device buffer overflow:%s -- results are incomplete; call ab_reserve with larger capacities",
+                   what.c_str());
+}
+
+int ab_enqueue_batch_device(ab_context* ctx, const uint8_t* dev_frames, int width, int height, size_t row_stride,
+                            size_t frame_stride, int n_frames, const float* K, const float* D, float marker_size) {
+    if (!ctx || !dev_frames || n_frames < 1 || row_stride < (size_t)width) return set_err(ctx, AB_E_INVALID, "bad arguments");
+    cudaSetDevice(ctx->device);
+    int rc = ensure_reserved(ctx, width, height, n_frames);
+    if (rc) return rc;
+    return run_batch(ctx, dev_frames, row_stride, frame_stride, n_frames, K, D, marker_size);
+}
+
+static int fetch_into(ab_context* ctx, ab_marker* out, int cap, int32_t* counts) {
+    if (!ctx->have_last) return set_err(ctx, AB_E_STATE, "no batch has been run");
+    const Batch& b = ctx->last;
+    int n = ctx->last_n;
+    cudaStream_t st = ctx->stream;
+    int ncopy = std::min(cap, b.cap_c);
+    size_t need = (size_t)n * ncopy * sizeof(ab_marker);
+    if (need > ctx->h_markers_bytes) {
+        if (ctx->h_markers) cudaFreeHost(ctx->h_markers);
+        ctx->h_markers = nullptr;
+        CK(cudaMallocHost(&ctx->h_markers, need));
+        ctx->h_markers_bytes = need;
+    }
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, ctx->counters_bytes, cudaMemcpyDeviceToHost, st));
+    if (out && ncopy > 0)
+        CK(cudaMemcpy2DAsync(ctx->h_markers, (size_t)ncopy * sizeof(ab_marker), b.markers, (size_t)b.cap_c * sizeof(ab_marker),
+                             (size_t)ncopy * sizeof(ab_marker), n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const Counters* c = (const Counters*)ctx->h_counters;
+    int rc = check_device_errors(ctx, c);
+    if (rc) return rc;
+    const unsigned* nm = (const unsigned*)(ctx->h_counters + sizeof(Counters)) + 2 * (size_t)ctx->maxB;
+    for (int f = 0; f < n; f++) {
+        if ((int)nm[f] > cap && out)
+            return set_err(ctx, AB_E_CAPACITY, "frame %d has %u markers but cap_per_frame is %d", f, nm[f], cap);
+        if (counts) counts[f] = (int32_t)nm[f];
+        if (out) memcpy(out + (size_t)f * cap, ctx->h_markers + (size_t)f * ncopy, sizeof(ab_marker) * std::min<int>(nm[f], ncopy));
+    }
+    return AB_OK;
+}
+
+int ab_fetch_results(ab_context* ctx, ab_marker* out, int cap_per_frame, int32_t* counts) {
+    if (!ctx || cap_per_frame < 0) return AB_E_INVALID;
+    cudaSetDevice(ctx->device);
+    return fetch_into(ctx, out, cap_per_frame, counts);
+}
+
+static int ensure_grey(ab_context* ctx, size_t bytes) {
+    if (ctx->grey_bytes >= bytes) return AB_OK;
+    for (int i = 0; i < 2; i++) {
+        if (ctx->d_grey[i]) cudaFree(ctx->d_grey[i]);
+        ctx->d_grey[i] = nullptr;
+        CK(cudaMalloc(&ctx->d_grey[i], bytes));
+    }
+    ctx->grey_bytes = bytes;
+    return AB_OK;
+}
+
+static int detect_host(ab_context* ctx, const uint8_t* frames, int width, int height, size_t row_stride, size_t frame_stride,
+                       int n_frames, const float* K, const float* D, float marker_size, ab_marker* out, int cap, int32_t* counts,
+                       int channels) {
+    if (!ctx || !frames || n_frames < 1 || row_stride < (size_t)width * channels || cap < 0)
+        return set_err(ctx, AB_E_INVALID, "bad arguments");
+    cudaSetDevice(ctx->device);
+    // chunk size: what was reserved for this geometry, else up to 32 frames
+    int chunk = (ctx->W == width && ctx->H == height && ctx->maxB > 0) ? std::min(ctx->maxB, n_frames) : std::min(n_frames, 32);
+    int rc = ensure_reserved(ctx, width, height, chunk);
+    if (rc) return rc;
+    chunk = std::min(ctx->maxB, n_frames);
+    size_t fpx = (size_t)width * height;
+    rc = ensure_grey(ctx, fpx * chunk);
+    if (rc) return rc;
+    if (channels == 3 && ctx->bgr_bytes < fpx * 3 * chunk) {
+        if (ctx->d_bgr) cudaFree(ctx->d_bgr);
+        ctx->d_bgr = nullptr;
+        CK(cudaMalloc(&ctx->d_bgr, fpx * 3 * chunk));
+        ctx->bgr_bytes = fpx * 3 * chunk;
+    }
+    int nchunks = (n_frames + chunk - 1) / chunk;
+    // H2D of chunk c+1 (copy stream) overlaps the kernels of chunk c (compute stream); results of chunk c
+    // are fetched before chunk c+1 is launched, so every intermediate buffer is single-buffered.
+    auto upload = [&](int c) -> int {
+        int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
+        int buf = c & 1;
+        if (c >= 2) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[buf], 0));
+        if (channels == 1) {
+            if (frame_stride == row_stride * (size_t)height) {
+                CK(cudaMemcpy2DAsync(ctx->d_grey[buf], width, frames + (size_t)f0 * frame_stride, row_stride, width,
+                                     (size_t)height * nf, cudaMemcpyHostToDevice, ctx->copy_stream));
+            } else {
+                for (int f = 0; f < nf; f++)
+                    CK(cudaMemcpy2DAsync(ctx->d_grey[buf] + (size_t)f * fpx, width, frames + (size_t)(f0 + f) * frame_stride,
+                                         row_stride, width, height, cudaMemcpyHostToDevice, ctx->copy_stream));
+            }
+        } else {
+            for (int f = 0; f < nf; f++)
+                CK(cudaMemcpy2DAsync(ctx->d_bgr + (size_t)f * fpx * 3, (size_t)width * 3, frames + (size_t)(f0 + f) * frame_stride,
+                                     row_stride, (size_t)width * 3, height, cudaMemcpyHostToDevice, ctx->copy_stream));
+            k_bgr2grey<<<ctx->sm_count * 8, 256, 0, ctx->copy_stream>>>(ctx->d_bgr, (size_t)width * 3, fpx * 3, ctx->d_grey[buf],
+                                                                       width, height, nf);
+        }
+        CK(cudaEventRecord(ctx->ev_h2d[buf], ctx->copy_stream));
+        return AB_OK;
+    };
+    rc = upload(0);
+    if (rc) return rc;
+    for (int c = 0; c < nchunks; c++) {
+        int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
+        int buf = c & 1;
+        if (c + 1 < nchunks && channels == 1) {
+            rc = upload(c + 1);
+            if (rc) return rc;
+        }
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[buf], 0));
+        rc = run_batch(ctx, ctx->d_grey[buf], width, fpx, nf, K, D, marker_size);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_done[buf], ctx->stream));
+        rc = fetch_into(ctx, out ? out + (size_t)f0 * cap : nullptr, cap, counts ? counts + f0 : nullptr);
+        if (rc) return rc;
+        if (c + 1 < nchunks && channels == 3) {  // the BGR staging buffer is single: upload after the fetch
+            rc = upload(c + 1);
+            if (rc) return rc;
+        }
+    }
+    return AB_OK;
+}
+
+int ab_detect_batch(ab_context* ctx, const uint8_t* frames, int width, int height, size_t row_stride, size_t frame_stride,
+                    int n_frames, const float* K, const float* D, float marker_size, ab_marker* out, int cap_per_frame,
+                    int32_t* counts) {
+    return detect_host(ctx, frames, width, height, row_stride, frame_stride, n_frames, K, D, marker_size, out, cap_per_frame,
+                       counts, 1);
+}
+
+int ab_detect_batch_bgr(ab_context* ctx, const uint8_t* frames, int width, int height, size_t row_stride, size_t frame_stride,
+                        int n_frames, const float* K, const float* D, float marker_size, ab_marker* out, int cap_per_frame,
+                        int32_t* counts) {
+    return detect_host(ctx, frames, width, height, row_stride, frame_stride, n_frames, K, D, marker_size, out, cap_per_frame,
+                       counts, 3);
+}
+
+// ---- state of the last batch ---------------------------------------------------------------------------
+int ab_get_thresholded(ab_context* ctx, int frame, uint8_t* dst, size_t dst_stride) {
+    if (!ctx || !ctx->have_last || frame < 0 || frame >= ctx->last_n || !dst) return set_err(ctx, AB_E_INVALID, "bad frame");
+    cudaSetDevice(ctx->device);
+    const Batch& b = ctx->last;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy2D(dst, dst_stride, b.thres + (size_t)frame * b.W * b.H, b.W, b.W, b.H, cudaMemcpyDeviceToHost));
+    return AB_OK;
+}
+
+int ab_get_grey(ab_context* ctx, int frame, uint8_t* dst, size_t dst_stride) {
+    if (!ctx || !ctx->have_last || frame < 0 || frame >= ctx->last_n || !dst) return set_err(ctx, AB_E_INVALID, "bad frame");
+    cudaSetDevice(ctx->device);
+    const Batch& b = ctx->last;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy2D(dst, dst_stride, b.grey + (size_t)frame * b.grey_frame, b.grey_row, b.W, b.H, cudaMemcpyDeviceToHost));
+    return AB_OK;
+}
+
+int ab_get_candidates(ab_context* ctx, int frame, float* quads, int32_t* ids, int32_t* n_rot, int cap, int32_t* n) {
+    if (!ctx || !ctx->have_last || frame < 0 || frame >= ctx->last_n || !n) return set_err(ctx, AB_E_INVALID, "bad frame");
+    cudaSetDevice(ctx->device);
+    const Batch& b = ctx->last;
+    CK(cudaStreamSynchronize(ctx->stream));
+    unsigned nc = 0;
+    CK(cudaMemcpy(&nc, b.n_cands + frame, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    nc = std::min<unsigned>(nc, b.cap_c);
+    *n = (int32_t)nc;
+    if ((int)nc > cap) return set_err(ctx, AB_E_CAPACITY, "%u candidates > cap %d", nc, cap);
+    std::vector<CandRec> h(nc);
+    if (nc) CK(cudaMemcpy(h.data(), b.cands + (size_t)frame * b.cap_c, sizeof(CandRec) * nc, cudaMemcpyDeviceToHost));
+    for (unsigned i = 0; i < nc; i++) {
+        if (quads) memcpy(quads + 8 * i, h[i].c, sizeof(float) * 8);
+        if (ids) ids[i] = h[i].id;
+        if (n_rot) n_rot[i] = h[i].nrot;
+    }
+    return AB_OK;
+}
+
+int ab_get_canonical(ab_context* ctx, int frame, int candidate, uint8_t* dst) {
+    if (!ctx || !ctx->have_last || frame < 0 || frame >= ctx->last_n || !dst || candidate < 0 || candidate >= ctx->last.cap_c)
+        return set_err(ctx, AB_E_INVALID, "bad frame/candidate");
+    cudaSetDevice(ctx->device);
+    const Batch& b = ctx->last;
+    CK(cudaStreamSynchronize(ctx->stream));
+    size_t ss = (size_t)b.S * b.S;
+    CK(cudaMemcpy(dst, b.canon + ((size_t)frame * b.cap_c + candidate) * ss, ss, cudaMemcpyDeviceToHost));
+    return AB_OK;
+}
+
+int ab_get_contour(ab_context* ctx, int frame, int candidate, int32_t* xy, int cap_points, int32_t* n) {
+    if (!ctx || !ctx->have_last || frame < 0 || frame >= ctx->last_n || !n || candidate < 0 || candidate >= ctx->last.cap_c)
+        return set_err(ctx, AB_E_INVALID, "bad frame/candidate");
+    cudaSetDevice(ctx->device);
+    const Batch& b = ctx->last;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CandRec cr;
+    CK(cudaMemcpy(&cr, b.cands + (size_t)frame * b.cap_c + candidate, sizeof(CandRec), cudaMemcpyDeviceToHost));
+    ContourRec rec;
+    CK(cudaMemcpy(&rec, b.contours + cr.contour, sizeof(ContourRec), cudaMemcpyDeviceToHost));
+    *n = (int32_t)rec.n;
+    if ((int)rec.n > cap_points) return set_err(ctx, AB_E_CAPACITY, "contour has %u points > cap %d", rec.n, cap_points);
+    std::vector<uint32_t> p(rec.n);
+    CK(cudaMemcpy(p.data(), b.pool + rec.off, sizeof(uint32_t) * rec.n, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < rec.n; i++) {
+        uint32_t v = cr.swapped ? p[rec.n - 1 - i] : p[i];  // the reference reverses swapped contours (:622-625)
+        xy[2 * i] = (int32_t)(v & 0xFFFFu);
+        xy[2 * i + 1] = (int32_t)(v >> 16);
+    }
+    return AB_OK;
+}
+
+int ab_get_counters(ab_context* ctx, int64_t* counters, int n) {
+    if (!ctx || !ctx->have_last || !counters) return set_err(ctx, AB_E_INVALID, "no batch");
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    Counters c;
+    CK(cudaMemcpy(&c, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost));
+    int64_t v[6] = {(int64_t)c.n_starts, (int64_t)c.n_contours, (int64_t)c.pool_used, (int64_t)c.n_quads_total,
+                    (int64_t)c.n_cands_total, (int64_t)c.n_markers_total};
+    for (int i = 0; i < n && i < 6; i++) counters[i] = v[i];
+    return AB_OK;
+}
+
+int ab_get_stage_ms(ab_context* ctx, float* ms, int n) {
+    if (!ctx || !ms || !ctx->timing || !ctx->have_last) return set_err(ctx, AB_E_STATE, "timing not enabled");
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n && i < 5; i++) CK(cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    return AB_OK;
+}
+
+// ---- public workers ---------------------------------------------------------------------------------------
+int ab_threshold(ab_context* ctx, const uint8_t* grey, int width, int height, size_t row_stride, int method, double param1,
+                 double param2, uint8_t* out, size_t out_stride) {
+    if (!ctx || !grey || !out) return AB_E_INVALID;
+    cudaSetDevice(ctx->device);
+    int rc = ensure_reserved(ctx, width, height, 1);
+    if (rc) return rc;
+    rc = ensure_grey(ctx, (size_t)width * height);
+    if (rc) return rc;
+    // markerdetector.cpp:646-649: -1 selects the stored parameters
+    if (param1 == -1) param1 = ctx->params.thres_param1;
+    if (param2 == -1) param2 = ctx->params.thres_param2;
+    CK(cudaMemcpy2DAsync(ctx->d_grey[0], width, grey, row_stride, width, height, cudaMemcpyHostToDevice, ctx->stream));
+    Batch b;
+    fill_batch(ctx, b, ctx->d_grey[0], width, (size_t)width * height, 1, nullptr, nullptr, -1.f);
+    rc = launch_threshold(ctx, b, method, param1, param2);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(out, out_stride, b.thres, width, width, height, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AB_OK;
+}
+
+int ab_detect_rectangles(ab_context* ctx, const uint8_t* thres, int width, int height, size_t row_stride, float* quads, int cap,
+                         int32_t* n) {
+    if (!ctx || !thres || !n) return AB_E_INVALID;
+    cudaSetDevice(ctx->device);
+    int rc = ensure_reserved(ctx, width, height, 1);
+    if (rc) return rc;
+    rc = ensure_grey(ctx, (size_t)width * height);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpy2DAsync(ctx->d_grey[0], width, thres, row_stride, width, height, cudaMemcpyHostToDevice, st));
+    Batch b;
+    fill_batch(ctx, b, ctx->d_grey[0], width, (size_t)width * height, 1, nullptr, nullptr, -1.f);
+    CK(cudaMemsetAsync(ctx->d_counters, 0, ctx->counters_bytes, st));
+    k_threshold_fixed<<<ctx->sm_count * 8, 256, 0, st>>>(b.grey, b.grey_row, b.grey_frame, b.thres, b.bits, b.bits_words, b.W, b.H,
+                                                          b.wpr, 0, 1, 1);
+    k_scan_starts<<<ctx->sm_count * 8, 256, 0, st>>>(b);
+    k_trace<<<ctx->sm_count * 8, 128, 0, st>>>(b);
+    k_polygon<<<ctx->sm_count * 4, 128, 0, st>>>(b);
+    k_frame_filter<<<1, 256, 0, st>>>(b);
+    CK(cudaGetLastError());
+    ctx->last = b;
+    ctx->have_last = true;
+    ctx->last_n = 1;
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, ctx->counters_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    rc = check_device_errors(ctx, (const Counters*)ctx->h_counters);
+    if (rc) return rc;
+    return ab_get_candidates(ctx, 0, quads, nullptr, nullptr, cap, n);
+}
+
+int ab_warp(ab_context* ctx, const uint8_t* grey, int width, int height, size_t row_stride, const float* quad, int size,
+            uint8_t* out) {
+    if (!ctx || !grey || !quad || !out || size < 1 || size > 1024) return set_err(ctx, AB_E_INVALID, "bad arguments");
+    cudaSetDevice(ctx->device);
+    uint8_t *d_img = nullptr, *d_out = nullptr;
+    float* d_quad = nullptr;
+    CK(cudaMalloc(&d_img, (size_t)width * height));
+    CK(cudaMalloc(&d_out, (size_t)size * size));
+    CK(cudaMalloc(&d_quad, 8 * sizeof(float)));
+    CK(cudaMemcpy2D(d_img, width, grey, row_stride, width, height, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_quad, quad, 8 * sizeof(float), cudaMemcpyHostToDevice));
+    k_warp_single<<<1, 256, 0, ctx->stream>>>(d_img, width, height, width, d_quad, size, d_out);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out, d_out, (size_t)size * size, cudaMemcpyDeviceToHost));
+    cudaFree(d_img);
+    cudaFree(d_out);
+    cudaFree(d_quad);
+    return AB_OK;
+}
+
+int ab_calculate_extrinsics(ab_context* ctx, ab_marker* markers, int n, const float* K, const float* D, float marker_size,
+                            int set_y_perp) {
+    if (!ctx || !markers || n < 0 || !K || !(marker_size > 0)) return set_err(ctx, AB_E_INVALID, "calculateExtrinsics: invalid arguments");
+    if (n == 0) return AB_OK;
+    cudaSetDevice(ctx->device);
+    ab_marker* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(ab_marker) * n));
+    CK(cudaMemcpy(d, markers, sizeof(ab_marker) * n, cudaMemcpyHostToDevice));
+    k_extrinsics<<<(n + 63) / 64, 64, 0, ctx->stream>>>(d, n, make_camera(K, D), marker_size, set_y_perp);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(markers, d, sizeof(ab_marker) * n, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return AB_OK;
+}
+
+int ab_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return AB_E_INVALID;
+    return cudaMallocHost(ptr, bytes) == cudaSuccess ? AB_OK : AB_E_CUDA;
+}
+
+int ab_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? AB_OK : AB_E_CUDA; }
+
+}  // extern "C"

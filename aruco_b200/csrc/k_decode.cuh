@@ -1,0 +1,163 @@
+// Stage 3: per-candidate identification (src/markerdetector.cpp:350-356).
+// One CTA per candidate: getPerspectiveTransform + warpPerspective(INTER_NEAREST) into shared memory
+// (MarkerDetector::warp, :684-697), 256-bin histogram -> Otsu (cv::threshold BINARY|OTSU), majority vote per
+// cell, then FiducidalMarkers::detect (src/arucofidmarkers.cpp:438-452) or HighlyReliableMarkers::detect
+// (src/highlyreliablemarkers.cpp:332-383).  The canonical image is also written out (getCandidates /
+// host-callback decoders need it).
+#pragma once
+#include "ab_device.cuh"
+
+namespace ab {
+
+constexpr int MAX_WARP_SIZE = 128;  // S <= 128
+constexpr int MAX_CELLS = 100;      // (n+2)^2 with n <= 8
+
+__device__ __forceinline__ int hrm_decode(const HrmDict& D, const uint8_t* cells, int ncell, int* nrot, int lane) {
+    // cells: (n+2)^2 majority bits; HRM ignores the border cells (highlyreliablemarkers.cpp:345)
+    const int n = D.n;
+    uint8_t code[64];
+    for (int y = 0; y < n; y++)
+        for (int x = 0; x < n; x++) code[y * n + x] = cells[(y + 1) * ncell + x + 1];
+    uint64_t bits[4];
+    uint32_t ids[4];
+    hrm_rotations(code, n, bits, ids);
+    // 1. exact lookup of the four folded ids in the balanced tree (findId, :483-496)
+    for (int r = 0; r < 4; r++) {
+        int pos = D.root;
+        while (pos != -1) {
+            uint32_t pid = D.ord_ids[pos];
+            if (pid == ids[r]) {
+                *nrot = r;
+                return D.ord_pos[pos];
+            }
+            pos = pid < ids[r] ? D.tree[2 * pos + 1] : D.tree[2 * pos];
+        }
+    }
+    // 2. error correction: min over dictionary of min over rotations (Dictionary::distance, :277-289),
+    //    first strict minimum wins in (marker, rotation) order
+    unsigned best = 0xFFFFFFFFu;  // (dist << 16) | (marker << 2) | rot
+    for (int i = lane; i < D.count; i += 32) {
+        uint64_t d0 = D.bits[i];
+        unsigned res = (unsigned)(n * n), mr = 0;
+        for (unsigned r = 0; r < 4; r++) {
+            unsigned hd = (unsigned)__popcll(d0 ^ bits[r]);
+            if (hd < res) {
+                res = hd;
+                mr = r;
+            }
+        }
+        if (res < (unsigned)(n * n)) {
+            unsigned key = (res << 16) | ((unsigned)i << 2) | mr;
+            best = min(best, key);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, d));
+    if (best != 0xFFFFFFFFu && (int)(best >> 16) <= D.correction) {
+        *nrot = (int)(best & 3u);
+        return (int)((best >> 2) & 0x3FFFu);
+    }
+    *nrot = 0;
+    return -1;
+}
+
+// mode 0: warp + decode; mode 1: warp only (host-callback decoder)
+__global__ void __launch_bounds__(128) k_decode(Batch b, int mode) {
+    __shared__ uint8_t s_img[MAX_WARP_SIZE * MAX_WARP_SIZE];
+    __shared__ int s_hist[256];
+    __shared__ int s_cnt[MAX_CELLS];
+    __shared__ uint8_t s_cells[MAX_CELLS];
+    __shared__ double s_Mi[9];
+    __shared__ int s_ok, s_thr;
+    const int f = blockIdx.y, ci = blockIdx.x, t = threadIdx.x;
+    if (ci >= (int)b.n_cands[f]) return;
+    CandRec* cand = b.cands + (size_t)f * b.cap_c + ci;
+    const int S = b.S;
+    if (t == 0) {
+        float dst[8] = {0.f, 0.f, (float)(S - 1), 0.f, (float)(S - 1), (float)(S - 1), 0.f, (float)(S - 1)};
+        double M[9], Mi[9];
+        bool ok = perspective_transform(cand->c, dst, M) && invert3(M, Mi);
+        s_ok = ok;
+        if (ok)
+            for (int i = 0; i < 9; i++) s_Mi[i] = Mi[i];
+    }
+    for (int i = t; i < 256; i += blockDim.x) s_hist[i] = 0;
+    if (t < MAX_CELLS) s_cnt[t] = 0;
+    __syncthreads();
+    const uint8_t* grey = b.grey + (size_t)f * b.grey_frame;
+    uint8_t* canon = b.canon + ((size_t)f * b.cap_c + ci) * (size_t)(S * S);
+    const int bw = warp_block_width(S);
+    const bool ok = s_ok != 0;
+    for (int i = t; i < S * S; i += blockDim.x) {
+        int y = i / S, x = i - y * S;
+        uint8_t v = 0;
+        if (ok) {
+            int sx, sy;
+            warp_src_coord(s_Mi, x, y, bw, &sx, &sy);
+            if (sx >= 0 && sy >= 0 && sx < b.W && sy < b.H) v = grey[(size_t)sy * b.grey_row + sx];
+        }
+        s_img[i] = v;
+        canon[i] = v;
+        atomicAdd(&s_hist[v], 1);
+    }
+    __syncthreads();
+    if (mode == 1) return;
+    if (t == 0) s_thr = otsu_threshold(s_hist, S * S);
+    __syncthreads();
+    const int thr = s_thr;
+    const int ncell = (b.decoder == AB_DECODER_HRM) ? b.dict.n + 2 : 7;
+    const int cell = S / ncell;
+    const int span = cell * ncell;
+    for (int i = t; i < span * span; i += blockDim.x) {
+        int y = i / span, x = i - y * span;
+        if (s_img[y * S + x] > thr) atomicAdd(&s_cnt[(y / cell) * ncell + (x / cell)], 1);
+    }
+    __syncthreads();
+    if (t < ncell * ncell) s_cells[t] = s_cnt[t] > (cell * cell) / 2;
+    __syncthreads();
+    if (b.decoder == AB_DECODER_HRM) {
+        if (t < 32) {
+            int nrot = 0;
+            int id = hrm_decode(b.dict, s_cells, ncell, &nrot, t);
+            if (t == 0) {
+                cand->id = id;
+                cand->nrot = nrot;
+            }
+        }
+    } else if (t == 0) {
+        int nrot = 0;
+        int id = fid_decode(s_cells, &nrot);
+        cand->id = id;
+        cand->nrot = nrot;
+    }
+}
+
+// public worker MarkerDetector::warp for one quad (grid 1)
+__global__ void k_warp_single(const uint8_t* grey, int W, int H, size_t row, const float* quad, int S, uint8_t* out) {
+    __shared__ double s_Mi[9];
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        float dst[8] = {0.f, 0.f, (float)(S - 1), 0.f, (float)(S - 1), (float)(S - 1), 0.f, (float)(S - 1)};
+        float q[8];
+        for (int i = 0; i < 8; i++) q[i] = quad[i];
+        double M[9], Mi[9];
+        bool ok = perspective_transform(q, dst, M) && invert3(M, Mi);
+        s_ok = ok;
+        if (ok)
+            for (int i = 0; i < 9; i++) s_Mi[i] = Mi[i];
+    }
+    __syncthreads();
+    const int bw = warp_block_width(S);
+    for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
+        int y = i / S, x = i - y * S;
+        uint8_t v = 0;
+        if (s_ok) {
+            int sx, sy;
+            warp_src_coord(s_Mi, x, y, bw, &sx, &sy);
+            if (sx >= 0 && sy >= 0 && sx < W && sy < H) v = grey[(size_t)sy * row + sx];
+        }
+        out[i] = v;
+    }
+}
+
+}  // namespace ab

@@ -1,0 +1,175 @@
+// Stage 1: MarkerDetector::thresHold (src/markerdetector.cpp:643-677) for a batch of grey frames.
+//   ADPT_THRES: cv::adaptiveThreshold(MEAN_C, BINARY_INV, k, C)  -- k x k box mean with replicate border,
+//               mean = (2S + k^2) / (2 k^2) (integer), dst = (src - mean <= -floor(C)) ? 255 : 0   
+//   FIXED_THRES: cv::threshold(BINARY_INV, p1): dst = src > floor(p1) ? 0 : 255
+// Output: the u8 {0,255} image (getThresholdedImage is API) and a 1-bit-per-pixel packed copy with zero
+// padding that the contour stage reads (8x less traffic than re-reading the u8 image).
+//
+// Kernel shape: one CTA owns a strip of TWo output columns x RH output rows.  Each thread owns 4 adjacent
+// columns (one 32-bit load per source row), keeps their vertical k-sums in registers (sliding down the
+// strip: + new row - row k back, the k most recent rows live in a shared-memory ring), publishes them to
+// shared memory and forms the horizontal k-sums from its neighbours' columns.  The division of the mean
+// is folded into the comparison:  mean >= T  <=>  2S + k^2 >= 2 k^2 T.
+#pragma once
+#include "ab_device.cuh"
+
+namespace ab {
+
+struct ThrArgs {
+    const uint8_t* grey;
+    size_t grey_row, grey_frame;
+    uint8_t* thres;
+    uint32_t* bits;
+    size_t bits_words;
+    int W, H, wpr;
+    int k, idelta;
+    int TWo, RH, R4;
+    int aligned4;  // source rows allow 32-bit loads
+};
+
+__global__ void k_threshold_adaptive(ThrArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int nth = blockDim.x, t = threadIdx.x, SPAN = 4 * nth;
+    const int k = a.k, r = k >> 1, k2 = k * k;
+    uint8_t* ring = smem;                                            // k rows of SPAN source pixels
+    uint32_t* cs = (uint32_t*)(smem + (((size_t)k * SPAN + 15) & ~(size_t)15));  // SPAN column sums
+    uint8_t* nib = (uint8_t*)(cs + SPAN);                            // nth result nibbles
+    const int X0 = blockIdx.x * a.TWo, y0 = blockIdx.y * a.RH, f = blockIdx.z;
+    const int c0 = X0 - a.R4 + 4 * t;
+    const uint8_t* src = a.grey + (size_t)f * a.grey_frame;
+    uint8_t* dst = a.thres + (size_t)f * a.W * a.H;
+    uint32_t* bits = a.bits + (size_t)f * a.bits_words;
+    const bool fast = a.aligned4 && c0 >= 0 && c0 + 3 < a.W;
+    int xc[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) xc[j] = min(max(c0 + j, 0), a.W - 1);
+    const int yEnd = min(y0 + a.RH, a.H);
+    const int nrows = (yEnd - y0) + 2 * r;
+    const bool is_out = c0 >= X0 && c0 < X0 + a.TWo && c0 < a.W;
+    int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int slot = 0, cslot = 0;  // ring slot of the incoming row / of the centre row
+    for (int i = 0; i < nrows; i++) {
+        int yy = min(max(y0 - r + i, 0), a.H - 1);
+        const uint8_t* rowp = src + (size_t)yy * a.grey_row;
+        uint32_t p;
+        if (fast)
+            p = *reinterpret_cast<const uint32_t*>(rowp + c0);
+        else
+            p = (uint32_t)rowp[xc[0]] | ((uint32_t)rowp[xc[1]] << 8) | ((uint32_t)rowp[xc[2]] << 16) | ((uint32_t)rowp[xc[3]] << 24);
+        uint32_t* rp = reinterpret_cast<uint32_t*>(ring + (size_t)slot * SPAN + 4 * t);
+        uint32_t old = (i >= k) ? *rp : 0u;
+        *rp = p;
+        s0 += (int)(p & 255u) - (int)(old & 255u);
+        s1 += (int)((p >> 8) & 255u) - (int)((old >> 8) & 255u);
+        s2 += (int)((p >> 16) & 255u) - (int)((old >> 16) & 255u);
+        s3 += (int)(p >> 24) - (int)(old >> 24);
+        if (++slot == k) slot = 0;
+        if (i >= 2 * r) {
+            const int yo = y0 + i - 2 * r;
+            *reinterpret_cast<uint4*>(cs + 4 * t) = make_uint4((uint32_t)s0, (uint32_t)s1, (uint32_t)s2, (uint32_t)s3);
+            __syncthreads();
+            uint32_t nibble = 0;
+            if (is_out) {
+                uint32_t c = *reinterpret_cast<const uint32_t*>(ring + (size_t)cslot * SPAN + 4 * t);
+                const uint32_t* w = cs + 4 * t;
+                int S = 0;
+                for (int d = -r; d <= r; d++) S += (int)w[d];
+                uint32_t outb = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    int T = (int)((c >> (8 * j)) & 255u) + a.idelta;
+                    bool on = (2 * S + k2 >= 2 * k2 * T) && (c0 + j < a.W);
+                    if (on) {
+                        nibble |= 1u << j;
+                        outb |= 255u << (8 * j);
+                    }
+                    if (j < 3) S += (int)w[j + 1 + r] - (int)w[j - r];
+                }
+                uint8_t* orow = dst + (size_t)yo * a.W + c0;
+                if (c0 + 3 < a.W && (a.W & 3) == 0) {
+                    *reinterpret_cast<uint32_t*>(orow) = outb;
+                } else {
+                    for (int j = 0; j < 4; j++)
+                        if (c0 + j < a.W) orow[j] = (uint8_t)(outb >> (8 * j));
+                }
+            }
+            nib[t] = (uint8_t)nibble;
+            __syncthreads();
+            if (t < (a.TWo >> 5) && X0 + 32 * t < a.W) {
+                const uint8_t* nb = nib + (a.R4 >> 2) + 8 * t;
+                uint32_t word = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) word |= (uint32_t)nb[q] << (4 * q);
+                bits[(size_t)(yo + 1) * a.wpr + 1 + (X0 >> 5) + t] = word;
+            }
+            if (++cslot == k) cslot = 0;
+        } else if (i >= r) {
+            if (++cslot == k) cslot = 0;
+        }
+    }
+}
+
+// FIXED_THRES and bit packing of an existing binary image: one thread per 32-pixel word.
+// mode 0: dst = src > thr ? 0 : 255 (threshold BINARY_INV);  mode 1: dst = src (non-zero = fg), pack only
+__global__ void k_threshold_fixed(const uint8_t* grey, size_t grey_row, size_t grey_frame, uint8_t* thres,
+                                  uint32_t* bits, size_t bits_words, int W, int H, int wpr, int thr, int mode, int B) {
+    int ww = (W + 31) >> 5;
+    size_t total = (size_t)ww * H * B;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int w = (int)(i % ww);
+        int y = (int)((i / ww) % H);
+        int f = (int)(i / ((size_t)ww * H));
+        const uint8_t* rowp = grey + (size_t)f * grey_frame + (size_t)y * grey_row;
+        uint8_t* orow = thres + ((size_t)f * H + y) * W;
+        uint32_t word = 0;
+        for (int j = 0; j < 32; j++) {
+            int x = 32 * w + j;
+            if (x >= W) break;
+            uint8_t v = rowp[x];
+            bool on = mode == 0 ? !((int)v > thr) : (v != 0);
+            if (on) word |= 1u << j;
+            if (mode == 0) orow[x] = on ? 255 : 0;
+            else if (orow + x != rowp + x) orow[x] = v;
+        }
+        bits[(size_t)f * bits_words + (size_t)(y + 1) * wpr + 1 + w] = word;
+    }
+}
+
+// 3x3 erosion (cv::erode(thres, Mat()), out-of-image = 255) on the packed image; rewrites thres and bits.
+__global__ void k_erode(const uint32_t* in, uint32_t* out, uint8_t* thres, size_t bits_words, int W, int H, int wpr, int B) {
+    int ww = (W + 31) >> 5;
+    size_t total = (size_t)ww * H * B;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int w = (int)(i % ww);
+        int y = (int)((i / ww) % H);
+        int f = (int)(i / ((size_t)ww * H));
+        const uint32_t* base = in + (size_t)f * bits_words;
+        int nvalid = min(32, W - 32 * w);
+        uint32_t vmask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+        uint32_t acc = 0xFFFFFFFFu;
+        for (int dy = -1; dy <= 1; dy++) {
+            int yy = y + dy;
+            uint32_t cur, prv, nxt;
+            if (yy < 0 || yy >= H) {
+                cur = prv = nxt = 0xFFFFFFFFu;
+            } else {
+                const uint32_t* row = base + (size_t)(yy + 1) * wpr + 1 + w;
+                cur = row[0] | ~vmask;                   // pixels beyond W count as 255
+                prv = (w == 0) ? 0xFFFFFFFFu : row[-1];  // pixels left of 0 count as 255
+                nxt = (w == ww - 1) ? 0xFFFFFFFFu : row[1];
+                if (w == ww - 2) {
+                    int nv2 = W - 32 * (w + 1);
+                    if (nv2 < 32) nxt |= ~((1u << nv2) - 1u);
+                }
+            }
+            uint32_t l = (cur << 1) | (prv >> 31), rr = (cur >> 1) | (nxt << 31);
+            acc &= cur & l & rr;
+        }
+        acc &= vmask;
+        out[(size_t)f * bits_words + (size_t)(y + 1) * wpr + 1 + w] = acc;
+        uint8_t* orow = thres + ((size_t)f * H + y) * W + 32 * w;
+        for (int j = 0; j < nvalid; j++) orow[j] = (acc >> j) & 1u ? 255 : 0;
+    }
+}
+
+}  // namespace ab

@@ -1,0 +1,153 @@
+/* aruco_b200 -- C ABI of the B200-native marker-detection hot path.
+ *
+ * Drop-in boundary for paroj/aruco's aruco::MarkerDetector (src/markerdetector.h:43-311 of the reference).
+ * Every entry point names the reference interface it replaces.  Plain pointers and sizes only; no C++ or
+ * torch types; every call returns 0 on success or a negative ab_status, with a message retrievable through
+ * ab_last_error().  Capacity overflows are reported (AB_E_CAPACITY), never truncated.  There is no CPU
+ * fallback: ab_create fails when no CUDA device is available.
+ *
+ * One ab_context per host thread (the reference's MarkerDetector instance is not re-entrant either:
+ * it mutates `thres` and `_candidates`, markerdetector.h:306-308).
+ */
+#ifndef ARUCO_B200_H
+#define ARUCO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define AB_API __declspec(dllexport)
+#else
+#define AB_API __attribute__((visibility("default")))
+#endif
+
+typedef struct ab_context ab_context;
+
+typedef enum ab_status {
+    AB_OK = 0,
+    AB_E_INVALID = -1,   /* bad argument (the reference would CV_Assert, e.g. markerdetector.cpp:644,1032,1048) */
+    AB_E_CUDA = -2,      /* CUDA runtime error                                                     */
+    AB_E_CAPACITY = -3,  /* a fixed-capacity device buffer overflowed; call ab_reserve with more    */
+    AB_E_NO_DEVICE = -4, /* no usable CUDA device (this library has no CPU path)                   */
+    AB_E_STATE = -5      /* call order error (e.g. HRM decoder selected without a dictionary)      */
+} ab_status;
+
+/* enum ThresholdMethods, markerdetector.h:125 */
+enum { AB_THRES_FIXED = 0, AB_THRES_ADAPTIVE = 1, AB_THRES_CANNY = 2 };
+/* enum CornerRefinementMethod, markerdetector.h:186 */
+enum { AB_CORNER_NONE = 0, AB_CORNER_HARRIS = 1, AB_CORNER_SUBPIX = 2, AB_CORNER_LINES = 3 };
+/* which decoder sits behind setMakerDetectorFunction (markerdetector.h:243): the two built-ins run on the
+ * device, anything else is called back on the host with the canonical images */
+enum { AB_DECODER_FIDUCIDAL = 0, AB_DECODER_HRM = 1, AB_DECODER_HOST_CALLBACK = 2 };
+
+/* Private state of MarkerDetector (markerdetector.h:288-311); defaults = ctor (markerdetector.cpp:235-249). */
+typedef struct ab_params {
+    int32_t thres_method;        /* _thresMethod      (setThresholdMethod, h:129)            */
+    double thres_param1;         /* _thresParam1      (setThresholdParams, h:140)            */
+    double thres_param2;         /* _thresParam2                                             */
+    int32_t corner_method;       /* _cornerMethod     (setCornerRefinementMethod, h:189)     */
+    float min_size;              /* _minSize          (setMinMaxSize, h:200)                 */
+    float max_size;              /* _maxSize                                                 */
+    int32_t warp_size;           /* _markerWarpSize   (setWarpSize, h:232)                   */
+    float border_dist;           /* _borderDistThres  (cpp:248)                              */
+    int32_t locked_corners;      /* _useLockedCorners (enableLockedCornersMethod, h:165)     */
+    int32_t erosion;             /* enableErosion (API-compat extension, default 0)          */
+    int32_t decoder;             /* AB_DECODER_*      (setMakerDetectorFunction, h:243)      */
+    int32_t set_y_perpendicular; /* detect(..., setYPerpendicular) h:102                     */
+} ab_params;
+
+/* aruco::Marker (marker.h:46-141): 4 corners, id, ssize, Rvec/Tvec (f64). has_pose=0 => Rvec/Tvec empty. */
+typedef struct ab_marker {
+    int32_t id;
+    int32_t has_pose;
+    float corners[8];
+    float ssize;
+    float pad_;
+    double rvec[3];
+    double tvec[3];
+} ab_marker;
+
+/* MarkerdetectorFunc (markerdetector.h:78): `int f(const cv::Mat& in, int& nRotations)`; `canonical` is a
+ * writable S x S 8UC1 image (the built-ins threshold it in place, arucofidmarkers.cpp:441-446). */
+typedef int (*ab_decoder_fn)(uint8_t* canonical, int size, int* n_rotations, void* user);
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+AB_API int ab_create(int device, ab_context** out);            /* MarkerDetector::MarkerDetector, cpp:235 */
+AB_API void ab_destroy(ab_context* ctx);                       /* ~MarkerDetector, cpp:257               */
+AB_API const char* ab_last_error(const ab_context* ctx);
+AB_API const char* ab_version(void);
+
+/* ---- configuration ------------------------------------------------------------------------------- */
+AB_API int ab_default_params(ab_params* p);                    /* ctor defaults, cpp:235-249             */
+AB_API int ab_set_params(ab_context* ctx, const ab_params* p); /* the set* methods, h:129-245            */
+AB_API int ab_get_params(const ab_context* ctx, ab_params* p);
+/* HighlyReliableMarkers::loadDictionary (highlyreliablemarkers.h:198-199, cpp:312-328):
+ * bits = count*n*n bytes (row-major, 0/1), correction radius = rate*((tau0-1)/2).                        */
+AB_API int ab_load_hrm_dictionary(ab_context* ctx, int n, int count, const uint8_t* bits, int tau0, float rate);
+AB_API int ab_set_decoder_callback(ab_context* ctx, ab_decoder_fn fn, void* user); /* h:243 (custom fn)  */
+/* Sizes device buffers. max_start_candidates / max_contour_points are per frame; <=0 picks defaults.     */
+AB_API int ab_reserve(ab_context* ctx, int width, int height, int max_batch, int max_quads_per_frame,
+                      int max_candidates_per_frame, int64_t max_start_candidates_per_frame,
+                      int64_t max_contour_points_per_frame);
+AB_API int ab_set_stream(ab_context* ctx, void* cuda_stream);  /* run on the caller's CUDA stream         */
+
+/* ---- detect: MarkerDetector::detect (markerdetector.h:102-120, cpp:302-478) ----------------------- */
+/* Host frames (8UC1, row stride `row_stride`, consecutive frames `frame_stride` bytes apart). Copies in,
+ * runs the whole path for the batch, copies the markers out.  K: 9 floats row-major or NULL; D: 5 floats
+ * or NULL (CameraParameters holds f32, cameraparameters.cpp:204-219).  out: n_frames*cap_per_frame.       */
+AB_API int ab_detect_batch(ab_context* ctx, const uint8_t* frames, int width, int height, size_t row_stride,
+                           size_t frame_stride, int n_frames, const float* K, const float* D, float marker_size,
+                           ab_marker* out, int cap_per_frame, int32_t* counts);
+/* Same with frames already resident in device memory: enqueue is asynchronous on the context's stream,
+ * fetch copies the markers to the host and reports device-side errors.                                    */
+AB_API int ab_enqueue_batch_device(ab_context* ctx, const uint8_t* dev_frames, int width, int height,
+                                   size_t row_stride, size_t frame_stride, int n_frames, const float* K,
+                                   const float* D, float marker_size);
+AB_API int ab_fetch_results(ab_context* ctx, ab_marker* out, int cap_per_frame, int32_t* counts);
+/* 8UC3 BGR front step (cvtColor BGR2GRAY, cpp:307-310) for host frames.                                   */
+AB_API int ab_detect_batch_bgr(ab_context* ctx, const uint8_t* frames_bgr, int width, int height, size_t row_stride,
+                               size_t frame_stride, int n_frames, const float* K, const float* D, float marker_size,
+                               ab_marker* out, int cap_per_frame, int32_t* counts);
+
+/* ---- state left by the last detect ----------------------------------------------------------------- */
+AB_API int ab_get_thresholded(ab_context* ctx, int frame, uint8_t* dst, size_t dst_stride); /* getThresholdedImage h:183 */
+AB_API int ab_get_grey(ab_context* ctx, int frame, uint8_t* dst, size_t dst_stride);
+/* every candidate that reached the decoder, in the reference's order (cpp:350): quads = n*8 floats (the
+ * corners entering warp), ids (-1 = rejected -> getCandidates h:266), n_rot.                              */
+AB_API int ab_get_candidates(ab_context* ctx, int frame, float* quads, int32_t* ids, int32_t* n_rot, int cap, int32_t* n);
+AB_API int ab_get_canonical(ab_context* ctx, int frame, int candidate, uint8_t* dst /* S*S */);
+AB_API int ab_get_contour(ab_context* ctx, int frame, int candidate, int32_t* xy, int cap_points, int32_t* n);
+/* counters[0]=start candidates [1]=contours kept (min<n<max) [2]=contour points [3]=quads before the
+ * too-near filter [4]=candidates [5]=markers (summed over the batch)                                      */
+AB_API int ab_get_counters(ab_context* ctx, int64_t* counters, int n);
+/* per-stage device milliseconds of the last ab_detect_batch/ab_enqueue (needs ab_enable_timing):
+ * [0]=threshold [1]=candidates [2]=decode [3]=refine [4]=filter+pose  (the reference's 5 phases, cpp:469-477) */
+AB_API int ab_enable_timing(ab_context* ctx, int enable);
+AB_API int ab_get_stage_ms(ab_context* ctx, float* ms, int n);
+
+/* ---- public workers of MarkerDetector ---------------------------------------------------------------- */
+/* thresHold (h:255, cpp:643-677) */
+AB_API int ab_threshold(ab_context* ctx, const uint8_t* grey, int width, int height, size_t row_stride, int method,
+                        double param1, double param2, uint8_t* out, size_t out_stride);
+/* detectRectangles (h:261, cpp:486-494): quads = cap*8 floats */
+AB_API int ab_detect_rectangles(ab_context* ctx, const uint8_t* thres, int width, int height, size_t row_stride,
+                                float* quads, int cap, int32_t* n);
+/* warp (h:275, cpp:684-697) */
+AB_API int ab_warp(ab_context* ctx, const uint8_t* grey, int width, int height, size_t row_stride, const float* quad,
+                   int size, uint8_t* out);
+/* Marker::calculateExtrinsics (marker.h / marker.cpp:112-125) for n markers */
+AB_API int ab_calculate_extrinsics(ab_context* ctx, ab_marker* markers, int n, const float* K, const float* D,
+                                   float marker_size, int set_y_perpendicular);
+
+/* pinned host memory for frame staging */
+AB_API int ab_host_alloc(void** ptr, size_t bytes);
+AB_API int ab_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARUCO_B200_H */
