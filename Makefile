@@ -1,6 +1,7 @@
 # Builds the product library (CUDA, sm_100a), the CPU oracle (test infrastructure) and the host-check shim.
 NVCC      ?= nvcc
-CXX       ?= g++
+# the image exports CXX=/opt/gcc/bin/g++ whose libgomp spec is missing: always use the system g++
+CXX       := /usr/bin/g++
 NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 \
              -Xcompiler -fPIC,-fvisibility=hidden --shared -Iinclude
 LIB       := aruco_b200/lib/libaruco_b200.so

@@ -459,6 +459,87 @@ AB_HD void project_marker(const Camera& cam, const double* p, const float* obj, 
     }
 }
 
+// residual (projection - measurement) of the 4 marker corners for pose p = (rvec, tvec)
+AB_HD void pnp_residual(const Camera& cam, const double* p, const float* obj, const double* m, double* err) {
+    double uv[8];
+    project_marker(cam, p, obj, uv);
+    for (int i = 0; i < 8; i++) err[i] = uv[i] - m[i];
+}
+
+// d(rotation matrix)/d(rvec): dR[k][i] = dR_i/dr_k (cvRodrigues2 jacobian), analytic
+AB_HD void rodrigues_jacobian(const double* r, double* R, double dR[3][9]) {
+    double theta = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    if (theta < DBL_EPSILON) {
+        for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0) ? 1. : 0.;
+        for (int k = 0; k < 3; k++)
+            for (int i = 0; i < 9; i++) dR[k][i] = 0;
+        dR[0][5] = -1; dR[0][7] = 1;
+        dR[1][2] = 1;  dR[1][6] = -1;
+        dR[2][1] = -1; dR[2][3] = 1;
+        return;
+    }
+    double c = cos(theta), s = sin(theta), c1 = 1. - c, it = 1. / theta;
+    double rv[3] = {r[0] * it, r[1] * it, r[2] * it};
+    double rrt[9], rx[9] = {0, -rv[2], rv[1], rv[2], 0, -rv[0], -rv[1], rv[0], 0};
+    const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) rrt[i * 3 + j] = rv[i] * rv[j];
+    for (int i = 0; i < 9; i++) R[i] = c * I[i] + c1 * rrt[i] + s * rx[i];
+    // R = c I + (1-c) n n^T + s [n]x with n = r/theta
+    for (int k = 0; k < 3; k++) {
+        // dtheta/dr_k = n_k ; dn_i/dr_k = (delta_ik - n_i n_k)/theta
+        double dn[3];
+        for (int i = 0; i < 3; i++) dn[i] = ((i == k ? 1. : 0.) - rv[i] * rv[k]) * it;
+        double drrt[9], drx[9] = {0, -dn[2], dn[1], dn[2], 0, -dn[0], -dn[1], dn[0], 0};
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) drrt[i * 3 + j] = dn[i] * rv[j] + rv[i] * dn[j];
+        for (int i = 0; i < 9; i++)
+            dR[k][i] = rv[k] * (-s * I[i] + s * rrt[i] + c * rx[i]) + c1 * drrt[i] + s * drx[i];
+    }
+}
+
+// residual and analytic Jacobian d(u,v)/d(rvec,tvec) (cvProjectPoints2 with dpdr, dpdt)
+AB_HD void pnp_residual_jacobian(const Camera& cam, const double* p, const float* obj, const double* m, double* err,
+                                 double J[8][6]) {
+    double R[9], dR[3][9];
+    rodrigues_jacobian(p, R, dR);
+    for (int i = 0; i < 4; i++) {
+        double X = obj[3 * i], Y = obj[3 * i + 1], Z = obj[3 * i + 2];
+        double x = R[0] * X + R[1] * Y + R[2] * Z + p[3];
+        double y = R[3] * X + R[4] * Y + R[5] * Z + p[4];
+        double z = R[6] * X + R[7] * Y + R[8] * Z + p[5];
+        double iz = z ? 1. / z : 1.;
+        double xn = x * iz, yn = y * iz;
+        double r2 = xn * xn + yn * yn, r4 = r2 * r2, r6 = r4 * r2;
+        double a1 = 2 * xn * yn, a2 = r2 + 2 * xn * xn, a3 = r2 + 2 * yn * yn;
+        double cdist = 1 + cam.k1 * r2 + cam.k2 * r4 + cam.k3 * r6;
+        double dc = cam.k1 + 2 * cam.k2 * r2 + 3 * cam.k3 * r4;  // d cdist / d r2
+        double xd = xn * cdist + cam.p1 * a1 + cam.p2 * a2, yd = yn * cdist + cam.p1 * a3 + cam.p2 * a1;
+        err[2 * i] = xd * cam.fx + cam.cx - m[2 * i];
+        err[2 * i + 1] = yd * cam.fy + cam.cy - m[2 * i + 1];
+        // d(xd,yd)/d(xn,yn)
+        double dxdx = cdist + 2 * xn * xn * dc + 2 * cam.p1 * yn + 6 * cam.p2 * xn;
+        double dxdy = 2 * xn * yn * dc + 2 * cam.p1 * xn + 2 * cam.p2 * yn;
+        double dydx = 2 * xn * yn * dc + 2 * cam.p1 * xn + 2 * cam.p2 * yn;
+        double dydy = cdist + 2 * yn * yn * dc + 6 * cam.p1 * yn + 2 * cam.p2 * xn;
+        // d(xn,yn)/d(x,y,z)
+        double dxn[3] = {iz, 0, -xn * iz}, dyn[3] = {0, iz, -yn * iz};
+        double du[3], dv[3];  // d(u,v)/d(camera point)
+        for (int c = 0; c < 3; c++) {
+            du[c] = cam.fx * (dxdx * dxn[c] + dxdy * dyn[c]);
+            dv[c] = cam.fy * (dydx * dxn[c] + dydy * dyn[c]);
+        }
+        for (int k = 0; k < 3; k++) {
+            double dX[3] = {dR[k][0] * X + dR[k][1] * Y + dR[k][2] * Z, dR[k][3] * X + dR[k][4] * Y + dR[k][5] * Z,
+                            dR[k][6] * X + dR[k][7] * Y + dR[k][8] * Z};
+            J[2 * i][k] = du[0] * dX[0] + du[1] * dX[1] + du[2] * dX[2];
+            J[2 * i + 1][k] = dv[0] * dX[0] + dv[1] * dX[1] + dv[2] * dX[2];
+            J[2 * i][3 + k] = du[k];
+            J[2 * i + 1][3 + k] = dv[k];
+        }
+    }
+}
+
 AB_HD bool solve6(double A[6][6], double* b) {
     for (int i = 0; i < 6; i++) {
         int k = i;
@@ -535,76 +616,64 @@ AB_HD bool solve_pnp_marker(const Camera& cam, const float* corners, float size,
     double R[9] = {h1[0], h2[0], c3[0], h1[1], h2[1], c3[1], h1[2], h2[2], c3[2]};
     orthonormalize3(R);
     mat_to_rodrigues(R, p);
-    // 3. Levenberg-Marquardt (numeric central-difference Jacobian, run to convergence)
+    // 3. Levenberg-Marquardt exactly as OpenCV's CvLevMarq drives it inside cvFindExtrinsicCameraParams2:
+    //    lambda = 10^k (k starts at -3), diag(JtJ) *= 1 + lambda, step = param - solve(JtJN, Jt err); a step
+    //    that raises |err| is retried with k+1 (up to 16), an accepted one lowers k; stop after 20 accepted
+    //    steps or when |param - prev| / |prev| < FLT_EPSILON.  Matching the trajectory (not just the
+    //    minimum) matters: near-frontal markers have two pose minima and 20 iterations may not converge.
     double m[8];
     for (int i = 0; i < 8; i++) m[i] = corners[i];
-    double uv[8], res[8], lambda = 1e-3;
-    project_marker(cam, p, obj, uv);
-    double err = 0;
-    for (int i = 0; i < 8; i++) {
-        res[i] = uv[i] - m[i];
-        err += res[i] * res[i];
-    }
-    for (int it = 0; it < 100; it++) {
-        double J[8][6];
-        for (int k = 0; k < 6; k++) {
-            double hstep = 1e-6 * (fabs(p[k]) > 1. ? fabs(p[k]) : 1.);
-            double pp[6], up[8], um[8];
-            for (int i = 0; i < 6; i++) pp[i] = p[i];
-            pp[k] = p[k] + hstep;
-            project_marker(cam, pp, obj, up);
-            pp[k] = p[k] - hstep;
-            project_marker(cam, pp, obj, um);
-            for (int i = 0; i < 8; i++) J[i][k] = (up[i] - um[i]) / (2 * hstep);
-        }
-        double JtJ[6][6], Jtr[6];
+    double J[8][6], err[8], JtJ[6][6], JtErr[6], prev[6];
+    int lambdaLg10 = -3, iters = 0;
+    double prevErrNorm = 0;
+    pnp_residual_jacobian(cam, p, obj, m, err, J);
+    for (;;) {
+        // state CALC_J
         for (int i = 0; i < 6; i++) {
-            Jtr[i] = 0;
-            for (int k = 0; k < 8; k++) Jtr[i] += J[k][i] * res[k];
+            double s = 0;
+            for (int k = 0; k < 8; k++) s += J[k][i] * err[k];
+            JtErr[i] = s;
             for (int j = 0; j < 6; j++) {
-                double s = 0;
-                for (int k = 0; k < 8; k++) s += J[k][i] * J[k][j];
-                JtJ[i][j] = s;
+                double q = 0;
+                for (int k = 0; k < 8; k++) q += J[k][i] * J[k][j];
+                JtJ[i][j] = q;
             }
+            prev[i] = p[i];
         }
-        bool improved = false;
-        double stepn = 0, pn = 0;
-        for (int tries = 0; tries < 30 && !improved; tries++) {
+        if (iters == 0) {
+            double s = 0;
+            for (int k = 0; k < 8; k++) s += err[k] * err[k];
+            prevErrNorm = sqrt(s);
+        }
+        double errNorm = 0;
+        for (;;) {
+            double lambda = exp(lambdaLg10 * 2.302585092994046);
             double A[6][6], d[6];
             for (int i = 0; i < 6; i++) {
                 for (int j = 0; j < 6; j++) A[i][j] = JtJ[i][j];
-                A[i][i] += lambda * (JtJ[i][i] > 1e-300 ? JtJ[i][i] : 1e-300);
-                d[i] = -Jtr[i];
+                A[i][i] *= 1. + lambda;
+                d[i] = JtErr[i];
             }
-            if (!solve6(A, d)) {
-                lambda *= 10;
-                continue;
-            }
-            double pp[6], nuv[8], nerr = 0;
-            for (int i = 0; i < 6; i++) pp[i] = p[i] + d[i];
-            project_marker(cam, pp, obj, nuv);
-            for (int i = 0; i < 8; i++) {
-                double e = nuv[i] - m[i];
-                nerr += e * e;
-            }
-            if (nerr <= err) {
-                stepn = 0;
-                pn = 0;
-                for (int i = 0; i < 6; i++) {
-                    stepn += d[i] * d[i];
-                    pn += pp[i] * pp[i];
-                    p[i] = pp[i];
-                }
-                for (int i = 0; i < 8; i++) res[i] = nuv[i] - m[i];
-                err = nerr;
-                lambda = lambda * 0.1 > 1e-12 ? lambda * 0.1 : 1e-12;
-                improved = true;
-            } else {
-                lambda *= 10;
-            }
+            if (!solve6(A, d))
+                for (int i = 0; i < 6; i++) d[i] = 0;
+            for (int i = 0; i < 6; i++) p[i] = prev[i] - d[i];
+            // state CHECK_ERR
+            pnp_residual(cam, p, obj, m, err);
+            double s = 0;
+            for (int k = 0; k < 8; k++) s += err[k] * err[k];
+            errNorm = sqrt(s);
+            if (errNorm > prevErrNorm && ++lambdaLg10 <= 16) continue;
+            break;
         }
-        if (!improved) break;
-        if (stepn <= 1e-26 * (pn > 1e-300 ? pn : 1e-300)) break;
+        lambdaLg10 = lambdaLg10 - 1 > -16 ? lambdaLg10 - 1 : -16;
+        double dn = 0, pn = 0;
+        for (int i = 0; i < 6; i++) {
+            dn += (p[i] - prev[i]) * (p[i] - prev[i]);
+            pn += prev[i] * prev[i];
+        }
+        if (++iters >= 20 || sqrt(dn) / sqrt(pn) < FLT_EPSILON) break;
+        prevErrNorm = errNorm;
+        pnp_residual_jacobian(cam, p, obj, m, err, J);
     }
     for (int i = 0; i < 3; i++) {
         rvec[i] = p[i];
