@@ -55,6 +55,7 @@ SYMBOLS = {
     "ab_get_counters": (_i, [_vp, _vp, _i]),
     "ab_enable_timing": (_i, [_vp, _i]),
     "ab_get_stage_ms": (_i, [_vp, _vp, _i]),
+    "ab_get_kernel_ms": (_i, [_vp, _vp, _i]),
     "ab_threshold": (_i, [_vp, _vp, _i, _i, _sz, _i, _d, _d, _vp, _sz]),
     "ab_detect_rectangles": (_i, [_vp, _vp, _i, _i, _sz, _vp, _i, C.POINTER(C.c_int32)]),
     "ab_warp": (_i, [_vp, _vp, _i, _i, _sz, _vp, _i, _vp]),

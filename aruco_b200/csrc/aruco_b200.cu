@@ -71,6 +71,7 @@ struct ab_context {
     // timing
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t kev[10] = {};  // per-kernel boundaries: memset|threshold|scan|trace|polygon|filter|decode|refine|finalize
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 };
 
@@ -166,6 +167,7 @@ int ab_create(int device, ab_context** out) {
         return AB_E_CUDA;
     }
     for (int i = 0; i < 6; i++) cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < 10; i++) cudaEventCreate(&ctx->kev[i]);
     for (int i = 0; i < 2; i++) {
         cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
@@ -189,6 +191,8 @@ void ab_destroy(ab_context* ctx) {
     F(ctx->d_dict_tree);
     for (int i = 0; i < 6; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 10; i++)
+        if (ctx->kev[i]) cudaEventDestroy(ctx->kev[i]);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
@@ -541,18 +545,24 @@ static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t f
     const int sms = ctx->sm_count;
     if (ctx->timing) cudaEventRecord(ctx->ev[0], st);
     CK(cudaMemsetAsync(ctx->d_counters, 0, ctx->counters_bytes, st));
+    if (ctx->timing) cudaEventRecord(ctx->kev[0], st);
     int rc = launch_threshold(ctx, b, P.thres_method, P.thres_param1, P.thres_param2);
     if (rc) return rc;
+    if (ctx->timing) cudaEventRecord(ctx->kev[1], st);
     if (P.erosion) {
         k_erode<<<sms * 8, 256, 0, st>>>(b.bits, b.bits2, b.thres, b.bits_words, b.W, b.H, b.wpr, b.B);
         std::swap(b.bits, b.bits2);
     }
     if (ctx->timing) cudaEventRecord(ctx->ev[1], st);
     k_scan_starts<<<sms * 8, 256, 0, st>>>(b);
+    if (ctx->timing) cudaEventRecord(ctx->kev[2], st);
     k_trace<<<sms * 8, 128, 0, st>>>(b);
+    if (ctx->timing) cudaEventRecord(ctx->kev[3], st);
     k_polygon<<<sms * 4, 128, 0, st>>>(b);
+    if (ctx->timing) cudaEventRecord(ctx->kev[4], st);
     k_frame_filter<<<n, 256, 0, st>>>(b);
     CK(cudaGetLastError());
+    if (ctx->timing) cudaEventRecord(ctx->kev[5], st);
     if (ctx->timing) cudaEventRecord(ctx->ev[2], st);
     dim3 gcand(b.cap_c, n);
     if (P.decoder == AB_DECODER_HOST_CALLBACK) {
@@ -584,6 +594,7 @@ static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t f
         k_decode<<<gcand, 128, 0, st>>>(b, 0);
         CK(cudaGetLastError());
     }
+    if (ctx->timing) cudaEventRecord(ctx->kev[6], st);
     if (ctx->timing) cudaEventRecord(ctx->ev[3], st);
     if (P.corner_method == AB_CORNER_LINES) {
         k_refine_lines<<<gcand, 128, 0, st>>>(b);
@@ -594,9 +605,11 @@ static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t f
         k_refine_subpix<<<dim3(b.cap_c, n), 128, smem, st>>>(b);
     }
     CK(cudaGetLastError());
+    if (ctx->timing) cudaEventRecord(ctx->kev[7], st);
     if (ctx->timing) cudaEventRecord(ctx->ev[4], st);
     k_finalize<<<n, 128, 0, st>>>(b);
     CK(cudaGetLastError());
+    if (ctx->timing) cudaEventRecord(ctx->kev[8], st);
     if (ctx->timing) cudaEventRecord(ctx->ev[5], st);
     ctx->last = b;
     ctx->have_last = true;
@@ -845,6 +858,14 @@ int ab_get_stage_ms(ab_context* ctx, float* ms, int n) {
     cudaSetDevice(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < n && i < 5; i++) CK(cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    return AB_OK;
+}
+
+int ab_get_kernel_ms(ab_context* ctx, float* ms, int n) {
+    if (!ctx || !ms || !ctx->timing || !ctx->have_last) return set_err(ctx, AB_E_STATE, "timing not enabled");
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n && i < 8; i++) CK(cudaEventElapsedTime(&ms[i], ctx->kev[i], ctx->kev[i + 1]));
     return AB_OK;
 }
 

@@ -49,7 +49,7 @@ def grid_for(n_markers: int):
 
 
 def render_frame(W: int, H: int, n_markers: int, seed: int, sigma: float = 2.0, marker_px: int | None = None,
-                 hrm_codes=None, hrm_n: int = 0, flips: int = 0, clean: bool = False):
+                 hrm_codes=None, hrm_n: int = 0, flips: int = 0, clean: bool = False, as_float: bool = False):
     """Returns (grey u8 HxW, truth) with truth = {'ids': [...], 'corners': (n,4,2) f64 image coords}."""
     rng = np.random.default_rng(seed)
     gx, gy = grid_for(n_markers)
@@ -115,6 +115,10 @@ def render_frame(W: int, H: int, n_markers: int, seed: int, sigma: float = 2.0, 
     out = p[:, :-2] * k3[0] + p[:, 1:-1] * k3[1] + p[:, 2:] * k3[2]
     out = out[:-2] * k3[0] + out[1:-1] * k3[1] + out[2:] * k3[2]
     out = out * np.float32(0.8) + np.float32(20)
+    if as_float:  # noise-free f32 image: the caller adds its own noise (bench: on the GPU, per frame)
+        tc = np.array(truth_c, np.float64)
+        ph = np.concatenate([tc, np.ones(tc.shape[:2] + (1,))], axis=2) @ Hm.T
+        return out, {"ids": truth_ids, "corners": ph[..., :2] / ph[..., 2:3]}
     if not clean and sigma > 0:
         out = out + rng.normal(0.0, sigma, size=out.shape).astype(np.float32)
     grey = np.clip(np.rint(out), 0, 255).astype(np.uint8)
