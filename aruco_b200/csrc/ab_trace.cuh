@@ -105,6 +105,59 @@ AB_HD bool make_start(const BitImage& im, int type, int x, int y, TraceStart& st
     return st.b >= 0;
 }
 
+struct WalkState {
+    int x, y, b;  // at pixel (x,y), came from the neighbour in direction b
+};
+
+AB_HD bool same_state(const WalkState& a, const WalkState& c) { return a.x == c.x && a.y == c.y && a.b == c.b; }
+
+// Is `s` the start state of a start candidate whose trigger scans before `key0`?  (nb = neighbours of s)
+AB_HD bool is_smaller_trigger(const BitImage& im, const WalkState& s, uint32_t nb, int64_t key0) {
+    int64_t k = (int64_t)s.y * im.W + s.x;
+    if (is_outer_candidate(nb) && k < key0 && s.b == first_clockwise(nb, 4)) return true;
+    if (is_hole_candidate_east(nb) && k + 1 < key0 && s.b == first_clockwise(nb, 0)) return true;
+    return false;
+}
+
+// successor state (the border-following step of OpenCV's tracer)
+AB_HD void walk_forward(WalkState& s, uint32_t nb) {
+    int d = next_dir(nb, s.b);
+    s.x += dir_dx(d);
+    s.y += dir_dy(d);
+    s.b = (d + 4) & 7;
+}
+
+// predecessor state: the successor function is a permutation of the states, its inverse probes clockwise
+AB_HD void walk_backward(const BitImage& im, WalkState& s) {
+    int qx = s.x + dir_dx(s.b), qy = s.y + dir_dy(s.b);
+    int d = (s.b + 4) & 7;  // direction from the predecessor pixel to the current one
+    s.b = first_clockwise(neighbours8(im, qx, qy), d);
+    s.x = qx;
+    s.y = qy;
+}
+
+// Bidirectional search: is `st` the Suzuki start of its border?  Walks forwards and backwards alternately
+// and stops as soon as either walker stands on the start state of a candidate with a smaller scan position
+// (the expected walk is then ~ the distance to the next higher candidate instead of most of the border).
+// When the walkers meet the whole cycle has been seen: *len = its length.
+AB_HD int find_start_bidir(const BitImage& im, const TraceStart& st, int max_len, int* len) {
+    WalkState fw{st.x, st.y, st.b}, bw = fw;
+    int nf = 0, ng = 0;
+    for (;;) {
+        walk_forward(fw, neighbours8(im, fw.x, fw.y));
+        nf++;
+        if (same_state(fw, bw)) break;
+        if (is_smaller_trigger(im, fw, neighbours8(im, fw.x, fw.y), st.key)) return TRACE_NOT_START;
+        walk_backward(im, bw);
+        ng++;
+        if (same_state(fw, bw)) break;
+        if (is_smaller_trigger(im, bw, neighbours8(im, bw.x, bw.y), st.key)) return TRACE_NOT_START;
+        if (nf + ng >= max_len) return TRACE_TOO_LONG;
+    }
+    *len = nf + ng;
+    return TRACE_OK;
+}
+
 // Walks the cycle of `st`.  Returns TRACE_OK with the length in *len when `st` is the Suzuki start of its
 // border and the length is < max_len; TRACE_NOT_START when a smaller trigger lies on the cycle;
 // TRACE_TOO_LONG when max_len points were passed without closing.  When `emit` is non-null the points are

@@ -59,39 +59,109 @@ __global__ void k_scan_starts(Batch b) {
     }
 }
 
-__global__ void k_trace(Batch b) {
+// Lane-scheduled walker.  Every lane owns one start candidate at a time and is refilled from a global work
+// counter as soon as it finishes, so a warp never idles behind its longest contour (border lengths range
+// from 2 to max_len).  Phase 1 = bidirectional search for a smaller start on the same cycle
+// (find_start_bidir in ab_trace.cuh, executed STEPS at a time); phase 2 = the Suzuki start of a kept border
+// re-walks it forwards and writes the ordered points into the pool.
+__global__ void __launch_bounds__(128) k_trace(Batch b) {
+    constexpr int STEPS = 8;
+    const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     unsigned long long n_starts = b.cnt->n_starts;
     if (n_starts > b.cap_starts) n_starts = b.cap_starts;
+    int phase = 0;  // 0 idle, 1 search, 2 emit
+    bool exhausted = false;
+    BitImage im = b.bit_image(0);
+    TraceStart st{0, 0, 0, 0};
+    WalkState fw{0, 0, 0}, bw{0, 0, 0};
+    int nf = 0, ng = 0, len = 0, frame = 0;
+    uint32_t* out = nullptr;
+    unsigned int ci = 0;
+    unsigned long long off = 0;
     for (;;) {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(&b.cnt->trace_work, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if ((unsigned long long)base >= n_starts) break;
-        unsigned long long i = (unsigned long long)base + lane;
-        if (i >= n_starts) continue;
-        uint2 rec = b.starts[i];
-        int f = (int)(rec.x & 0x7FFFFFFFu), type = (int)(rec.x >> 31);
-        int x = (int)(rec.y & 0xFFFFu), y = (int)(rec.y >> 16);
-        BitImage im = b.bit_image(f);
-        TraceStart st;
-        if (!make_start(im, type, x, y, st)) continue;  // isolated pixel: a 1-point contour, never kept
-        int len = 0;
-        if (trace_cycle(im, st, b.max_len, &len, nullptr) != TRACE_OK) continue;
-        if (len <= b.min_len || len >= b.max_len) continue;  // src/markerdetector.cpp:517
-        unsigned int ci = atomicAdd(&b.cnt->n_contours, 1u);
-        unsigned long long off = atomicAdd(&b.cnt->pool_used, (unsigned long long)len);
-        if (ci >= b.cap_contours) {
-            atomicOr(&b.cnt->err, ERR_CONTOURS_OVERFLOW);
+        unsigned idle = __ballot_sync(FULL, phase == 0 && !exhausted);
+        if (idle) {
+            unsigned base = 0;
+            int leader = __ffs((int)idle) - 1;
+            if (lane == leader) base = atomicAdd(&b.cnt->trace_work, (unsigned)__popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (phase == 0 && !exhausted) {
+                unsigned long long i = (unsigned long long)base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+                if (i >= n_starts) {
+                    exhausted = true;
+                } else {
+                    uint2 rec = b.starts[i];
+                    frame = (int)(rec.x & 0x7FFFFFFFu);
+                    im = b.bit_image(frame);
+                    if (make_start(im, (int)(rec.x >> 31), (int)(rec.y & 0xFFFFu), (int)(rec.y >> 16), st)) {
+                        fw = WalkState{st.x, st.y, st.b};
+                        bw = fw;
+                        nf = ng = 0;
+                        phase = 1;
+                    }  // else: isolated pixel, a 1-point contour that is never kept
+                }
+            }
+        }
+        if (__ballot_sync(FULL, phase != 0) == 0) {
+            if (__ballot_sync(FULL, !exhausted) == 0) break;
             continue;
         }
-        if (off + (unsigned long long)len > b.cap_pool) {
-            atomicOr(&b.cnt->err, ERR_POOL_OVERFLOW);
-            b.contours[ci] = ContourRec{(uint32_t)f, 0u, 0u, (uint32_t)st.key};
-            continue;
+        if (phase == 1) {
+            for (int r = 0; r < STEPS; r++) {
+                bool closed = false, dead = false;
+                walk_forward(fw, neighbours8(im, fw.x, fw.y));
+                nf++;
+                if (same_state(fw, bw)) {
+                    closed = true;
+                } else if (is_smaller_trigger(im, fw, neighbours8(im, fw.x, fw.y), st.key)) {
+                    dead = true;
+                } else {
+                    walk_backward(im, bw);
+                    ng++;
+                    if (same_state(fw, bw)) closed = true;
+                    else if (is_smaller_trigger(im, bw, neighbours8(im, bw.x, bw.y), st.key)) dead = true;
+                    else if (nf + ng >= b.max_len) dead = true;  // too long: dropped by :517 anyway
+                }
+                if (closed) {
+                    len = nf + ng;
+                    if (len <= b.min_len || len >= b.max_len) {  // src/markerdetector.cpp:517
+                        phase = 0;
+                        break;
+                    }
+                    ci = atomicAdd(&b.cnt->n_contours, 1u);
+                    off = atomicAdd(&b.cnt->pool_used, (unsigned long long)len);
+                    if (ci >= b.cap_contours) {
+                        atomicOr(&b.cnt->err, ERR_CONTOURS_OVERFLOW);
+                        phase = 0;
+                    } else if (off + (unsigned long long)len > b.cap_pool) {
+                        atomicOr(&b.cnt->err, ERR_POOL_OVERFLOW);
+                        b.contours[ci] = ContourRec{(uint32_t)frame, 0u, 0u, (uint32_t)st.key};
+                        phase = 0;
+                    } else {
+                        out = b.pool + off;
+                        fw = WalkState{st.x, st.y, st.b};
+                        nf = 0;
+                        phase = 2;
+                    }
+                    break;
+                }
+                if (dead) {
+                    phase = 0;
+                    break;
+                }
+            }
+        } else if (phase == 2) {
+            for (int r = 0; r < 2 * STEPS; r++) {
+                out[nf] = (uint32_t)fw.x | ((uint32_t)fw.y << 16);
+                walk_forward(fw, neighbours8(im, fw.x, fw.y));
+                if (++nf == len) {
+                    b.contours[ci] = ContourRec{(uint32_t)frame, (uint32_t)off, (uint32_t)len, (uint32_t)st.key};
+                    phase = 0;
+                    break;
+                }
+            }
         }
-        trace_cycle(im, st, b.max_len + 1, &len, b.pool + off);
-        b.contours[ci] = ContourRec{(uint32_t)f, (uint32_t)off, (uint32_t)len, (uint32_t)st.key};
     }
 }
 

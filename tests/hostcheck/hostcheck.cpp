@@ -46,7 +46,7 @@ int hc_find_contours(const uint8_t* img, int W, int H, int min_len, int max_len,
                 continue;
             }
             int len = 0;
-            int r = ab::trace_cycle(im, st, 1 << 30, &len, nullptr);
+            int r = ab::find_start_bidir(im, st, 1 << 30, &len);
             if (r != ab::TRACE_OK) continue;
             total++;
             if (len <= min_len || len >= max_len) continue;
@@ -187,4 +187,56 @@ void hc_undistort_px(const float* K, const float* D, const float* in, int n, flo
 }
 
 void hc_rotate_x_axis(double* rvec) { ab::rotate_x_axis(rvec); }
+}
+
+extern "C" {
+// diagnostic: total walk steps over all start candidates for the forward-only and the bidirectional search
+void hc_walk_cost(const uint8_t* img, int W, int H, int max_len, long long* fwd_steps, long long* bidir_steps, long long* kept_points) {
+    std::vector<uint32_t> bits(ab::bit_image_words(W, H));
+    hc_pack_bits(img, W, H, bits.data());
+    ab::BitImage im{bits.data(), ab::bit_words_per_row(W), W, H};
+    long long fs = 0, bs = 0, kp = 0;
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            uint32_t nb = ab::neighbours8(im, x, y);
+            bool fg = img[(size_t)y * W + x] != 0;
+            int type = -1;
+            if (fg && ab::is_outer_candidate(nb)) type = 0;
+            else if (!fg && (nb & (1u << 4)) && (nb & (1u << 2))) type = 1;
+            if (type < 0) continue;
+            ab::TraceStart st;
+            if (!ab::make_start(im, type, x, y, st)) continue;
+            {
+                int xx = st.x, yy = st.y, b = st.b, n = 0;
+                for (;;) {
+                    uint32_t nbb = ab::neighbours8(im, xx, yy);
+                    ab::WalkState s{xx, yy, b};
+                    if (n > 0 && ab::is_smaller_trigger(im, s, nbb, st.key)) break;
+                    n++;
+                    ab::walk_forward(s, nbb);
+                    xx = s.x; yy = s.y; b = s.b;
+                    if (xx == st.x && yy == st.y && b == st.b) break;
+                    if (n >= max_len) break;
+                }
+                fs += n;
+            }
+            {
+                ab::WalkState fw{st.x, st.y, st.b}, bw = fw;
+                int nf = 0, ng = 0;
+                bool ok = false;
+                for (;;) {
+                    ab::walk_forward(fw, ab::neighbours8(im, fw.x, fw.y)); nf++;
+                    if (ab::same_state(fw, bw)) { ok = true; break; }
+                    if (ab::is_smaller_trigger(im, fw, ab::neighbours8(im, fw.x, fw.y), st.key)) break;
+                    ab::walk_backward(im, bw); ng++;
+                    if (ab::same_state(fw, bw)) { ok = true; break; }
+                    if (ab::is_smaller_trigger(im, bw, ab::neighbours8(im, bw.x, bw.y), st.key)) break;
+                    if (nf + ng >= max_len) break;
+                }
+                bs += nf + ng;
+                if (ok) kp += nf + ng;
+            }
+        }
+    *fwd_steps = fs; *bidir_steps = bs; *kept_points = kp;
+}
 }

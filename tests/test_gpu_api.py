@@ -1,0 +1,89 @@
+"""-m gpu: the public workers and the error behaviour of the MarkerDetector mirror (markerdetector.h:129-280)."""
+import numpy as np
+import pytest
+
+from conftest import POSE_RTOL, intrinsics, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def det(built):
+    from aruco_b200 import MarkerDetector
+    return MarkerDetector(0)
+
+
+def test_defaults_and_setters_mirror_the_reference(built):
+    from aruco_b200 import ArucoError, MarkerDetector
+    d = MarkerDetector(0)
+    assert d.getThresholdMethod() == MarkerDetector.ADPT_THRES and d.getThresholdParams() == (7.0, 7.0)
+    assert d.getCornerRefinementMethod() == MarkerDetector.LINES and d.getWarpSize() == 56
+    mn, mx = d.getMinMaxSize()
+    assert abs(mn - 0.04) < 1e-7 and mx == 0.5
+    d.setDesiredSpeed(0)
+    assert (d.getWarpSize(), d.getCornerRefinementMethod()) == (56, MarkerDetector.SUBPIX)
+    d.setDesiredSpeed(2)
+    assert (d.getWarpSize(), d.getCornerRefinementMethod()) == (28, MarkerDetector.NONE)
+    d.setDesiredSpeed(3)  # passes the clamp and changes nothing
+    assert (d.getWarpSize(), d.getDesiredSpeed()) == (28, 3)
+    d.setDesiredSpeed(7)
+    assert d.getDesiredSpeed() == 2
+    d.enableLockedCornersMethod(False)
+    for bad in ((0, 0.5), (0.5, 0.4), (0.1, 1.5)):  # CV_Assert in setMinMaxSize (cpp:1031-1038)
+        with pytest.raises(ArucoError):
+            d.setMinMaxSize(*bad)
+    with pytest.raises(ArucoError):  # CV_Assert(val >= 10) in setWarpSize (cpp:1047-1051)
+        d.setWarpSize(9)
+    assert d.getWarpSize() == 28
+    with pytest.raises(ArucoError):  # CV_Assert(grey.type()==CV_8UC1) (cpp:644)
+        d.thresHold(1, np.zeros((10, 10), np.float32))
+    with pytest.raises(ArucoError):  # CV_Assert(points.size()==4) (cpp:685)
+        d.warp(np.zeros((20, 20), np.uint8), 56, [[0, 0], [1, 0], [1, 1]])
+
+
+@pytest.mark.parametrize("method,p1,p2", [(1, 7, 7), (1, -1, -1), (1, 2, 7), (1, 8, 6.5), (1, 21, 7), (1, 35, 3), (1, 61, 0), (0, 100, 0), (0, 127.5, 0)])
+def test_threshold_worker_bit_exact(det, frames, method, p1, p2):
+    from oracle import native
+    import ctypes as C
+    lib = native.load()
+    rng = np.random.default_rng(1)
+    for img in (frames["hrm"], rng.integers(0, 256, (97, 131), dtype=np.uint8), rng.integers(0, 256, (480, 1000), dtype=np.uint8)):
+        img = np.ascontiguousarray(img)
+        got = det.thresHold(method, img, p1, p2)
+        q1, q2 = (7.0 if p1 == -1 else p1), (7.0 if p2 == -1 else p2)
+        ref = np.empty_like(img)
+        lib.orc_threshold(img.ctypes.data_as(C.c_void_p), img.shape[1], img.shape[0], method, float(q1), float(q2), ref.ctypes.data_as(C.c_void_p))
+        assert (got == ref).all()
+
+
+def test_detect_rectangles_and_warp_workers(det, frames):
+    from oracle import native
+    from oracle.cv2_oracle import Params
+    ref = native.detect(frames["board"], Params())
+    quads = det.detectRectangles(ref["thres"])
+    assert quads.shape == ref["quads"].shape and (quads == ref["quads"]).all()
+    for i in range(len(quads)):
+        assert (det.warp(frames["board"], 56, quads[i]) == ref["canon"][i]).all()
+
+
+def test_calculate_extrinsics_worker(det, expected):
+    """Marker::calculateExtrinsics (marker.cpp:112-125) on the golden corners vs the golden poses."""
+    from aruco_b200 import ArucoError, Marker
+    K, D = intrinsics(expected, "single")
+    gold = expected["goldens"]["single"]["markers"]
+    ms = det.calculateExtrinsics([Marker(g["id"], g["corners"]) for g in gold], 1.0, K, D)
+    for m, g in zip(ms, gold):
+        assert rel_err(m.Rvec, g["rvec"]) < POSE_RTOL and rel_err(m.Tvec, g["tvec"]) < POSE_RTOL and m.ssize == 1.0
+    with pytest.raises(ArucoError):  # CV_Assert(markerSizeMeters > 0) (marker.cpp:114)
+        det.calculateExtrinsics(ms, -1.0, K, D)
+
+
+def test_hrm_requires_dictionary(built):
+    from aruco_b200 import ArucoError, HighlyReliableMarkers, MarkerDetector
+    saved = HighlyReliableMarkers._dict
+    HighlyReliableMarkers._dict = None
+    try:
+        with pytest.raises(ArucoError):
+            MarkerDetector(0).setMakerDetectorFunction(HighlyReliableMarkers.detect)
+    finally:
+        HighlyReliableMarkers._dict = saved
