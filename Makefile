@@ -7,7 +7,7 @@ NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -
 LIB       := aruco_b200/lib/libaruco_b200.so
 CSRC      := $(wildcard aruco_b200/csrc/*.cu aruco_b200/csrc/*.cuh) include/aruco_b200.h
 
-all: $(LIB) oracle hostcheck
+all: $(LIB) oracle hostcheck facade
 
 $(LIB): $(CSRC)
 	@mkdir -p aruco_b200/lib
@@ -23,7 +23,12 @@ tests/_build/libhostcheck.so: tests/hostcheck/hostcheck.cpp $(wildcard aruco_b20
 	@mkdir -p tests/_build
 	$(CXX) -O2 -ffp-contract=off -shared -fPIC -o $@ tests/hostcheck/hostcheck.cpp
 
+facade: tests/_build/aruco_simple
+tests/_build/aruco_simple: tests/cpp/aruco_simple.cpp include/aruco/markerdetector.hpp $(LIB)
+	@mkdir -p tests/_build
+	$(CXX) -std=c++14 -O1 -o $@ tests/cpp/aruco_simple.cpp -Laruco_b200/lib -laruco_b200 -Wl,-rpath,'$$ORIGIN/../../aruco_b200/lib'
+
 clean:
 	rm -rf aruco_b200/lib/*.so oracle/_build tests/_build
 
-.PHONY: all oracle hostcheck clean
+.PHONY: all oracle hostcheck facade clean

@@ -537,8 +537,8 @@ static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t f
         return set_err(ctx, AB_E_INVALID, "warp size too small for the dictionary");
     if (P.corner_method == AB_CORNER_SUBPIX && ((int)P.thres_param1 < 1 || (int)P.thres_param1 > 24))
         return set_err(ctx, AB_E_INVALID, "SUBPIX window %d outside 1..24", (int)P.thres_param1);
-    if (P.corner_method == AB_CORNER_HARRIS || P.locked_corners)
-        return set_err(ctx, AB_E_INVALID, "HARRIS refinement / locked corners are not implemented yet");
+    if (P.locked_corners && ((int)P.thres_param1 < 1 || (int)P.thres_param1 > 24))
+        return set_err(ctx, AB_E_INVALID, "locked-corner window %d outside 1..24", (int)P.thres_param1);
     Batch b;
     fill_batch(ctx, b, dgrey, row, frame, n, K, D, marker_size);
     cudaStream_t st = ctx->stream;
@@ -596,8 +596,17 @@ static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t f
     }
     if (ctx->timing) cudaEventRecord(ctx->kev[6], st);
     if (ctx->timing) cudaEventRecord(ctx->ev[3], st);
+    if (P.locked_corners && (P.corner_method == AB_CORNER_HARRIS || P.corner_method == AB_CORNER_SUBPIX)) {
+        // findCornerMaxima before the refiner (src/markerdetector.cpp:397-398)
+        int w = b.subpix_win;
+        size_t smem = (size_t)5 * (2 * w) * (2 * w) * sizeof(float);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_corner_maxima, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_corner_maxima<<<dim3(4 * b.cap_c, n), 64, smem, st>>>(b);
+    }
     if (P.corner_method == AB_CORNER_LINES) {
         k_refine_lines<<<gcand, 128, 0, st>>>(b);
+    } else if (P.corner_method == AB_CORNER_HARRIS) {
+        k_refine_harris<<<dim3(b.cap_c, n), 128, 0, st>>>(b);
     } else if (P.corner_method == AB_CORNER_SUBPIX) {
         int w = b.subpix_win, pw = 2 * w + 3;
         size_t smem = (size_t)4 * pw * pw * sizeof(float);

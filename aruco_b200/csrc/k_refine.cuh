@@ -212,4 +212,175 @@ __global__ void __launch_bounds__(128) k_refine_subpix(Batch b) {
     }
 }
 
+__device__ __forceinline__ int reflect101(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+    return p;
+}
+
+// findCornerMaxima ("locked corners", src/markerdetector.cpp:157-199): one CTA per corner.
+// cornerHarris(blockSize 3, ksize 3, k 0.04) over the +-wsize region around the corner (the Sobel of the C++
+// ROI reads the parent image, the 3x3 box sum reflects at the ROI border), 4x4 block sums over the interior,
+// arg-max of the centre-weighted response (first strict maximum in raster order).
+__global__ void __launch_bounds__(64) k_corner_maxima(Batch b) {
+    extern __shared__ float s_buf[];
+    __shared__ unsigned long long s_best;
+    const int f = blockIdx.y, corner = blockIdx.x, t = threadIdx.x;
+    const int ci = corner >> 2, k = corner & 3;
+    if (ci >= (int)b.n_cands[f]) return;
+    CandRec* cand = b.cands + (size_t)f * b.cap_c + ci;
+    if (cand->id < 0) return;
+    const int wsize = b.subpix_win;
+    const float cxf = cand->refined[2 * k], cyf = cand->refined[2 * k + 1];
+    const int x0 = max(0, (int)(cxf - wsize)), y0 = max(0, (int)(cyf - wsize));
+    const int x1 = min(b.W, (int)(cxf + wsize)), y1 = min(b.H, (int)(cyf + wsize));
+    const int rw = x1 - x0, rh = y1 - y0;
+    if (rw <= 0 || rh <= 0) {
+        if (t == 0) {
+            cand->refined[2 * k] = -1.f + x0;
+            cand->refined[2 * k + 1] = -1.f + y0;
+        }
+        return;
+    }
+    const int n = rw * rh;
+    float *ca = s_buf, *cb = ca + n, *cc = cb + n, *harr = cc + n, *hs = harr + n;
+    const uint8_t* img = b.grey + (size_t)f * b.grey_frame;
+    const float scale = (float)(1.0 / (4.0 * 3.0 * 255.0)), c2 = (float)(2.0 * (1.0 / (4.0 * 3.0 * 255.0)));
+    if (t == 0) s_best = 0ull;
+    for (int i = t; i < n; i += blockDim.x) {
+        int y = i / rw, x = i - y * rw, gx = x0 + x, gy = y0 + y;
+        int xm = reflect101(gx - 1, b.W), xc = gx, xp = reflect101(gx + 1, b.W);
+        const uint8_t* rm = img + (size_t)reflect101(gy - 1, b.H) * b.grey_row;
+        const uint8_t* r0 = img + (size_t)gy * b.grey_row;
+        const uint8_t* rp = img + (size_t)reflect101(gy + 1, b.H) * b.grey_row;
+        float d_m = (float)rm[xp] - (float)rm[xm], d_0 = (float)r0[xp] - (float)r0[xm], d_p = (float)rp[xp] - (float)rp[xm];
+        float dx = c2 * d_0 + scale * (d_m + d_p);
+        float s_m = c2 * (float)rm[xc] + scale * ((float)rm[xm] + (float)rm[xp]);
+        float s_p = c2 * (float)rp[xc] + scale * ((float)rp[xm] + (float)rp[xp]);
+        float dy = s_p - s_m;
+        ca[i] = dx * dx;
+        cb[i] = dx * dy;
+        cc[i] = dy * dy;
+    }
+    __syncthreads();
+    for (int i = t; i < n; i += blockDim.x) {
+        int y = i / rw, x = i - y * rw;
+        double sa = 0, sb = 0, sc = 0;
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+                int j = reflect101(y + dy, rh) * rw + reflect101(x + dx, rw);
+                sa += ca[j];
+                sb += cb[j];
+                sc += cc[j];
+            }
+        float a = (float)sa, bq = (float)sb, c = (float)sc;
+        harr[i] = (float)((double)(a * c - bq * bq) - 0.04 * (double)(a + c) * (double)(a + c));
+    }
+    __syncthreads();
+    unsigned long long best = 0ull;  // (float bits of the positive response << 32) | ~raster index
+    const float ccx = (float)(rw / 2), ccy = (float)(rh / 2), den = (float)(rw / 2 + rh / 2);
+    for (int i = t; i < n; i += blockDim.x) {
+        int y = i / rw, x = i - y * rw;
+        float h = harr[i];
+        if (y >= 4 && y < rh - 4 && x >= 4 && x < rw - 4) {
+            double sum = 0;
+            for (int dy = 0; dy < 4; dy++)
+                for (int dx = 0; dx < 4; dx++) sum += harr[(y + dy) * rw + x + dx];
+            h = (float)sum;
+        }
+        hs[i] = h;
+        float d = (float)(fabs((double)(ccx - (float)x)) + fabs((double)(ccy - (float)y))) / den;
+        float w = (float)(1. - (double)d);
+        float v = w * h;
+        if (v > 0.f) {
+            unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+            if (key > best) best = key;
+        }
+    }
+    if (best) atomicMax(&s_best, best);
+    __syncthreads();
+    if (t == 0) {
+        float bx = -1.f, by = -1.f;
+        if (s_best) {
+            int i = (int)(0xFFFFFFFFu - (unsigned)(s_best & 0xFFFFFFFFull));
+            by = (float)(i / rw);
+            bx = (float)(i - (i / rw) * rw);
+        }
+        cand->refined[2 * k] = bx + (float)x0;
+        cand->refined[2 * k + 1] = by + (float)y0;
+    }
+}
+
+// HARRIS mode: SubPixelCorner::RefineCorner (src/subpixelcorner.cpp:70-189), one warp per corner.  Reproduces
+// the reference's quirks: exactly one iteration, `D` (never assigned) in the y update, 8-bit
+// getRectSubPix patch (16-bit fixed-point bilinear weights) before the 3x3 Sobel.
+__global__ void __launch_bounds__(128) k_refine_harris(Batch b) {
+    __shared__ int s_patch[4][17 * 17];
+    const int f = blockIdx.y, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int corner = blockIdx.x * (blockDim.x >> 5) + wib;
+    const int ci = corner >> 2, k = corner & 3;
+    if (ci >= (int)b.n_cands[f]) return;
+    CandRec* cand = b.cands + (size_t)f * b.cap_c + ci;
+    if (cand->id < 0) return;
+    const int win = 15, S = 17;
+    const float ex = cand->refined[2 * k], ey = cand->refined[2 * k + 1];
+    if (ex < 0 || ey < 0 || ey > b.H || ey > b.W) return;  // (:87-89, the reference compares y with the width too)
+    int* patch = s_patch[wib];
+    const uint8_t* img = b.grey + (size_t)f * b.grey_frame;
+    {
+        float cx = ex - (float)(S - 1) * 0.5f, cy = ey - (float)(S - 1) * 0.5f;
+        int ipx = (int)floorf(cx), ipy = (int)floorf(cy);
+        float a = cx - (float)ipx, bb = cy - (float)ipy;
+        int a11 = __float2int_rn((1.f - a) * (1.f - bb) * 65536.f), a12 = __float2int_rn(a * (1.f - bb) * 65536.f);
+        int a21 = __float2int_rn((1.f - a) * bb * 65536.f), a22 = __float2int_rn(a * bb * 65536.f);
+        for (int i = lane; i < S * S; i += 32) {
+            int py = i / S, px = i - py * S;
+            int xx0 = min(max(ipx + px, 0), b.W - 1), xx1 = min(max(ipx + px + 1, 0), b.W - 1);
+            int yy0 = min(max(ipy + py, 0), b.H - 1), yy1 = min(max(ipy + py + 1, 0), b.H - 1);
+            int v = (int)img[(size_t)yy0 * b.grey_row + xx0] * a11 + (int)img[(size_t)yy0 * b.grey_row + xx1] * a12 +
+                    (int)img[(size_t)yy1 * b.grey_row + xx0] * a21 + (int)img[(size_t)yy1 * b.grey_row + xx1] * a22;
+            patch[i] = (v + (1 << 15)) >> 16;
+        }
+    }
+    __syncwarp();
+    const double coeff = 1. / (win * win);
+    double A = 0, B = 0, C = 0, E = 0, F = 0;
+    for (int i = lane; i < win * win; i += 32) {
+        int yy = i / win, xx = i - yy * win;  // window position 0..14  (patch index +1)
+        int ly = yy - win / 2, lx = xx - win / 2;
+        const int* q = patch + (yy + 1) * S + (xx + 1);
+        float dx = (float)((q[-S + 1] - q[-S - 1]) + 2 * (q[1] - q[-1]) + (q[S + 1] - q[S - 1]));
+        float dy = (float)((q[S - 1] - q[-S - 1]) + 2 * (q[S] - q[-S]) + (q[S + 1] - q[-S + 1]));
+        float mxv = (float)exp(-(double)(lx * lx) * coeff), myv = (float)exp(-(double)(ly * ly) * coeff);
+        double val = (double)(mxv * myv);
+        double dxx = (double)(dx * dx) * val, dyy = (double)(dy * dy) * val, dxy = (double)(dx * dy) * val;
+        A += dxx;
+        B += dxy;
+        E += dyy;
+        C += dxx * lx + dxy * ly;
+        F += dxy * lx + dyy * ly;
+    }
+    A = warp_sum_d(A);
+    B = warp_sum_d(B);
+    C = warp_sum_d(C);
+    E = warp_sum_d(E);
+    F = warp_sum_d(F);
+    if (lane == 0) {
+        const double D = 0;  // never assigned in the reference
+        double det = A * E - B * B;
+        float nx = ex, ny = ey;
+        if (fabs(det) > DBL_EPSILON * DBL_EPSILON) {
+            det = 1.0 / det;
+            nx = (float)((double)ex + ((C * E) - (B * F)) * det);
+            ny = (float)((double)ey + ((A * F) - (C * D)) * det);
+        }
+        if (fabs((double)ex - (double)nx) > win || fabs((double)ey - (double)ny) > win) {
+            nx = ex;
+            ny = ey;
+        }
+        cand->refined[2 * k] = nx;
+        cand->refined[2 * k + 1] = ny;
+    }
+}
+
 }  // namespace ab

@@ -764,6 +764,120 @@ void corner_subpix(const uint8_t* img, int W, int H, Pt2f* pt, int w) {
     *pt = cI;
 }
 
+// cv::getRectSubPix for 8u -> 8u (generic C++ path: 16-bit fixed-point bilinear weights, replicated border)
+void rect_subpix_u8(const uint8_t* img, int W, int H, float cx, float cy, int S, int* out) {
+    cx -= (S - 1) * 0.5f;
+    cy -= (S - 1) * 0.5f;
+    int ipx = (int)floorf(cx), ipy = (int)floorf(cy);
+    float a = cx - ipx, b = cy - ipy;
+    int a11 = (int)lrintf((1.f - a) * (1.f - b) * 65536.f), a12 = (int)lrintf(a * (1.f - b) * 65536.f);
+    int a21 = (int)lrintf((1.f - a) * b * 65536.f), a22 = (int)lrintf(a * b * 65536.f);
+    for (int i = 0; i < S; i++)
+        for (int j = 0; j < S; j++) {
+            int x0 = std::min(std::max(ipx + j, 0), W - 1), x1 = std::min(std::max(ipx + j + 1, 0), W - 1);
+            int y0 = std::min(std::max(ipy + i, 0), H - 1), y1 = std::min(std::max(ipy + i + 1, 0), H - 1);
+            int v = img[(size_t)y0 * W + x0] * a11 + img[(size_t)y0 * W + x1] * a12 + img[(size_t)y1 * W + x0] * a21 +
+                    img[(size_t)y1 * W + x1] * a22;
+            out[i * S + j] = (v + (1 << 15)) >> 16;
+        }
+}
+
+// SubPixelCorner::RefineCorner (src/subpixelcorner.cpp:70-189) with its quirks: one iteration,
+// D == 0 in the y update, u8 patch before Sobel.
+void harris_refine(const uint8_t* img, int W, int H, Pt2f* pt) {
+    const int win = 15, S = 17;
+    float mx[15];
+    double coeff = 1. / (win * win);
+    for (int i = -win / 2, k = 0; i <= win / 2; i++, k++) mx[k] = (float)exp(-i * i * coeff);
+    Pt2f est = *pt;
+    if (est.x < 0 || est.y < 0 || est.y > H || est.y > W) return;
+    int patch[17 * 17];
+    rect_subpix_u8(img, W, H, est.x, est.y, S, patch);
+    double A = 0, B = 0, C = 0, D = 0, E = 0, F = 0;
+    for (int i = 1; i <= win; i++) {
+        int ly = i - win / 2 - 1;
+        for (int j = 1; j <= win; j++) {
+            int lx = j - win / 2 - 1;
+            const int* q = patch + i * S + j;
+            float dx = (float)((q[-S + 1] - q[-S - 1]) + 2 * (q[1] - q[-1]) + (q[S + 1] - q[S - 1]));
+            float dy = (float)((q[S - 1] - q[-S - 1]) + 2 * (q[S] - q[-S]) + (q[S + 1] - q[-S + 1]));
+            double val = (float)(mx[lx + win / 2] * mx[ly + win / 2]);
+            double dxx = (float)(dx * dx) * val, dyy = (float)(dy * dy) * val, dxy = (float)(dx * dy) * val;
+            A += dxx; B += dxy; E += dyy;
+            C += dxx * lx + dxy * ly;
+            F += dxy * lx + dyy * ly;
+        }
+    }
+    double det = A * E - B * B;
+    Pt2f cur = est;
+    if (fabs(det) > DBL_EPSILON * DBL_EPSILON) {
+        det = 1.0 / det;
+        est.x = (float)(cur.x + ((C * E) - (B * F)) * det);
+        est.y = (float)(cur.y + ((A * F) - (C * D)) * det);
+    }
+    if (fabs(pt->x - est.x) > win || fabs(pt->y - est.y) > win) est = *pt;
+    *pt = est;
+}
+
+inline int reflect101(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+    return p;
+}
+
+// findCornerMaxima (src/markerdetector.cpp:157-199): cornerHarris(3,3,0.04) on the +-wsize region (the Sobel
+// of a C++ ROI reads the parent image outside the ROI; the 3x3 box sum reflects at the ROI border), 4x4 block
+// sums over the interior, maximum of the centre-weighted response.
+void find_corner_maxima(const uint8_t* grey, int W, int H, Pt2f* pt, int wsize) {
+    int x0 = std::max(0, (int)(pt->x - wsize)), y0 = std::max(0, (int)(pt->y - wsize));
+    int x1 = std::min(W, (int)(pt->x + wsize)), y1 = std::min(H, (int)(pt->y + wsize));
+    int rw = x1 - x0, rh = y1 - y0;
+    if (rw <= 0 || rh <= 0) { *pt = Pt2f{-1.f + x0, -1.f + y0}; return; }
+    const float scale = (float)(1.0 / (4.0 * 3.0 * 255.0)), c2 = (float)(2.0 * (1.0 / (4.0 * 3.0 * 255.0)));
+    auto px = [&](int x, int y) { return (float)grey[(size_t)reflect101(y, H) * W + reflect101(x, W)]; };
+    std::vector<float> ca((size_t)rw * rh), cb((size_t)rw * rh), cc((size_t)rw * rh), harr((size_t)rw * rh);
+    for (int y = 0; y < rh; y++)
+        for (int x = 0; x < rw; x++) {
+            int gx = x0 + x, gy = y0 + y;
+            float r_m = px(gx + 1, gy - 1) - px(gx - 1, gy - 1), r_0 = px(gx + 1, gy) - px(gx - 1, gy), r_p = px(gx + 1, gy + 1) - px(gx - 1, gy + 1);
+            float dx = c2 * r_0 + scale * (r_m + r_p);
+            float s_m = c2 * px(gx, gy - 1) + scale * (px(gx - 1, gy - 1) + px(gx + 1, gy - 1));
+            float s_p = c2 * px(gx, gy + 1) + scale * (px(gx - 1, gy + 1) + px(gx + 1, gy + 1));
+            float dy = s_p - s_m;
+            ca[y * rw + x] = dx * dx; cb[y * rw + x] = dx * dy; cc[y * rw + x] = dy * dy;
+        }
+    for (int y = 0; y < rh; y++)
+        for (int x = 0; x < rw; x++) {
+            double sa = 0, sb = 0, sc = 0;
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    int yy = reflect101(y + dy, rh), xx = reflect101(x + dx, rw);
+                    sa += ca[yy * rw + xx]; sb += cb[yy * rw + xx]; sc += cc[yy * rw + xx];
+                }
+            float a = (float)sa, b = (float)sb, c = (float)sc;
+            harr[y * rw + x] = (float)(a * c - b * b - 0.04 * (a + c) * (a + c));
+        }
+    std::vector<float> hs(harr);
+    for (int y = 4; y < rh - 4; y++)
+        for (int x = 4; x < rw - 4; x++) {
+            double sum = 0;
+            for (int dy = 0; dy < 4; dy++)
+                for (int dx = 0; dx < 4; dx++) sum += harr[(y + dy) * rw + x + dx];
+            hs[y * rw + x] = (float)sum;
+        }
+    float bx = -1, by = -1;
+    float ccx = (float)(rw / 2), ccy = (float)(rh / 2), den = (float)(rw / 2 + rh / 2);
+    double maxv = 0;
+    for (int i = 0; i < rh; i++)
+        for (int x = 0; x < rw; x++) {
+            float d = (float)(fabs(ccx - x) + fabs(ccy - i)) / den;
+            float w = (float)(1. - d);
+            float v = w * hs[i * rw + x];
+            if (v > maxv) { maxv = v; bx = (float)x; by = (float)i; }
+        }
+    *pt = Pt2f{bx + x0, by + y0};
+}
+
 // ------------------------------------------------------------------------------------------------
 // cv::solvePnP(ITERATIVE), 4 coplanar points: homography init + damped Gauss-Newton on the reprojection
 // error with forward-difference Jacobian
@@ -1083,7 +1197,7 @@ int orc_solve_pnp(const float* K, const float* D, const float* corners, float si
 // -2 for unsupported settings).
 int orc_detect(const uint8_t* grey, int W, int H, const orc_params* P, const float* K, const float* D, float marker_size,
                const orc_dict* dict, orc_marker* out, int cap, orc_debug* dbg) {
-    if (P->thres_method == 2 || P->corner_method == 1 || P->locked_corners) return -2;
+    if (P->thres_method == 2) return -2;
     std::vector<uint8_t> thres((size_t)W * H);
     orc_threshold(grey, W, H, P->thres_method, P->p1, P->p2, thres.data());
     if (P->erosion) {
@@ -1138,10 +1252,14 @@ int orc_detect(const uint8_t* grey, int W, int H, const orc_params* P, const flo
             det.push_back(d);
         }
     }
-    if (!det.empty() && P->corner_method == 2) {
+    if (!det.empty() && (P->corner_method == 1 || P->corner_method == 2)) {  // :388-410
         int w = (int)P->p1;
         for (auto& d : det)
-            for (int k = 0; k < 4; k++) corner_subpix(grey, W, H, &d.c[k], w);
+            for (int k = 0; k < 4; k++) {
+                if (P->locked_corners) find_corner_maxima(grey, W, H, &d.c[k], w);
+                if (P->corner_method == 1) harris_refine(grey, W, H, &d.c[k]);
+                else corner_subpix(grey, W, H, &d.c[k], w);
+            }
     }
     std::stable_sort(det.begin(), det.end(), [](const Det& a, const Det& b) { return a.id < b.id; });
     std::vector<char> rm(det.size(), 0);

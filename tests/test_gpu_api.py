@@ -87,3 +87,28 @@ def test_hrm_requires_dictionary(built):
             MarkerDetector(0).setMakerDetectorFunction(HighlyReliableMarkers.detect)
     finally:
         HighlyReliableMarkers._dict = saved
+
+
+def test_cpp_facade_aruco_simple(built, frames, expected, tmp_path):
+    """The header-only C++ facade (include/aruco/markerdetector.hpp): a headless utils/aruco_simple.cpp on the
+    reference's testdata/single frame must print the golden markers."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "tests", "_build", "aruco_simple")
+    assert os.path.exists(exe)
+    raw = tmp_path / "single.raw"
+    frames["single"].tofile(str(raw))
+    K, D = intrinsics(expected, "single")
+    args = [exe, str(raw), "640", "480", repr(float(K[0, 0])), repr(float(K[1, 1])), repr(float(K[0, 2])), repr(float(K[1, 2]))]
+    args += [repr(float(d)) for d in D] + ["1.0"]
+    out = subprocess.run(args, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    rows = [l.split() for l in out.stdout.strip().splitlines()]
+    gold = expected["goldens"]["single"]["markers"]
+    assert [int(r[0]) for r in rows] == [g["id"] for g in gold]
+    for r, g in zip(rows, gold):
+        c = np.array([float(v) for v in r[1:9]]).reshape(4, 2)
+        assert np.abs(c - np.array(g["corners"])).max() < 0.01 and int(r[9]) == 1
+        assert np.abs(np.array([float(v) for v in r[10:13]]) - np.array(g["rvec"])).max() < 1e-4
+        assert np.abs(np.array([float(v) for v in r[13:16]]) - np.array(g["tvec"])).max() < 1e-4

@@ -297,3 +297,38 @@ def test_capacity_overflow_is_an_error_not_a_truncation(built, frames):
     assert e.value.code == -3
     d.reserve(640, 480, 1)
     assert len(d.detect(frames["board"])) == 24
+
+
+@pytest.mark.parametrize("name,kw", [("single", dict(corner_method=1)), ("board", dict(corner_method=1)),
+                                     ("chessboard", dict(corner_method=2, locked_corners=True)),
+                                     ("chessboard", dict(corner_method=1, locked_corners=True)),
+                                     ("single", dict(corner_method=2, locked_corners=True, p1=9))])
+def test_harris_and_locked_corner_modes(det, frames, expected, name, kw):
+    """HARRIS refinement (SubPixelCorner::RefineCorner, subpixelcorner.cpp:70-189) and enableLockedCornersMethod
+    (findCornerMaxima, markerdetector.cpp:157-199) against the oracle."""
+    P = P_(**kw)
+    configure(det, P)
+    det.enableLockedCornersMethod(bool(kw.get("locked_corners")))
+    det.setCornerRefinementMethod(P.corner_method)
+    K, D = intrinsics(expected, name)
+    try:
+        check_frame(det, frames[name], P, K, D, 1.0)
+    finally:
+        det.enableLockedCornersMethod(False)
+        det.setCornerRefinementMethod(3)
+
+
+def test_synthetic_1080p_locked_corners_and_harris(det):
+    from aruco_b200 import synth
+    g, _ = synth.render_frame(1920, 1080, 50, 21, 2.0)
+    K, D = synth.camera_for(1920, 1080)
+    for kw in (dict(corner_method=1), dict(corner_method=2, locked_corners=True)):
+        P = P_(**kw)
+        configure(det, P)
+        det.enableLockedCornersMethod(bool(kw.get("locked_corners")))
+        det.setCornerRefinementMethod(P.corner_method)
+        try:
+            check_frame(det, g, P, K, D, 0.05)
+        finally:
+            det.enableLockedCornersMethod(False)
+            det.setCornerRefinementMethod(3)

@@ -121,3 +121,16 @@ def test_native_oracle_equals_cv2_oracle_synthetic_1080p(built):
         assert rel_err(x["rvec"], rv.ravel()) < POSE_RTOL and rel_err(x["tvec"], tv.ravel()) < POSE_RTOL
         direct += rel_err(x["rvec"], y["rvec"]) < POSE_RTOL and rel_err(x["tvec"], y["tvec"]) < POSE_RTOL
     assert direct >= 0.85 * len(a["markers"])
+
+
+@pytest.mark.parametrize("name,kw", [("single", dict(corner_method=1)), ("board", dict(corner_method=1)),
+                                     ("chessboard", dict(corner_method=2, locked_corners=True)),
+                                     ("chessboard", dict(corner_method=1, locked_corners=True))])
+def test_harris_and_locked_corners_native_equals_cv2(built, frames, name, kw):
+    from oracle import cv2_oracle as o
+    prm = Params(**kw)
+    a = native.detect(frames[name], prm)
+    b = o.detect(frames[name], prm)
+    assert [m["id"] for m in a["markers"]] == [m["id"] for m in b["markers"]] and len(a["markers"]) >= 6
+    for x, y in zip(a["markers"], b["markers"]):
+        assert np.abs(x["corners"] - y["corners"]).max() < CORNER_TOL
