@@ -15,7 +15,7 @@ enum : unsigned {
 };
 
 constexpr int MAX_QUADS = 1024;  // hard upper bound of quads per frame handled by the per-frame filter
-constexpr int MAX_CANDS = 512;   // hard upper bound of candidates per frame
+constexpr int MAX_CANDS = 1024;   // hard upper bound of candidates per frame
 
 struct ContourRec {
     uint32_t frame;

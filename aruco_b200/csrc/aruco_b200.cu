@@ -342,7 +342,7 @@ int ab_reserve(ab_context* ctx, int width, int height, int max_batch, int max_qu
     cudaDeviceSynchronize();
     free_buffers(ctx);
     int capQ = max_quads > 0 ? std::min(max_quads, MAX_QUADS) : MAX_QUADS;
-    int capC = max_cands > 0 ? std::min(max_cands, MAX_CANDS) : 256;
+    int capC = max_cands > 0 ? std::min(max_cands, MAX_CANDS) : 512;
     long long px = (long long)width * height;
     long long capS = max_starts_pf > 0 ? max_starts_pf : std::max(px / 8, 65536LL);
     long long capP = max_points_pf > 0 ? max_points_pf : std::max(px / 4, 65536LL);

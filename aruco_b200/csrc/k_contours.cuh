@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     unsigned long long n_starts = b.cnt->n_starts;
-    if (n_starts > b.cap_starts) n_starts = b.cap_starts;
+    if (n_starts > b.cap_starts) return;  // overflow already flagged by k_scan_starts; the list has holes
     int phase = 0;  // 0 idle, 1 search, 2 emit
     bool exhausted = false;
     BitImage im = b.bit_image(0);

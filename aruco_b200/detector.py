@@ -311,7 +311,7 @@ class MarkerDetector:
         self._check(self._lib.ab_get_thresholded(self._h, frame, _ptr(out), W))
         return out
 
-    def getAllCandidates(self, frame: int = 0, cap: int = 512):
+    def getAllCandidates(self, frame: int = 0, cap: int = 1024):
         """Every candidate that reached the decoder: (quads [n,4,2], ids [n], nrot [n])."""
         q = np.zeros((cap, 4, 2), np.float32)
         ids = np.zeros(cap, np.int32)

@@ -198,10 +198,10 @@ public:
     void getThresholdedImage(uint8_t* dst, size_t step) { check(ab_get_thresholded(h_, 0, dst, step)); }
     // getCandidates (h:266): quads rejected by the decoder in the last detect
     std::vector<std::vector<Point2f>> getCandidates() {
-        std::vector<float> q(8 * 512);
-        std::vector<int32_t> ids(512);
+        std::vector<float> q(8 * 1024);
+        std::vector<int32_t> ids(1024);
         int32_t n = 0;
-        check(ab_get_candidates(h_, 0, q.data(), ids.data(), nullptr, 512, &n));
+        check(ab_get_candidates(h_, 0, q.data(), ids.data(), nullptr, 1024, &n));
         std::vector<std::vector<Point2f>> out;
         for (int i = 0; i < n; i++)
             if (ids[i] < 0) {
@@ -217,9 +217,9 @@ public:
         check(ab_threshold(h_, grey.data, grey.cols, grey.rows, grey.step, method, param1, param2, out, out_step));
     }
     void detectRectangles(const ImageView& thres, std::vector<std::vector<Point2f>>& candidates) {
-        std::vector<float> q(8 * 512);
+        std::vector<float> q(8 * 1024);
         int32_t n = 0;
-        check(ab_detect_rectangles(h_, thres.data, thres.cols, thres.rows, thres.step, q.data(), 512, &n));
+        check(ab_detect_rectangles(h_, thres.data, thres.cols, thres.rows, thres.step, q.data(), 1024, &n));
         candidates.clear();
         for (int i = 0; i < n; i++) {
             std::vector<Point2f> c;
