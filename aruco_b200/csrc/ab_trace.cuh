@@ -28,17 +28,18 @@ namespace ab {
 // row above/below, so a 3x3 neighbourhood never needs a bounds test.
 struct BitImage {
     const uint32_t* bits;  // points at the padded buffer
-    int wpr;               // words per padded row = ceil(W/32) + 2
+    int wpr;               // words per padded row (bit_words_per_row)
     int W, H;
     AB_HD const uint32_t* row(int y) const { return bits + (size_t)(y + 1) * wpr; }
 };
 
-AB_HD int bit_words_per_row(int W) { return ((W + 31) >> 5) + 2; }
+constexpr int BIT_PAD = 4;  // zero words left of every row (16 B: rows stay 128-bit aligned); >= 1 zero word on the right
+AB_HD int bit_words_per_row(int W) { return (((W + 31) >> 5) + BIT_PAD + 1 + 3) & ~3; }
 AB_HD size_t bit_image_words(int W, int H) { return (size_t)bit_words_per_row(W) * (H + 2); }
 
 // bits of pixels x-1, x, x+1 of one padded row (bit0 = x-1)
 AB_HD uint32_t row3(const uint32_t* row, int x) {
-    int p = x + 31;  // pixel x-1 lives at padded bit x-1+32
+    int p = x - 1 + 32 * BIT_PAD;  // pixel x lives at padded bit x + 32*BIT_PAD
     uint32_t lo = row[p >> 5], hi = row[(p >> 5) + 1];
 #if defined(__CUDA_ARCH__)
     return __funnelshift_r(lo, hi, p & 31) & 7u;
@@ -128,12 +129,15 @@ AB_HD void walk_forward(WalkState& s, uint32_t nb) {
 }
 
 // predecessor state: the successor function is a permutation of the states, its inverse probes clockwise
-AB_HD void walk_backward(const BitImage& im, WalkState& s) {
+// returns the neighbour mask of the NEW position (callers reuse it for the trigger test)
+AB_HD uint32_t walk_backward(const BitImage& im, WalkState& s) {
     int qx = s.x + dir_dx(s.b), qy = s.y + dir_dy(s.b);
     int d = (s.b + 4) & 7;  // direction from the predecessor pixel to the current one
-    s.b = first_clockwise(neighbours8(im, qx, qy), d);
+    uint32_t nbq = neighbours8(im, qx, qy);
+    s.b = first_clockwise(nbq, d);
     s.x = qx;
     s.y = qy;
+    return nbq;
 }
 
 // Bidirectional search: is `st` the Suzuki start of its border?  Walks forwards and backwards alternately
@@ -143,15 +147,17 @@ AB_HD void walk_backward(const BitImage& im, WalkState& s) {
 AB_HD int find_start_bidir(const BitImage& im, const TraceStart& st, int max_len, int* len) {
     WalkState fw{st.x, st.y, st.b}, bw = fw;
     int nf = 0, ng = 0;
+    uint32_t nb_fw = neighbours8(im, fw.x, fw.y);
     for (;;) {
-        walk_forward(fw, neighbours8(im, fw.x, fw.y));
+        walk_forward(fw, nb_fw);
         nf++;
         if (same_state(fw, bw)) break;
-        if (is_smaller_trigger(im, fw, neighbours8(im, fw.x, fw.y), st.key)) return TRACE_NOT_START;
-        walk_backward(im, bw);
+        nb_fw = neighbours8(im, fw.x, fw.y);
+        if (is_smaller_trigger(im, fw, nb_fw, st.key)) return TRACE_NOT_START;
+        uint32_t nb_bw = walk_backward(im, bw);
         ng++;
         if (same_state(fw, bw)) break;
-        if (is_smaller_trigger(im, bw, neighbours8(im, bw.x, bw.y), st.key)) return TRACE_NOT_START;
+        if (is_smaller_trigger(im, bw, nb_bw, st.key)) return TRACE_NOT_START;
         if (nf + ng >= max_len) return TRACE_TOO_LONG;
     }
     *len = nf + ng;

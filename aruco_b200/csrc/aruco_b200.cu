@@ -12,6 +12,7 @@
 
 #include "ab_device.cuh"
 #include "k_threshold.cuh"
+#include "k_threshold_fast.cuh"
 #include "k_contours.cuh"
 #include "k_polygon.cuh"
 #include "k_decode.cuh"
@@ -438,7 +439,7 @@ static int launch_threshold(ab_context* ctx, const Batch& b, int method, double 
         size_t SPAN = 4 * (size_t)nth;
         size_t smem = (((size_t)k * SPAN + 15) & ~(size_t)15) + 4 * SPAN + nth;
         dim3 grid((b.W + a.TWo - 1) / a.TWo, (b.H + a.RH - 1) / a.RH, b.B);
-        k_threshold_adaptive<<<grid, nth, smem, st>>>(a);
+        if (!launch_threshold_fast(a, b.B, st)) k_threshold_adaptive<<<grid, nth, smem, st>>>(a);
     } else if (method == AB_THRES_FIXED) {
         int thr = (int)floor(p1);
         k_threshold_fixed<<<ctx->sm_count * 8, 256, 0, st>>>(b.grey, b.grey_row, b.grey_frame, b.thres, b.bits, b.bits_words,
@@ -565,8 +566,11 @@ static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t f
     if (ctx->timing) cudaEventRecord(ctx->kev[5], st);
     if (ctx->timing) cudaEventRecord(ctx->ev[2], st);
     dim3 gcand(b.cap_c, n);
+    dim3 gdec((b.cap_c + DECODE_WARPS - 1) / DECODE_WARPS, n);
+    const size_t dec_smem = DECODE_WARPS * decode_smem_per_warp(b.S);
+    if (dec_smem > 48 * 1024) cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
     if (P.decoder == AB_DECODER_HOST_CALLBACK) {
-        k_decode<<<gcand, 128, 0, st>>>(b, 1);
+        k_decode<<<gdec, 32 * DECODE_WARPS, dec_smem, st>>>(b, 1);
         CK(cudaGetLastError());
         // MarkerdetectorFunc plugin hook (markerdetector.h:78,243): canonical images go to the host, the
         // user function runs per candidate in the reference's order, ids/rotations come back.
@@ -591,7 +595,7 @@ static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t f
         CK(cudaStreamSynchronize(st));
         cudaFree(d_idrot);
     } else {
-        k_decode<<<gcand, 128, 0, st>>>(b, 0);
+        k_decode<<<gdec, 32 * DECODE_WARPS, dec_smem, st>>>(b, 0);
         CK(cudaGetLastError());
     }
     if (ctx->timing) cudaEventRecord(ctx->kev[6], st);

@@ -8,28 +8,38 @@
 
 namespace ab {
 
-__global__ void k_scan_starts(Batch b) {
+// one thread per 128 pixels (four packed words, 128-bit loads); candidates are appended with one atomic per warp
+__global__ void __launch_bounds__(256) k_scan_starts(Batch b) {
     const int ww = (b.W + 31) >> 5;
-    const size_t total = (size_t)ww * b.H * b.B;
+    const unsigned nq = (unsigned)(ww + 3) >> 2;  // quads per row
+    const unsigned long long total = (unsigned long long)nq * b.H * b.B;
     const int lane = threadIdx.x & 31;
-    for (size_t base = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(size_t)31; base < total;
-         base += (size_t)gridDim.x * blockDim.x) {
-        size_t i = base + lane;
-        uint32_t outer = 0, hole = 0;
-        int w = 0, y = 0, f = 0;
+    for (unsigned long long base = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; base < total;
+         base += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long i = base + lane;
+        uint32_t outer[4] = {0, 0, 0, 0}, hole[4] = {0, 0, 0, 0};
+        int q = 0, y = 0, f = 0, cnt = 0;
         if (i < total) {
-            w = (int)(i % ww);
-            y = (int)((i / ww) % b.H);
-            f = (int)(i / ((size_t)ww * b.H));
-            const uint32_t* row = b.bits + (size_t)f * b.bits_words + (size_t)(y + 1) * b.wpr + 1 + w;
+            q = (int)(i % nq);
+            unsigned long long r = i / nq;
+            y = (int)(r % (unsigned)b.H);
+            f = (int)(r / (unsigned)b.H);
+            const uint32_t* row = b.bits + (size_t)f * b.bits_words + (size_t)(y + 1) * b.wpr + BIT_PAD + 4 * q;
             const uint32_t* up = row - b.wpr;
-            uint32_t cur = row[0], west = (cur << 1) | (row[-1] >> 31);
-            uint32_t u = up[0], uw = (u << 1) | (up[-1] >> 31), ue = (u >> 1) | (up[1] << 31);
-            outer = cur & ~west & ~u & ~uw & ~ue;  // fg with W, N, NW, NE background
-            hole = ~cur & west & u;                // bg with W and N foreground
+            const uint4 c4 = *reinterpret_cast<const uint4*>(row);
+            const uint4 u4 = *reinterpret_cast<const uint4*>(up);
+            const uint32_t c[6] = {row[-1], c4.x, c4.y, c4.z, c4.w, 0u};
+            const uint32_t u[6] = {up[-1], u4.x, u4.y, u4.z, u4.w, up[4]};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t cur = c[k + 1], west = (cur << 1) | (c[k] >> 31);
+                uint32_t uu = u[k + 1], uw = (uu << 1) | (u[k] >> 31), ue = (uu >> 1) | (u[k + 2] << 31);
+                outer[k] = cur & ~west & ~uu & ~uw & ~ue;  // fg with W, N, NW, NE background
+                hole[k] = ~cur & west & uu;                // bg with W and N foreground
+                cnt += __popc(outer[k]) + __popc(hole[k]);
+            }
         }
-        int cnt = __popc(outer) + __popc(hole);
-        // warp-aggregated reservation
+        if (__ballot_sync(0xFFFFFFFFu, cnt != 0) == 0) continue;
         int incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -38,23 +48,28 @@ __global__ void k_scan_starts(Batch b) {
         }
         int tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
         unsigned long long wbase = 0;
-        if (lane == 31 && tot > 0) wbase = atomicAdd(&b.cnt->n_starts, (unsigned long long)tot);
+        if (lane == 31) wbase = atomicAdd(&b.cnt->n_starts, (unsigned long long)tot);
         wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
-        if (tot == 0) continue;
-        unsigned long long o = wbase + (unsigned long long)(incl - cnt);
         if (wbase + (unsigned long long)tot > b.cap_starts) {
             if (lane == 31) atomicOr(&b.cnt->err, ERR_STARTS_OVERFLOW);
             continue;
         }
-        while (outer) {
-            int j = __ffs((int)outer) - 1;
-            outer &= outer - 1;
-            b.starts[o++] = make_uint2((uint32_t)f, (uint32_t)(32 * w + j) | ((uint32_t)y << 16));
-        }
-        while (hole) {
-            int j = __ffs((int)hole) - 1;
-            hole &= hole - 1;
-            b.starts[o++] = make_uint2((uint32_t)f | 0x80000000u, (uint32_t)(32 * w + j) | ((uint32_t)y << 16));
+        unsigned long long o = wbase + (unsigned long long)(incl - cnt);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t m = outer[k];
+            const uint32_t xb = (uint32_t)(128 * q + 32 * k);
+            while (m) {
+                int j = __ffs((int)m) - 1;
+                m &= m - 1;
+                b.starts[o++] = make_uint2((uint32_t)f, (xb + j) | ((uint32_t)y << 16));
+            }
+            m = hole[k];
+            while (m) {
+                int j = __ffs((int)m) - 1;
+                m &= m - 1;
+                b.starts[o++] = make_uint2((uint32_t)f | 0x80000000u, (xb + j) | ((uint32_t)y << 16));
+            }
         }
     }
 }
@@ -75,6 +90,7 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
     BitImage im = b.bit_image(0);
     TraceStart st{0, 0, 0, 0};
     WalkState fw{0, 0, 0}, bw{0, 0, 0};
+    uint32_t nb_fw = 0;
     int nf = 0, ng = 0, len = 0, frame = 0;
     uint32_t* out = nullptr;
     unsigned int ci = 0;
@@ -97,6 +113,7 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                     if (make_start(im, (int)(rec.x >> 31), (int)(rec.y & 0xFFFFu), (int)(rec.y >> 16), st)) {
                         fw = WalkState{st.x, st.y, st.b};
                         bw = fw;
+                        nb_fw = neighbours8(im, fw.x, fw.y);
                         nf = ng = 0;
                         phase = 1;
                     }  // else: isolated pixel, a 1-point contour that is never kept
@@ -110,17 +127,17 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
         if (phase == 1) {
             for (int r = 0; r < STEPS; r++) {
                 bool closed = false, dead = false;
-                walk_forward(fw, neighbours8(im, fw.x, fw.y));
+                walk_forward(fw, nb_fw);
                 nf++;
                 if (same_state(fw, bw)) {
                     closed = true;
-                } else if (is_smaller_trigger(im, fw, neighbours8(im, fw.x, fw.y), st.key)) {
+                } else if (is_smaller_trigger(im, fw, nb_fw = neighbours8(im, fw.x, fw.y), st.key)) {
                     dead = true;
                 } else {
-                    walk_backward(im, bw);
+                    uint32_t nb_bw = walk_backward(im, bw);
                     ng++;
                     if (same_state(fw, bw)) closed = true;
-                    else if (is_smaller_trigger(im, bw, neighbours8(im, bw.x, bw.y), st.key)) dead = true;
+                    else if (is_smaller_trigger(im, bw, nb_bw, st.key)) dead = true;
                     else if (nf + ng >= b.max_len) dead = true;  // too long: dropped by :517 anyway
                 }
                 if (closed) {
@@ -141,6 +158,7 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                     } else {
                         out = b.pool + off;
                         fw = WalkState{st.x, st.y, st.b};
+                        nb_fw = neighbours8(im, fw.x, fw.y);
                         nf = 0;
                         phase = 2;
                     }
@@ -154,7 +172,8 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
         } else if (phase == 2) {
             for (int r = 0; r < 2 * STEPS; r++) {
                 out[nf] = (uint32_t)fw.x | ((uint32_t)fw.y << 16);
-                walk_forward(fw, neighbours8(im, fw.x, fw.y));
+                walk_forward(fw, nb_fw);
+                nb_fw = neighbours8(im, fw.x, fw.y);
                 if (++nf == len) {
                     b.contours[ci] = ContourRec{(uint32_t)frame, (uint32_t)off, (uint32_t)len, (uint32_t)st.key};
                     phase = 0;

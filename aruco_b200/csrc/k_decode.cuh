@@ -1,9 +1,11 @@
 // Stage 3: per-candidate identification (src/markerdetector.cpp:350-356).
-// One CTA per candidate: getPerspectiveTransform + warpPerspective(INTER_NEAREST) into shared memory
-// (MarkerDetector::warp, :684-697), 256-bin histogram -> Otsu (cv::threshold BINARY|OTSU), majority vote per
-// cell, then FiducidalMarkers::detect (src/arucofidmarkers.cpp:438-452) or HighlyReliableMarkers::detect
-// (src/highlyreliablemarkers.cpp:332-383).  The canonical image is also written out (getCandidates /
-// host-callback decoders need it).
+// One WARP per candidate (4 candidates per CTA): getPerspectiveTransform + warpPerspective(INTER_NEAREST) into
+// shared memory (MarkerDetector::warp, :684-697), 256-bin histogram -> Otsu (cv::threshold BINARY|OTSU),
+// majority vote per cell, then FiducidalMarkers::detect (src/arucofidmarkers.cpp:438-452) or
+// HighlyReliableMarkers::detect (src/highlyreliablemarkers.cpp:332-383).  The serial f64 pieces (8x8 LU, the
+// Otsu recurrence -- both must follow OpenCV's operation order to stay bit-exact) run on lane 0; giving every
+// candidate its own warp keeps ~48 of those chains in flight per SM instead of 6 with a CTA per candidate.
+// The canonical image is also written out (getCandidates / host-callback decoders need it).
 #pragma once
 #include "ab_device.cuh"
 
@@ -11,6 +13,7 @@ namespace ab {
 
 constexpr int MAX_WARP_SIZE = 128;  // S <= 128
 constexpr int MAX_CELLS = 100;      // (n+2)^2 with n <= 8
+constexpr int DECODE_WARPS = 4;
 
 __device__ __forceinline__ int hrm_decode(const HrmDict& D, const uint8_t* cells, int ncell, int* nrot, int lane) {
     // cells: (n+2)^2 majority bits; HRM ignores the border cells (highlyreliablemarkers.cpp:345)
@@ -61,34 +64,44 @@ __device__ __forceinline__ int hrm_decode(const HrmDict& D, const uint8_t* cells
     return -1;
 }
 
-// mode 0: warp + decode; mode 1: warp only (host-callback decoder)
-__global__ void __launch_bounds__(128) k_decode(Batch b, int mode) {
-    __shared__ uint8_t s_img[MAX_WARP_SIZE * MAX_WARP_SIZE];
-    __shared__ int s_hist[256];
-    __shared__ int s_cnt[MAX_CELLS];
-    __shared__ uint8_t s_cells[MAX_CELLS];
-    __shared__ double s_Mi[9];
-    __shared__ int s_ok, s_thr;
-    const int f = blockIdx.y, ci = blockIdx.x, t = threadIdx.x;
-    if (ci >= (int)b.n_cands[f]) return;
-    CandRec* cand = b.cands + (size_t)f * b.cap_c + ci;
+inline size_t decode_smem_per_warp(int S) {
+    return (((size_t)S * S + 15) & ~(size_t)15) + 256 * sizeof(int) + MAX_CELLS * sizeof(int) + 112 + 9 * sizeof(double) + 8;
+}
+
+// mode 0: warp + decode; mode 1: warp only (host-callback decoder).  grid = (ceil(cap_c / DECODE_WARPS), B)
+__global__ void __launch_bounds__(32 * DECODE_WARPS) k_decode(Batch b, int mode) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int f = blockIdx.y, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int ci = blockIdx.x * DECODE_WARPS + wib;
+    if (ci >= (int)b.n_cands[f] || ci >= b.cap_c) return;  // whole warp leaves; only warp-level sync below
     const int S = b.S;
-    if (t == 0) {
+    const size_t img_bytes = ((size_t)S * S + 15) & ~(size_t)15;
+    const size_t per_warp = img_bytes + 256 * sizeof(int) + MAX_CELLS * sizeof(int) + 112 + 9 * sizeof(double) + 8;
+    unsigned char* base = s_raw + (size_t)wib * per_warp;
+    uint8_t* s_img = base;
+    int* s_hist = reinterpret_cast<int*>(base + img_bytes);
+    int* s_cnt = s_hist + 256;
+    uint8_t* s_cells = reinterpret_cast<uint8_t*>(s_cnt + MAX_CELLS);
+    double* s_Mi = reinterpret_cast<double*>(base + img_bytes + 256 * sizeof(int) + MAX_CELLS * sizeof(int) + 112);
+    CandRec* cand = b.cands + (size_t)f * b.cap_c + ci;
+    int ok_i = 0;
+    if (lane == 0) {
         float dst[8] = {0.f, 0.f, (float)(S - 1), 0.f, (float)(S - 1), (float)(S - 1), 0.f, (float)(S - 1)};
         double M[9], Mi[9];
         bool ok = perspective_transform(cand->c, dst, M) && invert3(M, Mi);
-        s_ok = ok;
+        ok_i = ok;
         if (ok)
             for (int i = 0; i < 9; i++) s_Mi[i] = Mi[i];
     }
-    for (int i = t; i < 256; i += blockDim.x) s_hist[i] = 0;
-    if (t < MAX_CELLS) s_cnt[t] = 0;
-    __syncthreads();
+    for (int i = lane; i < 256; i += 32) s_hist[i] = 0;
+    for (int i = lane; i < MAX_CELLS; i += 32) s_cnt[i] = 0;
+    ok_i = __shfl_sync(0xFFFFFFFFu, ok_i, 0);
+    __syncwarp();
     const uint8_t* grey = b.grey + (size_t)f * b.grey_frame;
     uint8_t* canon = b.canon + ((size_t)f * b.cap_c + ci) * (size_t)(S * S);
     const int bw = warp_block_width(S);
-    const bool ok = s_ok != 0;
-    for (int i = t; i < S * S; i += blockDim.x) {
+    const bool ok = ok_i != 0;
+    for (int i = lane; i < S * S; i += 32) {
         int y = i / S, x = i - y * S;
         uint8_t v = 0;
         if (ok) {
@@ -100,31 +113,29 @@ __global__ void __launch_bounds__(128) k_decode(Batch b, int mode) {
         canon[i] = v;
         atomicAdd(&s_hist[v], 1);
     }
-    __syncthreads();
+    __syncwarp();
     if (mode == 1) return;
-    if (t == 0) s_thr = otsu_threshold(s_hist, S * S);
-    __syncthreads();
-    const int thr = s_thr;
+    int thr = 0;
+    if (lane == 0) thr = otsu_threshold(s_hist, S * S);
+    thr = __shfl_sync(0xFFFFFFFFu, thr, 0);
     const int ncell = (b.decoder == AB_DECODER_HRM) ? b.dict.n + 2 : 7;
     const int cell = S / ncell;
     const int span = cell * ncell;
-    for (int i = t; i < span * span; i += blockDim.x) {
+    for (int i = lane; i < span * span; i += 32) {
         int y = i / span, x = i - y * span;
         if (s_img[y * S + x] > thr) atomicAdd(&s_cnt[(y / cell) * ncell + (x / cell)], 1);
     }
-    __syncthreads();
-    if (t < ncell * ncell) s_cells[t] = s_cnt[t] > (cell * cell) / 2;
-    __syncthreads();
+    __syncwarp();
+    for (int i = lane; i < ncell * ncell; i += 32) s_cells[i] = s_cnt[i] > (cell * cell) / 2;
+    __syncwarp();
     if (b.decoder == AB_DECODER_HRM) {
-        if (t < 32) {
-            int nrot = 0;
-            int id = hrm_decode(b.dict, s_cells, ncell, &nrot, t);
-            if (t == 0) {
-                cand->id = id;
-                cand->nrot = nrot;
-            }
+        int nrot = 0;
+        int id = hrm_decode(b.dict, s_cells, ncell, &nrot, lane);
+        if (lane == 0) {
+            cand->id = id;
+            cand->nrot = nrot;
         }
-    } else if (t == 0) {
+    } else if (lane == 0) {
         int nrot = 0;
         int id = fid_decode(s_cells, &nrot);
         cand->id = id;
