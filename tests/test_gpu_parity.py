@@ -47,7 +47,7 @@ def check_frame(det, grey, P, K=None, D=None, size=-1.0, hrm_text=None, frame=0,
     """Full per-stage comparison of one frame against the C++ oracle (and the cv2 oracle when available)."""
     from oracle import native
     hn = native.dict_from_yaml_text(hrm_text) if hrm_text else None
-    ref = native.detect(grey, P, K, D, size, hn)
+    ref = native.detect(grey, P, K, D, size, hn, cap=2048)
     if markers is None:
         markers = det.detect(grey, K, D, size, bool(P.set_y_perpendicular))
     assert (det.getThresholdedImage(frame) == ref["thres"]).all(), "binarised image not bit-exact"
