@@ -60,11 +60,16 @@ AB_HD int dir_dy(int d) { return (d >= 1 && d <= 3) ? -1 : ((d >= 5) ? 1 : 0); }
 
 // first foreground neighbour going CLOCKWISE from direction `from` (exclusive), -1 if none
 AB_HD int first_clockwise(uint32_t nb, int from) {
-    for (int k = 1; k <= 8; k++) {
-        int d = (from - k) & 7;
-        if ((nb >> d) & 1u) return d;
-    }
-    return -1;
+    // branch-free: rotate so that direction `from` sits at bit 0; the clockwise-nearest neighbour is then the
+    // HIGHEST set bit (bit 7 = from-1, ..., bit 0 = from itself after a full turn)
+    uint32_t r = (((nb << 8) | nb) >> from) & 0xFFu;
+    if (r == 0) return -1;
+#if defined(__CUDA_ARCH__)
+    int j = 31 - __clz((int)r);
+#else
+    int j = 31 - __builtin_clz(r);
+#endif
+    return (from + j) & 7;
 }
 
 // successor: first foreground neighbour going COUNTER-CLOCKWISE from back-direction b (exclusive).

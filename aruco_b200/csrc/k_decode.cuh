@@ -14,6 +14,7 @@ namespace ab {
 constexpr int MAX_WARP_SIZE = 128;  // S <= 128
 constexpr int MAX_CELLS = 100;      // (n+2)^2 with n <= 8
 constexpr int DECODE_WARPS = 4;
+constexpr int DECODE_LIST = 1024;   // per-warp list of pixels that need the exact f64 coordinate
 
 __device__ __forceinline__ int hrm_decode(const HrmDict& D, const uint8_t* cells, int ncell, int* nrot, int lane) {
     // cells: (n+2)^2 majority bits; HRM ignores the border cells (highlyreliablemarkers.cpp:345)
@@ -65,7 +66,8 @@ __device__ __forceinline__ int hrm_decode(const HrmDict& D, const uint8_t* cells
 }
 
 inline size_t decode_smem_per_warp(int S) {
-    return (((size_t)S * S + 15) & ~(size_t)15) + 256 * sizeof(int) + MAX_CELLS * sizeof(int) + 112 + 9 * sizeof(double) + 8;
+    return (((size_t)S * S + 15) & ~(size_t)15) + 256 * sizeof(int) + MAX_CELLS * sizeof(int) + 112 + 9 * sizeof(double) + 8 +
+           DECODE_LIST * sizeof(unsigned short);
 }
 
 // mode 0: warp + decode; mode 1: warp only (host-callback decoder).  grid = (ceil(cap_c / DECODE_WARPS), B)
@@ -76,13 +78,14 @@ __global__ void __launch_bounds__(32 * DECODE_WARPS) k_decode(Batch b, int mode)
     if (ci >= (int)b.n_cands[f] || ci >= b.cap_c) return;  // whole warp leaves; only warp-level sync below
     const int S = b.S;
     const size_t img_bytes = ((size_t)S * S + 15) & ~(size_t)15;
-    const size_t per_warp = img_bytes + 256 * sizeof(int) + MAX_CELLS * sizeof(int) + 112 + 9 * sizeof(double) + 8;
+    const size_t per_warp = img_bytes + 256 * sizeof(int) + MAX_CELLS * sizeof(int) + 112 + 9 * sizeof(double) + 8 + DECODE_LIST * sizeof(unsigned short);
     unsigned char* base = s_raw + (size_t)wib * per_warp;
     uint8_t* s_img = base;
     int* s_hist = reinterpret_cast<int*>(base + img_bytes);
     int* s_cnt = s_hist + 256;
     uint8_t* s_cells = reinterpret_cast<uint8_t*>(s_cnt + MAX_CELLS);
     double* s_Mi = reinterpret_cast<double*>(base + img_bytes + 256 * sizeof(int) + MAX_CELLS * sizeof(int) + 112);
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_Mi + 10);
     CandRec* cand = b.cands + (size_t)f * b.cap_c + ci;
     int ok_i = 0;
     if (lane == 0) {
@@ -101,14 +104,69 @@ __global__ void __launch_bounds__(32 * DECODE_WARPS) k_decode(Batch b, int mode)
     uint8_t* canon = b.canon + ((size_t)f * b.cap_c + ci) * (size_t)(S * S);
     const int bw = warp_block_width(S);
     const bool ok = ok_i != 0;
-    for (int i = lane; i < S * S; i += 32) {
-        int y = i / S, x = i - y * S;
-        uint8_t v = 0;
-        if (ok) {
-            int sx, sy;
-            warp_src_coord(s_Mi, x, y, bw, &sx, &sy);
-            if (sx >= 0 && sy >= 0 && sx < b.W && sy < b.H) v = grey[(size_t)sy * b.grey_row + sx];
+    // Filtered arithmetic: OpenCV's source coordinate is rint() of an f64 expression.  An f32 evaluation
+    // (error << 0.05 px for |coord| < 32768) decides every pixel whose coordinate is not within 0.05 px of a
+    // rounding boundary -- the integer it rounds to is then provably the same; the remaining ~10 % are
+    // collected (ballot compaction) and redone densely with the exact f64 sequence.  FP64 issue rate, not
+    // memory, was the limiter of this kernel (ncu r1d).
+    float Mf[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) Mf[q] = ok ? (float)s_Mi[q] : 0.f;
+    int nunc = 0;
+    for (int i0 = 0; i0 < S * S; i0 += 32) {
+        const int i = i0 + lane;
+        bool unc = false;
+        if (i < S * S) {
+            const int y = i / S, x = i - y * S;
+            if (!ok) {
+                s_img[i] = 0;
+                canon[i] = 0;
+                atomicAdd(&s_hist[0], 1);
+            } else {
+                const float fxp = (float)x, fyp = (float)y;
+                const float den = Mf[6] * fxp + Mf[7] * fyp + Mf[8];
+                const float fx = (Mf[0] * fxp + Mf[1] * fyp + Mf[2]) / den, fy = (Mf[3] * fxp + Mf[4] * fyp + Mf[5]) / den;
+                const float rx = rintf(fx), ry = rintf(fy);
+                unc = !(fabsf(fx) < 32768.f && fabsf(fy) < 32768.f) || fabsf(fx - rx) > 0.45f || fabsf(fy - ry) > 0.45f;
+                if (!unc) {
+                    const int sx = (int)rx, sy = (int)ry;
+                    uint8_t v = 0;
+                    if (sx >= 0 && sy >= 0 && sx < b.W && sy < b.H) v = grey[(size_t)sy * b.grey_row + sx];
+                    s_img[i] = v;
+                    canon[i] = v;
+                    atomicAdd(&s_hist[v], 1);
+                }
+            }
         }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, unc);
+        if (m) {
+            const int pos = nunc + __popc(m & ((1u << lane) - 1u));
+            if (unc) {
+                if (pos < DECODE_LIST) {
+                    s_list[pos] = (unsigned short)i;
+                } else {  // list full (cannot happen for guard 0.05 unless the map is degenerate): do it now
+                    const int y = i / S, x = i - y * S;
+                    int sx, sy;
+                    warp_src_coord(s_Mi, x, y, bw, &sx, &sy);
+                    uint8_t v = 0;
+                    if (sx >= 0 && sy >= 0 && sx < b.W && sy < b.H) v = grey[(size_t)sy * b.grey_row + sx];
+                    s_img[i] = v;
+                    canon[i] = v;
+                    atomicAdd(&s_hist[v], 1);
+                }
+            }
+            nunc += __popc(m);
+        }
+    }
+    __syncwarp();
+    const int n2 = min(nunc, DECODE_LIST);
+    for (int k = lane; k < n2; k += 32) {
+        const int i = (int)s_list[k];
+        const int y = i / S, x = i - y * S;
+        int sx, sy;
+        warp_src_coord(s_Mi, x, y, bw, &sx, &sy);
+        uint8_t v = 0;
+        if (sx >= 0 && sy >= 0 && sx < b.W && sy < b.H) v = grey[(size_t)sy * b.grey_row + sx];
         s_img[i] = v;
         canon[i] = v;
         atomicAdd(&s_hist[v], 1);

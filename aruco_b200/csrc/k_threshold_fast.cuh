@@ -1,9 +1,12 @@
 // Fast path of the adaptive threshold for the common odd block sizes (compile-time K): same arithmetic as
-// k_threshold_adaptive (k_threshold.cuh), restructured to cut shared-memory traffic (the generic kernel is
-// LSU/shared-memory bound: ncu r1a showed memory pipes 93 % busy at 12.7 % DRAM throughput):
+// k_threshold_adaptive (k_threshold.cuh), restructured around instruction count (ncu r1a/r1d: the kernel is
+// issue bound -- 68 % issue slots busy at 13 % DRAM throughput -- so every removed instruction is time):
 //   * the K most recent source rows of a thread's 4 columns live in REGISTERS (ring unrolled K times),
-//   * vertical sums are published as 4 x u16 in one 8-byte store, double buffered -> one barrier per row,
-//   * the horizontal window is read back with 8-byte loads (4 + 2*R4 values = 3 loads for K = 7),
+//   * vertical sums are kept as packed 2 x u16 (even / odd columns) and updated with plain 32-bit adds,
+//   * they are published as 4 x u16 in one 8-byte store, double buffered -> one barrier per row,
+//   * the horizontal window is read back with 8-byte loads and, for K <= 15 (sums < 65536), summed as packed
+//     u16 pairs: 15 integer ops give the four window sums of a thread for K = 7,
+//   * mean >= T is tested as  S >= K^2 (src + idelta) - (K^2 - 1)/2  (no division, one IMAD per pixel),
 //   * 128 output threads are word aligned (thread t owns columns X0+4t), halo columns are computed by a few
 //     extra threads, so the 1-bit packed copy is assembled with three warp shuffles and no second barrier.
 #pragma once
@@ -15,9 +18,22 @@ constexpr int THR_OUT_THREADS = 128;            // output threads per CTA
 constexpr int THR_TWO = 4 * THR_OUT_THREADS;    // 512 output columns per CTA
 constexpr int THR_RH = 128;                     // output rows per CTA
 
+// (v[i] | v[i+1] << 16) from the packed words w[] (w[q] = v[2q] | v[2q+1] << 16)
+template <int I>
+__device__ __forceinline__ uint32_t thr_pair(const uint32_t* w) {
+    if constexpr ((I & 1) == 0) return w[I / 2];
+    else return __byte_perm(w[(I - 1) / 2], w[(I + 1) / 2], 0x5432);
+}
+template <int I, int END>
+__device__ __forceinline__ uint32_t thr_pair_sum(const uint32_t* w) {
+    if constexpr (I > END) return 0u;
+    else return thr_pair<I>(w) + thr_pair_sum<I + 1, END>(w);
+}
+
 template <int K>
 __global__ void __launch_bounds__(160) k_threshold_fast(ThrArgs a) {
-    constexpr int R = K / 2, R4 = (R + 3) & ~3, HT = R4 / 4, NV = 4 + 2 * R4, CSW = THR_TWO + 2 * R4, K2 = K * K;
+    constexpr int R = K / 2, R4 = (R + 3) & ~3, HT = R4 / 4, NV = 4 + 2 * R4, NW = NV / 2, CSW = THR_TWO + 2 * R4, K2 = K * K;
+    constexpr bool PACKED = K2 * 255 < 65536;
     __shared__ __align__(16) unsigned short cs[2][CSW];
     const int t = threadIdx.x;
     if (t >= THR_OUT_THREADS + 2 * HT) return;  // spare lanes of the halo warp
@@ -35,19 +51,23 @@ __global__ void __launch_bounds__(160) k_threshold_fast(ThrArgs a) {
         c0 = X0 - R4 + ci;
     }
     const uint8_t* src = a.grey + (size_t)f * a.grey_frame;
-    uint8_t* dst = a.thres + (size_t)f * a.W * a.H;
-    uint32_t* bits = a.bits + (size_t)f * a.bits_words;
     const bool fast = a.aligned4 && c0 >= 0 && c0 + 3 < a.W;
     const bool live = c0 < a.W + R4;  // columns far right of the image are never needed
-    int xc0 = min(max(c0, 0), a.W - 1), xc1 = min(max(c0 + 1, 0), a.W - 1), xc2 = min(max(c0 + 2, 0), a.W - 1),
-        xc3 = min(max(c0 + 3, 0), a.W - 1);
+    const int xc0 = min(max(c0, 0), a.W - 1), xc1 = min(max(c0 + 1, 0), a.W - 1), xc2 = min(max(c0 + 2, 0), a.W - 1),
+              xc3 = min(max(c0 + 3, 0), a.W - 1);
     const int yEnd = min(y0 + THR_RH, a.H);
     const int nrows = (yEnd - y0) + 2 * R;
     const bool store_vec = (c0 + 3 < a.W) && ((a.W & 3) == 0);
+    // validity of the 4 columns as a nibble
+    const uint32_t vmask = c0 >= a.W ? 0u : (c0 + 3 < a.W ? 15u : ((1u << (a.W - c0)) - 1u));
+    uint8_t* orow = a.thres + (size_t)f * a.W * a.H + (size_t)y0 * a.W + c0;
+    uint32_t* brow = a.bits + (size_t)f * a.bits_words + (size_t)(y0 + 1) * a.wpr + BIT_PAD + (X0 >> 5) + (t >> 3);
+    const int cst = K2 * a.idelta - (K2 - 1) / 2;  // S >= K2*src + cst  <=>  src - mean <= -idelta
+    const uint32_t M = 0x00FF00FFu;
     uint32_t ring[K];
 #pragma unroll
     for (int j = 0; j < K; j++) ring[j] = 0u;
-    int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    uint32_t E = 0u, O = 0u;  // vertical sums of columns (0,2) and (1,3), 16 bits each
     int buf = 0;
     for (int base = 0; base < nrows; base += K) {
 #pragma unroll
@@ -65,54 +85,61 @@ __global__ void __launch_bounds__(160) k_threshold_fast(ThrArgs a) {
                 }
                 const uint32_t old = ring[j];
                 ring[j] = p;
-                s0 += (int)(p & 255u) - (int)(old & 255u);
-                s1 += (int)((p >> 8) & 255u) - (int)((old >> 8) & 255u);
-                s2 += (int)((p >> 16) & 255u) - (int)((old >> 16) & 255u);
-                s3 += (int)(p >> 24) - (int)(old >> 24);
+                E = E + (p & M) - (old & M);
+                O = O + ((p >> 8) & M) - ((old >> 8) & M);
                 if (i >= 2 * R) {
-                    const int yo = y0 + i - 2 * R;
-                    *reinterpret_cast<uint2*>(&cs[buf][ci]) = make_uint2((uint32_t)s0 | ((uint32_t)s1 << 16), (uint32_t)s2 | ((uint32_t)s3 << 16));
+                    *reinterpret_cast<uint2*>(&cs[buf][ci]) = make_uint2(__byte_perm(E, O, 0x5410), __byte_perm(E, O, 0x7632));
                     __syncthreads();
                     if (is_out) {
-                        int v[NV];
+                        uint32_t w[NW];
                         const uint2* wp = reinterpret_cast<const uint2*>(&cs[buf][ci - R4]);
 #pragma unroll
-                        for (int q = 0; q < NV / 4; q++) {
+                        for (int q = 0; q < NW / 2; q++) {
                             uint2 u = wp[q];
-                            v[4 * q] = (int)(u.x & 0xFFFFu);
-                            v[4 * q + 1] = (int)(u.x >> 16);
-                            v[4 * q + 2] = (int)(u.y & 0xFFFFu);
-                            v[4 * q + 3] = (int)(u.y >> 16);
+                            w[2 * q] = u.x;
+                            w[2 * q + 1] = u.y;
                         }
-                        int S = 0;
+                        int S0, S1, S2, S3;
+                        if constexpr (PACKED) {
+                            // (S0,S1) = sum of pairs starting at R4-R .. R4+R; (S2,S3) = the same window two columns on
+                            uint32_t s01 = thr_pair_sum<R4 - R, R4 + R>(w);
+                            uint32_t s23 = s01 - thr_pair<R4 - R>(w) - thr_pair<R4 - R + 1>(w) + thr_pair<R4 + R + 1>(w) + thr_pair<R4 + R + 2>(w);
+                            S0 = (int)(s01 & 0xFFFFu);
+                            S1 = (int)(s01 >> 16);
+                            S2 = (int)(s23 & 0xFFFFu);
+                            S3 = (int)(s23 >> 16);
+                        } else {
+                            int v[NV];
 #pragma unroll
-                        for (int d = R4 - R; d <= R4 + R; d++) S += v[d];
+                            for (int q = 0; q < NW; q++) {
+                                v[2 * q] = (int)(w[q] & 0xFFFFu);
+                                v[2 * q + 1] = (int)(w[q] >> 16);
+                            }
+                            S0 = 0;
+#pragma unroll
+                            for (int d = R4 - R; d <= R4 + R; d++) S0 += v[d];
+                            S1 = S0 + v[R4 + 1 + R] - v[R4 - R];
+                            S2 = S1 + v[R4 + 2 + R] - v[R4 + 1 - R];
+                            S3 = S2 + v[R4 + 3 + R] - v[R4 + 2 - R];
+                        }
                         const uint32_t c = ring[(j + K - R) % K];  // centre row
-                        uint32_t nibble = 0, outb = 0;
-#pragma unroll
-                        for (int jj = 0; jj < 4; jj++) {
-                            int T = (int)((c >> (8 * jj)) & 255u) + a.idelta;
-                            bool on = (2 * S + K2 >= 2 * K2 * T) && (c0 + jj < a.W);
-                            if (on) {
-                                nibble |= 1u << jj;
-                                outb |= 255u << (8 * jj);
-                            }
-                            if (jj < 3) S += v[R4 + jj + 1 + R] - v[R4 + jj - R];
-                        }
-                        if (c0 < a.W) {
-                            uint8_t* orow = dst + (size_t)yo * a.W + c0;
-                            if (store_vec) {
-                                *reinterpret_cast<uint32_t*>(orow) = outb;
-                            } else {
-                                for (int jj = 0; jj < 4; jj++)
-                                    if (c0 + jj < a.W) orow[jj] = (uint8_t)(outb >> (8 * jj));
-                            }
+                        uint32_t nibble = (uint32_t)(S0 >= (int)(c & 255u) * K2 + cst) | ((uint32_t)(S1 >= (int)((c >> 8) & 255u) * K2 + cst) << 1) |
+                                          ((uint32_t)(S2 >= (int)((c >> 16) & 255u) * K2 + cst) << 2) | ((uint32_t)(S3 >= (int)(c >> 24) * K2 + cst) << 3);
+                        nibble &= vmask;
+                        const uint32_t outb = ((nibble * 0x00204081u) & 0x01010101u) * 255u;  // bit j -> byte j = 0xFF
+                        if (store_vec) {
+                            *reinterpret_cast<uint32_t*>(orow) = outb;
+                        } else {
+                            for (int jj = 0; jj < 4; jj++)
+                                if ((vmask >> jj) & 1u) orow[jj] = (uint8_t)(outb >> (8 * jj));
                         }
                         uint32_t word = nibble << (4 * (t & 7));
                         word |= __shfl_xor_sync(0xFFFFFFFFu, word, 1);
                         word |= __shfl_xor_sync(0xFFFFFFFFu, word, 2);
                         word |= __shfl_xor_sync(0xFFFFFFFFu, word, 4);
-                        if ((t & 7) == 0 && c0 < a.W) bits[(size_t)(yo + 1) * a.wpr + BIT_PAD + (X0 >> 5) + (t >> 3)] = word;
+                        if ((t & 7) == 0 && vmask) *brow = word;
+                        orow += a.W;
+                        brow += a.wpr;
                     }
                     buf ^= 1;
                 }
