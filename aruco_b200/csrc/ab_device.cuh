@@ -46,7 +46,7 @@ struct Counters {
     unsigned int n_contours;
     unsigned int trace_work;
     unsigned int err;
-    unsigned int pad;
+    unsigned int emit_work;
     unsigned long long n_quads_total, n_cands_total, n_markers_total;
 };
 

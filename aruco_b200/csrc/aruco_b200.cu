@@ -558,6 +558,7 @@ static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t f
     k_scan_starts<<<sms * 8, 256, 0, st>>>(b);
     if (ctx->timing) cudaEventRecord(ctx->kev[2], st);
     k_trace<<<sms * 8, 128, 0, st>>>(b);
+    k_emit<<<sms * 8, 128, 0, st>>>(b);
     if (ctx->timing) cudaEventRecord(ctx->kev[3], st);
     k_polygon<<<sms * 4, 128, 0, st>>>(b);
     if (ctx->timing) cudaEventRecord(ctx->kev[4], st);
@@ -921,6 +922,7 @@ int ab_detect_rectangles(ab_context* ctx, const uint8_t* thres, int width, int h
                                                           b.wpr, 0, 1, 1);
     k_scan_starts<<<ctx->sm_count * 8, 256, 0, st>>>(b);
     k_trace<<<ctx->sm_count * 8, 128, 0, st>>>(b);
+    k_emit<<<ctx->sm_count * 8, 128, 0, st>>>(b);
     k_polygon<<<ctx->sm_count * 4, 128, 0, st>>>(b);
     k_frame_filter<<<1, 256, 0, st>>>(b);
     CK(cudaGetLastError());

@@ -76,55 +76,52 @@ __global__ void __launch_bounds__(256) k_scan_starts(Batch b) {
 
 // Lane-scheduled walker.  Every lane owns one start candidate at a time and is refilled from a global work
 // counter as soon as it finishes, so a warp never idles behind its longest contour (border lengths range
-// from 2 to max_len).  Phase 1 = bidirectional search for a smaller start on the same cycle
-// (find_start_bidir in ab_trace.cuh, executed STEPS at a time); phase 2 = the Suzuki start of a kept border
-// re-walks it forwards and writes the ordered points into the pool.
+// from 2 to max_len).  The walk is the bidirectional search of find_start_bidir (ab_trace.cuh), executed
+// STEPS at a time; the Suzuki start of a border with min_len < n < max_len reserves its slice of the point
+// pool and leaves a contour record -- the points themselves are written by k_emit.
 __global__ void __launch_bounds__(128) k_trace(Batch b) {
     constexpr int STEPS = 8;
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     unsigned long long n_starts = b.cnt->n_starts;
     if (n_starts > b.cap_starts) return;  // overflow already flagged by k_scan_starts; the list has holes
-    int phase = 0;  // 0 idle, 1 search, 2 emit
-    bool exhausted = false;
+    bool active = false, exhausted = false;
     BitImage im = b.bit_image(0);
     TraceStart st{0, 0, 0, 0};
     WalkState fw{0, 0, 0}, bw{0, 0, 0};
-    uint32_t nb_fw = 0;
-    int nf = 0, ng = 0, len = 0, frame = 0;
-    uint32_t* out = nullptr;
-    unsigned int ci = 0;
-    unsigned long long off = 0;
+    uint32_t nb_fw = 0, type_bit = 0;
+    int nf = 0, ng = 0, frame = 0;
     for (;;) {
-        unsigned idle = __ballot_sync(FULL, phase == 0 && !exhausted);
+        unsigned idle = __ballot_sync(FULL, !active && !exhausted);
         if (idle) {
             unsigned base = 0;
             int leader = __ffs((int)idle) - 1;
             if (lane == leader) base = atomicAdd(&b.cnt->trace_work, (unsigned)__popc(idle));
             base = __shfl_sync(FULL, base, leader);
-            if (phase == 0 && !exhausted) {
+            if (!active && !exhausted) {
                 unsigned long long i = (unsigned long long)base + (unsigned)__popc(idle & ((1u << lane) - 1u));
                 if (i >= n_starts) {
                     exhausted = true;
                 } else {
                     uint2 rec = b.starts[i];
                     frame = (int)(rec.x & 0x7FFFFFFFu);
+                    type_bit = rec.x & 0x80000000u;
                     im = b.bit_image(frame);
                     if (make_start(im, (int)(rec.x >> 31), (int)(rec.y & 0xFFFFu), (int)(rec.y >> 16), st)) {
                         fw = WalkState{st.x, st.y, st.b};
                         bw = fw;
                         nb_fw = neighbours8(im, fw.x, fw.y);
                         nf = ng = 0;
-                        phase = 1;
+                        active = true;
                     }  // else: isolated pixel, a 1-point contour that is never kept
                 }
             }
         }
-        if (__ballot_sync(FULL, phase != 0) == 0) {
+        if (__ballot_sync(FULL, active) == 0) {
             if (__ballot_sync(FULL, !exhausted) == 0) break;
             continue;
         }
-        if (phase == 1) {
+        if (active) {
             for (int r = 0; r < STEPS; r++) {
                 bool closed = false, dead = false;
                 walk_forward(fw, nb_fw);
@@ -141,43 +138,105 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                     else if (nf + ng >= b.max_len) dead = true;  // too long: dropped by :517 anyway
                 }
                 if (closed) {
-                    len = nf + ng;
-                    if (len <= b.min_len || len >= b.max_len) {  // src/markerdetector.cpp:517
-                        phase = 0;
-                        break;
+                    const int len = nf + ng;
+                    if (len > b.min_len && len < b.max_len) {  // src/markerdetector.cpp:517
+                        unsigned int ci = atomicAdd(&b.cnt->n_contours, 1u);
+                        unsigned long long off = atomicAdd(&b.cnt->pool_used, (unsigned long long)len);
+                        if (ci >= b.cap_contours) {
+                            atomicOr(&b.cnt->err, ERR_CONTOURS_OVERFLOW);
+                        } else if (off + (unsigned long long)len > b.cap_pool) {
+                            atomicOr(&b.cnt->err, ERR_POOL_OVERFLOW);
+                            b.contours[ci] = ContourRec{(uint32_t)frame | type_bit, 0u, 0u, (uint32_t)st.key};
+                        } else {
+                            b.contours[ci] = ContourRec{(uint32_t)frame | type_bit, (uint32_t)off, (uint32_t)len, (uint32_t)st.key};
+                        }
                     }
-                    ci = atomicAdd(&b.cnt->n_contours, 1u);
-                    off = atomicAdd(&b.cnt->pool_used, (unsigned long long)len);
-                    if (ci >= b.cap_contours) {
-                        atomicOr(&b.cnt->err, ERR_CONTOURS_OVERFLOW);
-                        phase = 0;
-                    } else if (off + (unsigned long long)len > b.cap_pool) {
-                        atomicOr(&b.cnt->err, ERR_POOL_OVERFLOW);
-                        b.contours[ci] = ContourRec{(uint32_t)frame, 0u, 0u, (uint32_t)st.key};
-                        phase = 0;
-                    } else {
-                        out = b.pool + off;
-                        fw = WalkState{st.x, st.y, st.b};
-                        nb_fw = neighbours8(im, fw.x, fw.y);
-                        nf = 0;
-                        phase = 2;
-                    }
+                    active = false;
                     break;
                 }
                 if (dead) {
-                    phase = 0;
+                    active = false;
                     break;
                 }
             }
-        } else if (phase == 2) {
-            for (int r = 0; r < 2 * STEPS; r++) {
-                out[nf] = (uint32_t)fw.x | ((uint32_t)fw.y << 16);
-                walk_forward(fw, nb_fw);
-                nb_fw = neighbours8(im, fw.x, fw.y);
-                if (++nf == len) {
-                    b.contours[ci] = ContourRec{(uint32_t)frame, (uint32_t)off, (uint32_t)len, (uint32_t)st.key};
-                    phase = 0;
-                    break;
+        }
+    }
+}
+
+// Writes the ordered points of every kept contour.  Two work items per contour: one walks forwards from the
+// start and fills the first half, the other walks backwards and fills the second half from the end (the
+// successor function is a permutation, so the predecessor walk visits the same cycle in reverse).  Lane
+// scheduled like k_trace.
+__global__ void __launch_bounds__(128) k_emit(Batch b) {
+    constexpr int STEPS = 16;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    unsigned int ncont = b.cnt->n_contours;
+    if (ncont > b.cap_contours) ncont = b.cap_contours;
+    const unsigned int n_items = 2u * ncont;
+    bool active = false, exhausted = false, backward = false;
+    BitImage im = b.bit_image(0);
+    WalkState w{0, 0, 0};
+    uint32_t nb = 0;
+    int remaining = 0;
+    uint32_t* out = nullptr;
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, !active && !exhausted);
+        if (idle) {
+            unsigned base = 0;
+            int leader = __ffs((int)idle) - 1;
+            if (lane == leader) base = atomicAdd(&b.cnt->emit_work, (unsigned)__popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (!active && !exhausted) {
+                unsigned i = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+                if (i >= n_items) {
+                    exhausted = true;
+                } else {
+                    const ContourRec rec = b.contours[i >> 1];
+                    const int n = (int)rec.n;
+                    if (n > 0) {
+                        im = b.bit_image((int)(rec.frame & 0x7FFFFFFFu));
+                        TraceStart st;
+                        make_start(im, (int)(rec.frame >> 31), (int)(rec.key % (uint32_t)b.W), (int)(rec.key / (uint32_t)b.W), st);
+                        w = WalkState{st.x, st.y, st.b};
+                        const int h0 = (n + 1) >> 1;
+                        backward = (i & 1u) != 0;
+                        if (!backward) {
+                            out = b.pool + rec.off;  // positions 0 .. h0-1, ascending
+                            remaining = h0;
+                            nb = neighbours8(im, w.x, w.y);
+                        } else {
+                            out = b.pool + rec.off + n - 1;  // positions n-1 .. h0, descending
+                            remaining = n - h0;
+                        }
+                        active = remaining > 0;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(FULL, active) == 0) {
+            if (__ballot_sync(FULL, !exhausted) == 0) break;
+            continue;
+        }
+        if (active) {
+            if (!backward) {
+                for (int r = 0; r < STEPS; r++) {
+                    *out++ = (uint32_t)w.x | ((uint32_t)w.y << 16);
+                    if (--remaining == 0) {
+                        active = false;
+                        break;
+                    }
+                    walk_forward(w, nb);
+                    nb = neighbours8(im, w.x, w.y);
+                }
+            } else {
+                for (int r = 0; r < STEPS; r++) {
+                    walk_backward(im, w);
+                    *out-- = (uint32_t)w.x | ((uint32_t)w.y << 16);
+                    if (--remaining == 0) {
+                        active = false;
+                        break;
+                    }
                 }
             }
         }

@@ -65,6 +65,76 @@ __device__ __forceinline__ int hrm_decode(const HrmDict& D, const uint8_t* cells
     return -1;
 }
 
+// cv::threshold(OTSU) threshold, same arithmetic per bin as otsu_threshold() in ab_math.cuh.  Only
+// the recurrence of (q1, mu1) is inherently sequential (its rounding sequence must be reproduced); it runs on
+// lane 0 in chunks of 32 bins, the other lanes then evaluate mu2 / sigma of "their" bin, and the first strict
+// maximum is found by a warp reduction.  Leading empty bins and the bins after q1 saturates are skipped: both
+// are exact no-ops of the sequential loop.  `scratch` = 64 doubles of shared memory.
+__device__ __forceinline__ int otsu_threshold_warp(const int* h, int N, double* scratch, int lane) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    // mu = sum i*h[i] / N : integer valued partial sums are exact in f64, so the order is free
+    long long part = 0;
+    for (int i = lane; i < 256; i += 32) part += (long long)i * h[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(FULL, part, d);
+    const double scale = 1. / N;
+    const double mu = (double)part * scale;
+    double* s_q = scratch;
+    double* s_m = scratch + 32;
+    double mu1 = 0, q1 = 0;  // lane 0 only
+    bool done = false;
+    double best_sigma = 0;
+    int best_i = 0;
+    for (int c = 0; c < 8; c++) {
+        if (lane == 0) {
+            for (int k = 0; k < 32; k++) {
+                const int i = 32 * c + k;
+                double q = -1.0, m = 0;
+                if (!done) {
+                    const double p_i = h[i] * scale;
+                    mu1 *= q1;
+                    q1 += p_i;
+                    const double q2 = 1. - q1;
+                    const double mn = q1 < q2 ? q1 : q2, mx = q1 < q2 ? q2 : q1;
+                    if (mx > 1. - FLT_EPSILON && q1 > q2) {
+                        done = true;  // q1 only grows: every later bin is skipped by the same test
+                    } else if (!(mn < FLT_EPSILON || mx > 1. - FLT_EPSILON)) {
+                        mu1 = (mu1 + i * p_i) / q1;
+                        q = q1;
+                        m = mu1;
+                    }
+                }
+                s_q[k] = q;
+                s_m[k] = m;
+            }
+        }
+        __syncwarp();
+        const double q = s_q[lane], m = s_m[lane];
+        if (q >= 0) {
+            const double q2 = 1. - q;
+            const double mu2 = (mu - q * m) / q2;
+            const double sigma = q * q2 * (m - mu2) * (m - mu2);
+            if (sigma > best_sigma) {  // within a lane bins come in increasing order: first strict maximum
+                best_sigma = sigma;
+                best_i = 32 * c + lane;
+            }
+        }
+        __syncwarp();
+    }
+    // across lanes: larger sigma wins, ties go to the smaller bin index
+    unsigned long long sb = (unsigned long long)__double_as_longlong(best_sigma);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        unsigned long long os = __shfl_xor_sync(FULL, sb, d);
+        int oi = __shfl_xor_sync(FULL, best_i, d);
+        if (os > sb || (os == sb && oi < best_i)) {
+            sb = os;
+            best_i = oi;
+        }
+    }
+    return sb ? best_i : 0;
+}
+
 inline size_t decode_smem_per_warp(int S) {
     return (((size_t)S * S + 15) & ~(size_t)15) + 256 * sizeof(int) + MAX_CELLS * sizeof(int) + 112 + 9 * sizeof(double) + 8 +
            DECODE_LIST * sizeof(unsigned short);
@@ -127,7 +197,11 @@ __global__ void __launch_bounds__(32 * DECODE_WARPS) k_decode(Batch b, int mode)
                 const float den = Mf[6] * fxp + Mf[7] * fyp + Mf[8];
                 const float fx = (Mf[0] * fxp + Mf[1] * fyp + Mf[2]) / den, fy = (Mf[3] * fxp + Mf[4] * fyp + Mf[5]) / den;
                 const float rx = rintf(fx), ry = rintf(fy);
-                unc = !(fabsf(fx) < 32768.f && fabsf(fy) < 32768.f) || fabsf(fx - rx) > 0.45f || fabsf(fy - ry) > 0.45f;
+                // forward error bound of the f32 evaluation (unit roundoff 6e-8; 1e-6 leaves > 3x slack), doubled
+                const float iad = 1.f / fabsf(den);
+                const float ex = 2e-6f * ((fabsf(Mf[0] * fxp) + fabsf(Mf[1] * fyp) + fabsf(Mf[2])) * iad + fabsf(fx)) + 2e-4f;
+                const float ey = 2e-6f * ((fabsf(Mf[3] * fxp) + fabsf(Mf[4] * fyp) + fabsf(Mf[5])) * iad + fabsf(fy)) + 2e-4f;
+                unc = !(fabsf(fx) < 32768.f && fabsf(fy) < 32768.f) || !(0.5f - fabsf(fx - rx) > ex) || !(0.5f - fabsf(fy - ry) > ey);
                 if (!unc) {
                     const int sx = (int)rx, sy = (int)ry;
                     uint8_t v = 0;
@@ -173,9 +247,7 @@ __global__ void __launch_bounds__(32 * DECODE_WARPS) k_decode(Batch b, int mode)
     }
     __syncwarp();
     if (mode == 1) return;
-    int thr = 0;
-    if (lane == 0) thr = otsu_threshold(s_hist, S * S);
-    thr = __shfl_sync(0xFFFFFFFFu, thr, 0);
+    const int thr = otsu_threshold_warp(s_hist, S * S, reinterpret_cast<double*>(s_list), lane);
     const int ncell = (b.decoder == AB_DECODER_HRM) ? b.dict.n + 2 : 7;
     const int cell = S / ncell;
     const int span = cell * ncell;

@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(128) k_polygon(Batch b) {
     unsigned int ncont = b.cnt->n_contours;
     if (ncont > b.cap_contours) ncont = b.cap_contours;
     for (unsigned int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < ncont; ci += nwarps) {
-        const ContourRec rec = b.contours[ci];
+        ContourRec rec = b.contours[ci];
+        rec.frame &= 0x7FFFFFFFu;  // bit 31 = border type (outer/hole), used by k_emit only
         const int n = (int)rec.n;
         if (n < 4) continue;
         const uint32_t* pts = b.pool + rec.off;

@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 W, H, N_MARKERS, BATCH, SIGMA = 3840, 2160, 100, 256, 2.0
 N_BASE = 8          # distinct rendered scenes; every frame of a batch gets its own noise realisation
 MARKER_SIZE = 0.05
-KERNELS_PER_BATCH = 8  # threshold, scan_starts, trace, polygon, frame_filter, decode, refine_lines, finalize
+KERNELS_PER_BATCH = 9  # threshold, scan_starts, trace, emit, polygon, frame_filter, decode, refine_lines, finalize
 
 
 def log(*a):
@@ -86,6 +86,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, so do not ask OpenMP)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def oracle_params():
     from oracle.cv2_oracle import Params
     return Params()
@@ -107,7 +115,7 @@ def run_reference(args):
     from aruco_b200 import synth
     from oracle import native
     native.load()
-    threads = native.max_threads()
+    threads = host_threads()
     sample = max(threads, 16)
     rng = np.random.default_rng(7)
     scenes = base_scenes(min(N_BASE, 4), 0)
@@ -307,7 +315,7 @@ def main():
     cpu = None
     if not args.skip_cpu:
         from oracle import native
-        threads = native.max_threads()
+        threads = host_threads()
         sample = max(2 * threads, 32)
         hostf = frames[:sample].cpu().numpy()
         native.detect_batch(hostf[:threads], oracle_params(), K, D, MARKER_SIZE, threads=threads)
