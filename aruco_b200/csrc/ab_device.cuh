@@ -24,6 +24,15 @@ struct ContourRec {
     uint32_t key;  // raster scan position of the Suzuki start (ordering = reverse discovery)
 };
 
+// a border walk parked by k_trace<false> for k_trace<true> (full walker state)
+struct LongRec {
+    uint32_t frame;  // bit 31 = border type
+    uint32_t key;
+    uint32_t sxy, fxy, bxy;  // start / forward walker / backward walker pixel (x | y << 16)
+    uint32_t dirs;           // fw.b | bw.b << 4 | start.b << 8
+    uint32_t nf, ng;
+};
+
 struct QuadRec {
     short x[4], y[4];
     uint32_t key;
@@ -47,6 +56,7 @@ struct Counters {
     unsigned int trace_work;
     unsigned int err;
     unsigned int emit_work;
+    unsigned int n_long, long_work;
     unsigned long long n_quads_total, n_cands_total, n_markers_total;
 };
 
@@ -76,6 +86,8 @@ struct Batch {
     unsigned int cap_contours;
     uint32_t* pool;
     unsigned long long cap_pool;
+    LongRec* longq;
+    unsigned int cap_long;
     QuadRec* quads;  // [B][cap_q]
     int cap_q;
     CandRec* cands;  // [B][cap_c]

@@ -45,6 +45,8 @@ struct ab_context {
     uint2* d_starts = nullptr;
     ContourRec* d_contours = nullptr;
     uint32_t* d_pool = nullptr;
+    LongRec* d_longq = nullptr;
+    unsigned capLongPF = 8192;
     QuadRec* d_quads = nullptr;
     CandRec* d_cands = nullptr;
     uint8_t* d_canon = nullptr;
@@ -109,6 +111,7 @@ static void free_buffers(ab_context* c) {
     F(c->d_starts);
     F(c->d_contours);
     F(c->d_pool);
+    F(c->d_longq);
     F(c->d_quads);
     F(c->d_cands);
     F(c->d_canon);
@@ -366,6 +369,7 @@ int ab_reserve(ab_context* ctx, int width, int height, int max_batch, int max_qu
     CK(cudaMalloc(&ctx->d_starts, B * capS * sizeof(uint2)));
     CK(cudaMalloc(&ctx->d_contours, B * ctx->capContoursPF * sizeof(ContourRec)));
     CK(cudaMalloc(&ctx->d_pool, B * capP * 4));
+    CK(cudaMalloc(&ctx->d_longq, B * ctx->capLongPF * sizeof(LongRec)));
     CK(cudaMalloc(&ctx->d_quads, B * capQ * sizeof(QuadRec)));
     CK(cudaMalloc(&ctx->d_cands, B * capC * sizeof(CandRec)));
     CK(cudaMalloc(&ctx->d_canon, B * capC * (size_t)ctx->S_alloc * ctx->S_alloc));
@@ -490,6 +494,8 @@ static int fill_batch(ab_context* ctx, Batch& b, const uint8_t* dgrey, size_t ro
     b.cap_starts = (unsigned long long)ctx->capStartsPF * n;
     b.contours = ctx->d_contours;
     b.cap_contours = ctx->capContoursPF * (unsigned)n;
+    b.longq = ctx->d_longq;
+    b.cap_long = ctx->capLongPF * (unsigned)n;
     b.pool = ctx->d_pool;
     b.cap_pool = (unsigned long long)ctx->capPoolPF * n;
     b.quads = ctx->d_quads;
@@ -557,7 +563,8 @@ static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t f
     if (ctx->timing) cudaEventRecord(ctx->ev[1], st);
     k_scan_starts<<<sms * 8, 256, 0, st>>>(b);
     if (ctx->timing) cudaEventRecord(ctx->kev[2], st);
-    k_trace<<<sms * 8, 128, 0, st>>>(b);
+    k_trace<false><<<sms * 8, 128, 0, st>>>(b);
+    k_trace<true><<<sms * 4, 128, 0, st>>>(b);
     k_emit<<<sms * 8, 128, 0, st>>>(b);
     if (ctx->timing) cudaEventRecord(ctx->kev[3], st);
     k_polygon<<<sms * 4, 128, 0, st>>>(b);
@@ -921,7 +928,8 @@ int ab_detect_rectangles(ab_context* ctx, const uint8_t* thres, int width, int h
     k_threshold_fixed<<<ctx->sm_count * 8, 256, 0, st>>>(b.grey, b.grey_row, b.grey_frame, b.thres, b.bits, b.bits_words, b.W, b.H,
                                                           b.wpr, 0, 1, 1);
     k_scan_starts<<<ctx->sm_count * 8, 256, 0, st>>>(b);
-    k_trace<<<ctx->sm_count * 8, 128, 0, st>>>(b);
+    k_trace<false><<<ctx->sm_count * 8, 128, 0, st>>>(b);
+    k_trace<true><<<ctx->sm_count * 4, 128, 0, st>>>(b);
     k_emit<<<ctx->sm_count * 8, 128, 0, st>>>(b);
     k_polygon<<<ctx->sm_count * 4, 128, 0, st>>>(b);
     k_frame_filter<<<1, 256, 0, st>>>(b);

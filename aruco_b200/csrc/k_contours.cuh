@@ -79,13 +79,29 @@ __global__ void __launch_bounds__(256) k_scan_starts(Batch b) {
 // from 2 to max_len).  The walk is the bidirectional search of find_start_bidir (ab_trace.cuh), executed
 // STEPS at a time; the Suzuki start of a border with min_len < n < max_len reserves its slice of the point
 // pool and leaves a contour record -- the points themselves are written by k_emit.
+//
+// Two-level scheduling: border lengths are extremely skewed (thousands of 2..30-step speckle walks per frame,
+// a few hundred walks of 300..3800 steps).  A walk that is still alive after LONG_T steps is parked in a queue
+// (full walker state) and its lane is refilled; k_trace<true> then runs the parked walks to completion in
+// densely populated warps.  Without this, the long walks end up one or two per warp and the kernel spends
+// most of its time issuing instructions for ~9 of 32 lanes (ncu r1e).
+constexpr int TRACE_LONG_T = 48;
+
+template <bool LONG>
 __global__ void __launch_bounds__(128) k_trace(Batch b) {
     constexpr int STEPS = 8;
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
-    unsigned long long n_starts = b.cnt->n_starts;
-    if (n_starts > b.cap_starts) return;  // overflow already flagged by k_scan_starts; the list has holes
-    bool active = false, exhausted = false;
+    unsigned long long n_items;
+    if (LONG) {
+        n_items = b.cnt->n_long;
+        if (n_items > b.cap_long) n_items = b.cap_long;
+    } else {
+        n_items = b.cnt->n_starts;
+        if (n_items > b.cap_starts) return;  // overflow already flagged by k_scan_starts; the list has holes
+    }
+    unsigned int* work = LONG ? &b.cnt->long_work : &b.cnt->trace_work;
+    bool active = false, exhausted = false, nodefer = LONG;
     BitImage im = b.bit_image(0);
     TraceStart st{0, 0, 0, 0};
     WalkState fw{0, 0, 0}, bw{0, 0, 0};
@@ -96,12 +112,27 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
         if (idle) {
             unsigned base = 0;
             int leader = __ffs((int)idle) - 1;
-            if (lane == leader) base = atomicAdd(&b.cnt->trace_work, (unsigned)__popc(idle));
+            if (lane == leader) base = atomicAdd(work, (unsigned)__popc(idle));
             base = __shfl_sync(FULL, base, leader);
             if (!active && !exhausted) {
                 unsigned long long i = (unsigned long long)base + (unsigned)__popc(idle & ((1u << lane) - 1u));
-                if (i >= n_starts) {
+                if (i >= n_items) {
                     exhausted = true;
+                } else if (LONG) {
+                    const LongRec q = b.longq[i];
+                    frame = (int)(q.frame & 0x7FFFFFFFu);
+                    type_bit = q.frame & 0x80000000u;
+                    im = b.bit_image(frame);
+                    st.key = q.key;
+                    st.x = (int)(q.sxy & 0xFFFFu);
+                    st.y = (int)(q.sxy >> 16);
+                    st.b = (int)((q.dirs >> 8) & 7u);
+                    fw = WalkState{(int)(q.fxy & 0xFFFFu), (int)(q.fxy >> 16), (int)(q.dirs & 7u)};
+                    bw = WalkState{(int)(q.bxy & 0xFFFFu), (int)(q.bxy >> 16), (int)((q.dirs >> 4) & 7u)};
+                    nf = (int)q.nf;
+                    ng = (int)q.ng;
+                    nb_fw = neighbours8(im, fw.x, fw.y);
+                    active = true;
                 } else {
                     uint2 rec = b.starts[i];
                     frame = (int)(rec.x & 0x7FFFFFFFu);
@@ -112,6 +143,7 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                         bw = fw;
                         nb_fw = neighbours8(im, fw.x, fw.y);
                         nf = ng = 0;
+                        nodefer = false;
                         active = true;
                     }  // else: isolated pixel, a 1-point contour that is never kept
                 }
@@ -157,6 +189,24 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                 if (dead) {
                     active = false;
                     break;
+                }
+            }
+            if (!LONG && active && !nodefer && nf >= TRACE_LONG_T) {
+                unsigned int qi = atomicAdd(&b.cnt->n_long, 1u);
+                if (qi < b.cap_long) {
+                    LongRec q;
+                    q.frame = (uint32_t)frame | type_bit;
+                    q.key = (uint32_t)st.key;
+                    q.sxy = (uint32_t)st.x | ((uint32_t)st.y << 16);
+                    q.fxy = (uint32_t)fw.x | ((uint32_t)fw.y << 16);
+                    q.bxy = (uint32_t)bw.x | ((uint32_t)bw.y << 16);
+                    q.dirs = (uint32_t)fw.b | ((uint32_t)bw.b << 4) | ((uint32_t)st.b << 8);
+                    q.nf = (uint32_t)nf;
+                    q.ng = (uint32_t)ng;
+                    b.longq[qi] = q;
+                    active = false;
+                } else {
+                    nodefer = true;  // queue full: finish this walk in place (correct, just slower)
                 }
             }
         }

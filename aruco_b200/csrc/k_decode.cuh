@@ -191,7 +191,6 @@ __global__ void __launch_bounds__(32 * DECODE_WARPS) k_decode(Batch b, int mode)
             if (!ok) {
                 s_img[i] = 0;
                 canon[i] = 0;
-                atomicAdd(&s_hist[0], 1);
             } else {
                 const float fxp = (float)x, fyp = (float)y;
                 const float den = Mf[6] * fxp + Mf[7] * fyp + Mf[8];
@@ -208,7 +207,6 @@ __global__ void __launch_bounds__(32 * DECODE_WARPS) k_decode(Batch b, int mode)
                     if (sx >= 0 && sy >= 0 && sx < b.W && sy < b.H) v = grey[(size_t)sy * b.grey_row + sx];
                     s_img[i] = v;
                     canon[i] = v;
-                    atomicAdd(&s_hist[v], 1);
                 }
             }
         }
@@ -226,7 +224,6 @@ __global__ void __launch_bounds__(32 * DECODE_WARPS) k_decode(Batch b, int mode)
                     if (sx >= 0 && sy >= 0 && sx < b.W && sy < b.H) v = grey[(size_t)sy * b.grey_row + sx];
                     s_img[i] = v;
                     canon[i] = v;
-                    atomicAdd(&s_hist[v], 1);
                 }
             }
             nunc += __popc(m);
@@ -243,20 +240,32 @@ __global__ void __launch_bounds__(32 * DECODE_WARPS) k_decode(Batch b, int mode)
         if (sx >= 0 && sy >= 0 && sx < b.W && sy < b.H) v = grey[(size_t)sy * b.grey_row + sx];
         s_img[i] = v;
         canon[i] = v;
-        atomicAdd(&s_hist[v], 1);
     }
     __syncwarp();
     if (mode == 1) return;
+    // 256-bin histogram: lanes holding the same grey level are matched, one of them adds the group size
+    // (shared-memory atomics on a bimodal image serialise almost completely: 18 % of the stall samples in r1e)
+    for (int i0 = 0; i0 < S * S; i0 += 32) {
+        const int i = i0 + lane;
+        const unsigned v = i < S * S ? (unsigned)s_img[i] : 0x100u + (unsigned)lane;
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, v);
+        if (i < S * S && lane == __ffs((int)peers) - 1) s_hist[v] += __popc(peers);
+    }
+    __syncwarp();
     const int thr = otsu_threshold_warp(s_hist, S * S, reinterpret_cast<double*>(s_list), lane);
     const int ncell = (b.decoder == AB_DECODER_HRM) ? b.dict.n + 2 : 7;
     const int cell = S / ncell;
     const int span = cell * ncell;
-    for (int i = lane; i < span * span; i += 32) {
-        int y = i / span, x = i - y * span;
-        if (s_img[y * S + x] > thr) atomicAdd(&s_cnt[(y / cell) * ncell + (x / cell)], 1);
+    (void)span;
+    for (int cidx = lane; cidx < ncell * ncell; cidx += 32) {  // one lane per cell: no atomics
+        const int cy = cidx / ncell, cx = cidx - cy * ncell;
+        int cnt = 0;
+        for (int yy = 0; yy < cell; yy++) {
+            const uint8_t* rowp = s_img + (cy * cell + yy) * S + cx * cell;
+            for (int xx = 0; xx < cell; xx++) cnt += rowp[xx] > thr;
+        }
+        s_cells[cidx] = cnt > (cell * cell) / 2;
     }
-    __syncwarp();
-    for (int i = lane; i < ncell * ncell; i += 32) s_cells[i] = s_cnt[i] > (cell * cell) / 2;
     __syncwarp();
     if (b.decoder == AB_DECODER_HRM) {
         int nrot = 0;
