@@ -156,14 +156,21 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
         if (active) {
             for (int r = 0; r < STEPS; r++) {
                 bool closed = false, dead = false;
+                // both walkers step first so that their neighbourhood loads are in flight together (the two
+                // dependent load rounds per iteration were the latency floor of long walks); the backward step
+                // is only COMMITTED if the forward step neither closed the cycle nor hit a smaller start
+                const WalkState bw0 = bw;
                 walk_forward(fw, nb_fw);
+                nb_fw = neighbours8(im, fw.x, fw.y);
+                WalkState bw1 = bw0;
+                const uint32_t nb_bw = walk_backward(im, bw1);
                 nf++;
-                if (same_state(fw, bw)) {
+                if (same_state(fw, bw0)) {
                     closed = true;
-                } else if (is_smaller_trigger(im, fw, nb_fw = neighbours8(im, fw.x, fw.y), st.key)) {
+                } else if (is_smaller_trigger(im, fw, nb_fw, st.key)) {
                     dead = true;
                 } else {
-                    uint32_t nb_bw = walk_backward(im, bw);
+                    bw = bw1;
                     ng++;
                     if (same_state(fw, bw)) closed = true;
                     else if (is_smaller_trigger(im, bw, nb_bw, st.key)) dead = true;

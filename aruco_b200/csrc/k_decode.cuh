@@ -183,21 +183,28 @@ __global__ void __launch_bounds__(32 * DECODE_WARPS) k_decode(Batch b, int mode)
 #pragma unroll
     for (int q = 0; q < 9; q++) Mf[q] = ok ? (float)s_Mi[q] : 0.f;
     int nunc = 0;
+    int px = lane % S, py = lane / S;  // pixel (x,y) of index i = i0 + lane, advanced incrementally
     for (int i0 = 0; i0 < S * S; i0 += 32) {
         const int i = i0 + lane;
         bool unc = false;
+        const int x = px, y = py;
+        px += 32;
+        while (px >= S) {
+            px -= S;
+            py++;
+        }
         if (i < S * S) {
-            const int y = i / S, x = i - y * S;
             if (!ok) {
                 s_img[i] = 0;
                 canon[i] = 0;
             } else {
                 const float fxp = (float)x, fyp = (float)y;
                 const float den = Mf[6] * fxp + Mf[7] * fyp + Mf[8];
-                const float fx = (Mf[0] * fxp + Mf[1] * fyp + Mf[2]) / den, fy = (Mf[3] * fxp + Mf[4] * fyp + Mf[5]) / den;
+                const float iden = __frcp_rn(den);
+                const float fx = (Mf[0] * fxp + Mf[1] * fyp + Mf[2]) * iden, fy = (Mf[3] * fxp + Mf[4] * fyp + Mf[5]) * iden;
                 const float rx = rintf(fx), ry = rintf(fy);
                 // forward error bound of the f32 evaluation (unit roundoff 6e-8; 1e-6 leaves > 3x slack), doubled
-                const float iad = 1.f / fabsf(den);
+                const float iad = fabsf(iden);
                 const float ex = 2e-6f * ((fabsf(Mf[0] * fxp) + fabsf(Mf[1] * fyp) + fabsf(Mf[2])) * iad + fabsf(fx)) + 2e-4f;
                 const float ey = 2e-6f * ((fabsf(Mf[3] * fxp) + fabsf(Mf[4] * fyp) + fabsf(Mf[5])) * iad + fabsf(fy)) + 2e-4f;
                 unc = !(fabsf(fx) < 32768.f && fabsf(fy) < 32768.f) || !(0.5f - fabsf(fx - rx) > ex) || !(0.5f - fabsf(fy - ry) > ey);
