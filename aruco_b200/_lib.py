@@ -22,6 +22,15 @@ class ab_params(C.Structure):
                 ("erosion", C.c_int32), ("decoder", C.c_int32), ("set_y_perpendicular", C.c_int32)]
 
 
+class ab_board_config(C.Structure):
+    _fields_ = [("n_markers", C.c_int32), ("info_type", C.c_int32), ("ids", C.c_void_p), ("corners", C.c_void_p)]
+
+
+class ab_board(C.Structure):
+    _fields_ = [("n_markers", C.c_int32), ("has_pose", C.c_int32), ("prob", C.c_float), ("ssize", C.c_float),
+                ("rvec", C.c_double * 3), ("tvec", C.c_double * 3)]
+
+
 class ab_marker(C.Structure):
     _fields_ = [("id", C.c_int32), ("has_pose", C.c_int32), ("corners", C.c_float * 8), ("ssize", C.c_float),
                 ("pad_", C.c_float), ("rvec", C.c_double * 3), ("tvec", C.c_double * 3)]
@@ -60,6 +69,7 @@ SYMBOLS = {
     "ab_detect_rectangles": (_i, [_vp, _vp, _i, _i, _sz, _vp, _i, C.POINTER(C.c_int32)]),
     "ab_warp": (_i, [_vp, _vp, _i, _i, _sz, _vp, _i, _vp]),
     "ab_calculate_extrinsics": (_i, [_vp, _vp, _i, _vp, _vp, _f, _i]),
+    "ab_detect_board": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _f, _i, _vp, _vp]),
     "ab_host_alloc": (_i, [C.POINTER(_vp), _sz]),
     "ab_host_free": (_i, [_vp]),
 }

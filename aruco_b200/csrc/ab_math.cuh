@@ -704,4 +704,245 @@ AB_HD void rotate_x_axis(double* rvec) {
     mat_to_rodrigues(Rd, rvec);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// N-point planar pose (BoardDetector::detect -> cv::solvePnP on 4*M stacked marker corners,
+// src/boarddetector.cpp:132-157, and its outlier re-solve :172-194).  Same structure as
+// cvFindExtrinsicCameraParams2's planar branch: centre the object points, homography to the normalised image
+// points (normalised DLT, least squares for N > 4), decomposition, then the CvLevMarq schedule over all points.
+// ---------------------------------------------------------------------------------------------------
+AB_HD void jacobi_eigen9(double A[9][9], double V[9][9]) {
+    for (int i = 0; i < 9; i++)
+        for (int j = 0; j < 9; j++) V[i][j] = (i == j) ? 1. : 0.;
+    for (int sweep = 0; sweep < 30; sweep++) {
+        double off = 0;
+        for (int i = 0; i < 9; i++)
+            for (int j = i + 1; j < 9; j++) off += A[i][j] * A[i][j];
+        if (off < 1e-300) break;
+        for (int p = 0; p < 8; p++)
+            for (int q = p + 1; q < 9; q++) {
+                if (fabs(A[p][q]) < 1e-300) continue;
+                double th = (A[q][q] - A[p][p]) / (2 * A[p][q]);
+                double t = (th >= 0 ? 1. : -1.) / (fabs(th) + sqrt(th * th + 1));
+                double c = 1 / sqrt(t * t + 1), sn = t * c;
+                for (int k = 0; k < 9; k++) {
+                    double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - sn * akq;
+                    A[k][q] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < 9; k++) {
+                    double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - sn * aqk;
+                    A[q][k] = sn * apk + c * aqk;
+                }
+                for (int k = 0; k < 9; k++) {
+                    double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - sn * vkq;
+                    V[k][q] = sn * vkp + c * vkq;
+                }
+            }
+    }
+}
+
+// residual (and J^T J, J^T e) of all N points for pose p; returns |e|^2
+AB_HD double pnp_accumulate(const Camera& cam, const double* p, const float* obj, const float* img, int N, bool with_jac,
+                            double JtJ[6][6], double* JtErr) {
+    double R[9], dR[3][9];
+    if (with_jac) {
+        rodrigues_jacobian(p, R, dR);
+        for (int i = 0; i < 6; i++) {
+            JtErr[i] = 0;
+            for (int j = 0; j < 6; j++) JtJ[i][j] = 0;
+        }
+    } else {
+        rodrigues_to_mat(p, R);
+    }
+    double e2 = 0;
+    for (int n = 0; n < N; n++) {
+        double X = obj[3 * n], Y = obj[3 * n + 1], Z = obj[3 * n + 2];
+        double x = R[0] * X + R[1] * Y + R[2] * Z + p[3];
+        double y = R[3] * X + R[4] * Y + R[5] * Z + p[4];
+        double z = R[6] * X + R[7] * Y + R[8] * Z + p[5];
+        double iz = z ? 1. / z : 1.;
+        double xn = x * iz, yn = y * iz;
+        double r2 = xn * xn + yn * yn, r4 = r2 * r2, r6 = r4 * r2;
+        double a1 = 2 * xn * yn, a2 = r2 + 2 * xn * xn, a3 = r2 + 2 * yn * yn;
+        double cdist = 1 + cam.k1 * r2 + cam.k2 * r4 + cam.k3 * r6;
+        double xd = xn * cdist + cam.p1 * a1 + cam.p2 * a2, yd = yn * cdist + cam.p1 * a3 + cam.p2 * a1;
+        double eu = xd * cam.fx + cam.cx - (double)img[2 * n], ev = yd * cam.fy + cam.cy - (double)img[2 * n + 1];
+        e2 += eu * eu + ev * ev;
+        if (!with_jac) continue;
+        double dc = cam.k1 + 2 * cam.k2 * r2 + 3 * cam.k3 * r4;
+        double dxdx = cdist + 2 * xn * xn * dc + 2 * cam.p1 * yn + 6 * cam.p2 * xn;
+        double dxdy = 2 * xn * yn * dc + 2 * cam.p1 * xn + 2 * cam.p2 * yn;
+        double dydx = dxdy;
+        double dydy = cdist + 2 * yn * yn * dc + 6 * cam.p1 * yn + 2 * cam.p2 * xn;
+        double dxn[3] = {iz, 0, -xn * iz}, dyn[3] = {0, iz, -yn * iz};
+        double du[3], dv[3], Ju[6], Jv[6];
+        for (int c = 0; c < 3; c++) {
+            du[c] = cam.fx * (dxdx * dxn[c] + dxdy * dyn[c]);
+            dv[c] = cam.fy * (dydx * dxn[c] + dydy * dyn[c]);
+        }
+        for (int k = 0; k < 3; k++) {
+            double dX[3] = {dR[k][0] * X + dR[k][1] * Y + dR[k][2] * Z, dR[k][3] * X + dR[k][4] * Y + dR[k][5] * Z,
+                            dR[k][6] * X + dR[k][7] * Y + dR[k][8] * Z};
+            Ju[k] = du[0] * dX[0] + du[1] * dX[1] + du[2] * dX[2];
+            Jv[k] = dv[0] * dX[0] + dv[1] * dX[1] + dv[2] * dX[2];
+            Ju[3 + k] = du[k];
+            Jv[3 + k] = dv[k];
+        }
+        for (int i = 0; i < 6; i++) {
+            JtErr[i] += Ju[i] * eu + Jv[i] * ev;
+            for (int j = 0; j < 6; j++) JtJ[i][j] += Ju[i] * Ju[j] + Jv[i] * Jv[j];
+        }
+    }
+    return e2;
+}
+
+// obj: N x 3 (a z = const plane), img: N x 2 pixels.  Returns false for degenerate input.
+AB_HD bool solve_pnp_planar(const Camera& cam, const float* obj, const float* img, int N, double* rvec, double* tvec) {
+    if (N < 4) return false;
+    // object centroid; the board must lie in a z = const plane (every reference board configuration does)
+    double Mc[3] = {0, 0, 0};
+    for (int n = 0; n < N; n++)
+        for (int c = 0; c < 3; c++) Mc[c] += obj[3 * n + c];
+    for (int c = 0; c < 3; c++) Mc[c] /= N;
+    double spread = 0, zdev = 0;
+    for (int n = 0; n < N; n++) {
+        spread += fabs(obj[3 * n] - Mc[0]) + fabs(obj[3 * n + 1] - Mc[1]);
+        zdev += fabs(obj[3 * n + 2] - Mc[2]);
+    }
+    if (!(spread > 0) || zdev > 1e-6 * spread) return false;
+    // normalised DLT (cv::findHomography, method 0): object (X,Y) -> normalised image (x,y)
+    double cM[2] = {Mc[0], Mc[1]}, cm[2] = {0, 0}, sM[2] = {0, 0}, sm[2] = {0, 0};
+    for (int n = 0; n < N; n++) {
+        double xn, yn;
+        undistort_point_norm(cam, img[2 * n], img[2 * n + 1], &xn, &yn);
+        cm[0] += xn;
+        cm[1] += yn;
+    }
+    cm[0] /= N;
+    cm[1] /= N;
+    for (int n = 0; n < N; n++) {
+        double xn, yn;
+        undistort_point_norm(cam, img[2 * n], img[2 * n + 1], &xn, &yn);
+        sm[0] += fabs(xn - cm[0]);
+        sm[1] += fabs(yn - cm[1]);
+        sM[0] += fabs(obj[3 * n] - cM[0]);
+        sM[1] += fabs(obj[3 * n + 1] - cM[1]);
+    }
+    if (fabs(sM[0]) < DBL_EPSILON || fabs(sM[1]) < DBL_EPSILON || fabs(sm[0]) < DBL_EPSILON || fabs(sm[1]) < DBL_EPSILON) return false;
+    sm[0] = N / sm[0];
+    sm[1] = N / sm[1];
+    sM[0] = N / sM[0];
+    sM[1] = N / sM[1];
+    double LtL[9][9], V[9][9];
+    for (int i = 0; i < 9; i++)
+        for (int j = 0; j < 9; j++) LtL[i][j] = 0;
+    for (int n = 0; n < N; n++) {
+        double xn, yn;
+        undistort_point_norm(cam, img[2 * n], img[2 * n + 1], &xn, &yn);
+        double x = (xn - cm[0]) * sm[0], y = (yn - cm[1]) * sm[1];
+        double X = (obj[3 * n] - cM[0]) * sM[0], Y = (obj[3 * n + 1] - cM[1]) * sM[1];
+        double Lx[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x}, Ly[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
+        for (int j = 0; j < 9; j++)
+            for (int k = j; k < 9; k++) LtL[j][k] += Lx[j] * Lx[k] + Ly[j] * Ly[k];
+    }
+    for (int j = 0; j < 9; j++)
+        for (int k = 0; k < j; k++) LtL[j][k] = LtL[k][j];
+    jacobi_eigen9(LtL, V);
+    int best = 0;
+    for (int j = 1; j < 9; j++)
+        if (LtL[j][j] < LtL[best][best]) best = j;
+    double H0[9];
+    for (int j = 0; j < 9; j++) H0[j] = V[j][best];
+    // H = invHnorm * H0 * Hnorm2
+    double iH[9] = {1. / sm[0], 0, cm[0], 0, 1. / sm[1], cm[1], 0, 0, 1};
+    double H2[9] = {sM[0], 0, -cM[0] * sM[0], 0, sM[1], -cM[1] * sM[1], 0, 0, 1};
+    double T[9], Hm[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double q = 0;
+            for (int k = 0; k < 3; k++) q += iH[i * 3 + k] * H0[k * 3 + j];
+            T[i * 3 + j] = q;
+        }
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double q = 0;
+            for (int k = 0; k < 3; k++) q += T[i * 3 + k] * H2[k * 3 + j];
+            Hm[i * 3 + j] = q;
+        }
+    if (fabs(Hm[8]) < 1e-300) return false;
+    // Hm maps ABSOLUTE object (X,Y) (Hnorm2 removes the centroid); the reference maps centred coordinates and
+    // adds R*T_transform afterwards -- identical pose
+    for (int j = 0; j < 9; j++) Hm[j] /= Hm[8];
+    double h1[3] = {Hm[0], Hm[3], Hm[6]}, h2[3] = {Hm[1], Hm[4], Hm[7]}, h3[3] = {Hm[2], Hm[5], Hm[8]};
+    double n1 = sqrt(h1[0] * h1[0] + h1[1] * h1[1] + h1[2] * h1[2]);
+    double n2 = sqrt(h2[0] * h2[0] + h2[1] * h2[1] + h2[2] * h2[2]);
+    if (!(n1 > DBL_EPSILON) || !(n2 > DBL_EPSILON)) return false;
+    for (int i = 0; i < 3; i++) {
+        h1[i] /= n1;
+        h2[i] /= n2;
+    }
+    double sc = 2. / (n1 + n2);
+    double p[6];
+    double c3[3] = {h1[1] * h2[2] - h1[2] * h2[1], h1[2] * h2[0] - h1[0] * h2[2], h1[0] * h2[1] - h1[1] * h2[0]};
+    double R[9] = {h1[0], h2[0], c3[0], h1[1], h2[1], c3[1], h1[2], h2[2], c3[2]};
+    orthonormalize3(R);
+    mat_to_rodrigues(R, p);
+    // translation of the plane origin (z = Mc[2] offset folded in: t = h3*sc - R*(0,0,Mc_z) ... the homography was
+    // fitted on (X,Y) only, so the plane's constant z enters through R's third column)
+    p[3] = h3[0] * sc - R[2] * Mc[2];
+    p[4] = h3[1] * sc - R[5] * Mc[2];
+    p[5] = h3[2] * sc - R[8] * Mc[2];
+    if (p[5] < 0) {  // the plane must be in front of the camera: take the mirrored decomposition
+        for (int i = 0; i < 3; i++) {
+            h1[i] = -h1[i];
+            h2[i] = -h2[i];
+        }
+        double R2[9] = {h1[0], h2[0], c3[0], h1[1], h2[1], c3[1], h1[2], h2[2], c3[2]};
+        orthonormalize3(R2);
+        mat_to_rodrigues(R2, p);
+        p[3] = -h3[0] * sc - R2[2] * Mc[2];
+        p[4] = -h3[1] * sc - R2[5] * Mc[2];
+        p[5] = -h3[2] * sc - R2[8] * Mc[2];
+    }
+    // CvLevMarq schedule (see solve_pnp_marker)
+    double JtJ[6][6], JtErr[6], prev[6];
+    int lambdaLg10 = -3, iters = 0;
+    double prevErrNorm = sqrt(pnp_accumulate(cam, p, obj, img, N, true, JtJ, JtErr));
+    for (;;) {
+        for (int i = 0; i < 6; i++) prev[i] = p[i];
+        double errNorm = 0;
+        for (;;) {
+            double lambda = exp(lambdaLg10 * 2.302585092994046);
+            double A[6][6], d[6];
+            for (int i = 0; i < 6; i++) {
+                for (int j = 0; j < 6; j++) A[i][j] = JtJ[i][j];
+                A[i][i] *= 1. + lambda;
+                d[i] = JtErr[i];
+            }
+            if (!solve6(A, d))
+                for (int i = 0; i < 6; i++) d[i] = 0;
+            for (int i = 0; i < 6; i++) p[i] = prev[i] - d[i];
+            errNorm = sqrt(pnp_accumulate(cam, p, obj, img, N, false, nullptr, nullptr));
+            if (errNorm > prevErrNorm && ++lambdaLg10 <= 16) continue;
+            break;
+        }
+        lambdaLg10 = lambdaLg10 - 1 > -16 ? lambdaLg10 - 1 : -16;
+        double dn = 0, pn = 0;
+        for (int i = 0; i < 6; i++) {
+            dn += (p[i] - prev[i]) * (p[i] - prev[i]);
+            pn += prev[i] * prev[i];
+        }
+        if (++iters >= 20 || sqrt(dn) / sqrt(pn) < FLT_EPSILON) break;
+        prevErrNorm = errNorm;
+        pnp_accumulate(cam, p, obj, img, N, true, JtJ, JtErr);
+    }
+    for (int i = 0; i < 3; i++) {
+        rvec[i] = p[i];
+        tvec[i] = p[3 + i];
+    }
+    return true;
+}
+
 }  // namespace ab

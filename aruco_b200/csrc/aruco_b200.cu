@@ -981,6 +981,82 @@ int ab_calculate_extrinsics(ab_context* ctx, ab_marker* markers, int n, const fl
     return AB_OK;
 }
 
+int ab_detect_board(ab_context* ctx, const ab_marker* markers, int n, const ab_board_config* cfg, const float* K, const float* D,
+                    float marker_size, float repj_err_thres, int set_y_perp, ab_marker* board_markers, ab_board* out) {
+    if (!ctx || !cfg || !out || n < 0 || (n > 0 && !markers)) return set_err(ctx, AB_E_INVALID, "ab_detect_board: bad arguments");
+    // CV_Assert(BConf.objPoints.size() != 0 ...) (boarddetector.cpp:93)
+    if (cfg->n_markers <= 0 || !cfg->ids || !cfg->corners) return set_err(ctx, AB_E_INVALID, "invalid BoardConfig that is empty");
+    cudaSetDevice(ctx->device);
+    memset(out, 0, sizeof(*out));
+    const float* c0 = cfg->corners;
+    double d01 = sqrt((double)(c0[0] - c0[3]) * (c0[0] - c0[3]) + (double)(c0[1] - c0[4]) * (c0[1] - c0[4]) + (double)(c0[2] - c0[5]) * (c0[2] - c0[5]));
+    float ssize = -1.f;
+    if (cfg->info_type == 0 && marker_size > 0) ssize = marker_size;
+    else if (cfg->info_type == 1) ssize = (float)d01;
+    // markers that belong to the configuration, in detection order (:104-111) -- pure data selection
+    std::vector<float> obj, img;
+    int nb = 0;
+    double mpp = cfg->info_type == 0 ? (double)marker_size / d01 : 1.0;  // marker_meter_per_pix (:132-136)
+    for (int i = 0; i < n; i++) {
+        int k = -1;
+        for (int j = 0; j < cfg->n_markers; j++)
+            if (cfg->ids[j] == markers[i].id) {
+                k = j;
+                break;
+            }
+        if (k < 0) continue;
+        if (board_markers) {
+            board_markers[nb] = markers[i];
+            board_markers[nb].ssize = ssize;
+        }
+        nb++;
+        for (int p = 0; p < 4; p++) {
+            img.push_back(markers[i].corners[2 * p]);
+            img.push_back(markers[i].corners[2 * p + 1]);
+            for (int c = 0; c < 3; c++) obj.push_back((float)((double)cfg->corners[(size_t)k * 12 + 3 * p + c] * mpp));  // Point3f * double
+        }
+    }
+    out->n_markers = nb;
+    out->ssize = ssize;
+    out->prob = (float)nb / (float)cfg->n_markers;
+    bool enough = (marker_size > 0 && cfg->info_type == 0) || cfg->info_type == 1;
+    if (nb == 0 || !K) {
+        out->prob = 0.f;  // "return 0" (:117-118)
+        return AB_OK;
+    }
+    if (!enough) {
+        out->prob = 0.f;
+        return AB_OK;
+    }
+    int N = 4 * nb;
+    float *d_obj = nullptr, *d_img = nullptr, *d_obj2 = nullptr, *d_img2 = nullptr;
+    double* d_out = nullptr;
+    CK(cudaMalloc(&d_obj, sizeof(float) * 3 * N));
+    CK(cudaMalloc(&d_img, sizeof(float) * 2 * N));
+    CK(cudaMalloc(&d_obj2, sizeof(float) * 3 * N));
+    CK(cudaMalloc(&d_img2, sizeof(float) * 2 * N));
+    CK(cudaMalloc(&d_out, sizeof(double) * 8));
+    CK(cudaMemcpy(d_obj, obj.data(), sizeof(float) * 3 * N, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_img, img.data(), sizeof(float) * 2 * N, cudaMemcpyHostToDevice));
+    float zeros[5] = {0, 0, 0, 0, 0};
+    k_board_pose<<<1, 32, 0, ctx->stream>>>(d_obj, d_img, N, make_camera(K, D ? D : zeros), repj_err_thres, set_y_perp, d_obj2, d_img2, d_out);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    double res[8];
+    CK(cudaMemcpy(res, d_out, sizeof(res), cudaMemcpyDeviceToHost));
+    cudaFree(d_obj);
+    cudaFree(d_img);
+    cudaFree(d_obj2);
+    cudaFree(d_img2);
+    cudaFree(d_out);
+    out->has_pose = res[6] != 0.;
+    for (int i = 0; i < 3; i++) {
+        out->rvec[i] = res[i];
+        out->tvec[i] = res[3 + i];
+    }
+    return AB_OK;
+}
+
 int ab_host_alloc(void** ptr, size_t bytes) {
     if (!ptr) return AB_E_INVALID;
     return cudaMallocHost(ptr, bytes) == cudaSuccess ? AB_OK : AB_E_CUDA;

@@ -146,6 +146,29 @@ AB_API int ab_warp(ab_context* ctx, const uint8_t* grey, int width, int height, 
 AB_API int ab_calculate_extrinsics(ab_context* ctx, ab_marker* markers, int n, const float* K, const float* D,
                                    float marker_size, int set_y_perpendicular);
 
+/* ---- next row: BoardDetector::detect (src/boarddetector.cpp:90-204) ------------------------------------ */
+/* BoardConfiguration (src/board.h:56-97): ids + 4 object corners per marker, in pixels (info_type 0) or meters (1) */
+typedef struct ab_board_config {
+    int32_t n_markers;
+    int32_t info_type;      /* BoardConfiguration::PIX = 0, METERS = 1 */
+    const int32_t* ids;     /* n_markers */
+    const float* corners;   /* n_markers * 4 * 3 */
+} ab_board_config;
+/* Board (src/board.h:103-140): the matched markers are returned separately; pose as in ab_marker */
+typedef struct ab_board {
+    int32_t n_markers;      /* detected markers that belong to the configuration */
+    int32_t has_pose;
+    float prob;             /* return value of BoardDetector::detect: n_markers / config size */
+    float ssize;
+    double rvec[3];
+    double tvec[3];
+} ab_board;
+/* id filter, stacked 4*M-point solvePnP, optional reprojection-outlier re-solve (repj_err_thres > 0, cpp:172-194),
+ * optional rotateXAxis.  board_markers (cap n) receives the matched markers in input order.                 */
+AB_API int ab_detect_board(ab_context* ctx, const ab_marker* markers, int n, const ab_board_config* cfg, const float* K,
+                           const float* D, float marker_size, float repj_err_thres, int set_y_perpendicular,
+                           ab_marker* board_markers, ab_board* out);
+
 /* pinned host memory for frame staging */
 AB_API int ab_host_alloc(void** ptr, size_t bytes);
 AB_API int ab_host_free(void* ptr);

@@ -565,3 +565,40 @@ def detect(image: np.ndarray, P: Params = None, K=None, D=None, marker_size: flo
             m["rvec"], m["tvec"], m["ssize"] = rvec, tvec.reshape(3).astype(np.float64), float(marker_size)
     res["markers"] = markers
     return res
+
+
+def board_detect(markers, board_cfg: dict, K=None, D=None, marker_size: float = -1.0, repj_err_thres: float = -1.0,
+                 set_y_perpendicular: bool = False):
+    """BoardDetector::detect (src/boarddetector.cpp:90-204) on real OpenCV.  markers: list of {'id','corners'};
+    board_cfg: {'mInfoType', 'markers': [{'id','corners' 4x3}]}.  Returns dict(prob, markers, rvec, tvec)."""
+    ids = [m["id"] for m in board_cfg["markers"]]
+    pts = {m["id"]: np.array(m["corners"], np.float32) for m in board_cfg["markers"]}
+    first = np.array(board_cfg["markers"][0]["corners"], np.float32)
+    d01 = float(np.sqrt(((first[0].astype(np.float64) - first[1].astype(np.float64)) ** 2).sum()))
+    pix = board_cfg["mInfoType"] == 0
+    sel = [m for m in markers if m["id"] in pts]
+    out = {"prob": 0.0, "markers": sel, "rvec": None, "tvec": None}
+    if not sel or K is None:
+        return out
+    if not ((marker_size > 0 and pix) or not pix):
+        return out
+    mpp = float(marker_size) / d01 if pix else 1.0
+    obj, img = [], []
+    for m in sel:
+        for p in range(4):
+            img.append(np.asarray(m["corners"], np.float32)[p])
+            obj.append((pts[m["id"]][p].astype(np.float64) * mpp).astype(np.float32))
+    obj, img = np.array(obj, np.float32), np.array(img, np.float32)
+    K = np.asarray(K, np.float32).reshape(3, 3)
+    Dm = np.zeros((1, 4), np.float32) if D is None else np.asarray(D, np.float32).reshape(1, -1)
+    _, rvec, tvec = cv2.solvePnP(obj, img.reshape(-1, 1, 2), K, Dm)
+    if repj_err_thres > 0:
+        rep = cv2.projectPoints(obj, rvec, tvec, K, Dm)[0].reshape(-1, 2).astype(np.float32)
+        err = np.sqrt(((rep - img).astype(np.float64) ** 2).sum(axis=1)).astype(np.float32)
+        keep = err < np.float32(repj_err_thres)
+        _, rvec, tvec = cv2.solvePnP(obj[keep], img[keep].reshape(-1, 1, 2), K, Dm)
+    rvec = rvec.reshape(3).astype(np.float64)
+    if set_y_perpendicular:
+        rvec = rotate_x_axis(rvec)
+    out.update(prob=len(sel) / len(ids), rvec=rvec, tvec=tvec.reshape(3).astype(np.float64))
+    return out

@@ -240,3 +240,8 @@ void hc_walk_cost(const uint8_t* img, int W, int H, int max_len, long long* fwd_
     *fwd_steps = fs; *bidir_steps = bs; *kept_points = kp;
 }
 }
+
+extern "C" int hc_solve_pnp_planar(const float* K, const float* D, const float* obj, const float* img, int N, double* rvec, double* tvec) {
+    ab::Camera c = make_cam(K, D);
+    return ab::solve_pnp_planar(c, obj, img, N, rvec, tvec) ? 1 : 0;
+}

@@ -112,3 +112,41 @@ def test_cpp_facade_aruco_simple(built, frames, expected, tmp_path):
         assert np.abs(c - np.array(g["corners"])).max() < 0.01 and int(r[9]) == 1
         assert np.abs(np.array([float(v) for v in r[10:13]]) - np.array(g["rvec"])).max() < 1e-4
         assert np.abs(np.array([float(v) for v in r[13:16]]) - np.array(g["tvec"])).max() < 1e-4
+
+
+@pytest.mark.parametrize("name,cfgname", [("board", "board_pix"), ("chessboard", "chessboard_pix")])
+def test_board_detector_goldens(built, frames, expected, name, cfgname):
+    """Aruco.Board / Aruco.Multi (test/core_tests.cpp:164-228) through the device: detect without camera, then
+    BoardDetector::detect -> the golden board pose; also vs cv2 when importable, incl. the outlier re-solve."""
+    from aruco_b200 import BoardConfiguration, BoardDetector
+    bd = BoardDetector()
+    cfg = BoardConfiguration.from_dict(expected["boards"][cfgname])
+    K, D = intrinsics(expected, name)
+    markers = bd.getMarkerDetector().detect(frames[name])
+    prob, board = bd.detect(markers, cfg, K, D, 1.0)
+    g = expected["goldens"][name]
+    assert len(board) == len(g["markers"]) and abs(prob - len(board) / cfg.size()) < 1e-6
+    assert [m.id for m in board] == [m["id"] for m in g["markers"]] and all(m.ssize == 1.0 for m in board)
+    assert np.abs(board.Rvec - np.array(g["rvec"])).max() < 1e-4 and np.abs(board.Tvec - np.array(g["tvec"])).max() < 1e-4
+    try:
+        from oracle import cv2_oracle as o
+        assert o.cv2 is not None
+    except Exception:
+        return
+    ms = [{"id": m.id, "corners": m.corners} for m in markers]
+    for thr, yperp in ((-1.0, False), (1.5, False), (0.8, True)):
+        bd.set_repj_err_thres(thr)
+        bd.setYPerpendicular(yperp)
+        prob, board = bd.detect(markers, cfg, K, D, 1.0)
+        ref = o.board_detect(ms, expected["boards"][cfgname], K, D, 1.0, thr, yperp)
+        assert rel_err(board.Rvec, ref["rvec"]) < 1e-4 and rel_err(board.Tvec, ref["tvec"]) < 1e-4
+    # no camera -> no pose, probability 0 (boarddetector.cpp:117-118)
+    prob, board = bd.detect(markers, cfg)
+    assert prob == 0.0 and board.Rvec is None and len(board) == len(g["markers"])
+    # meters configuration needs no marker size
+    cfgm = BoardConfiguration.from_dict(expected["boards"][cfgname.replace("_pix", "_meters")])
+    bd.set_repj_err_thres(-1.0)
+    bd.setYPerpendicular(False)
+    prob, board = bd.detect(markers, cfgm, K, D)
+    refm = o.board_detect(ms, expected["boards"][cfgname.replace("_pix", "_meters")], K, D)
+    assert rel_err(board.Rvec, refm["rvec"]) < 1e-4 and rel_err(board.Tvec, refm["tvec"]) < 1e-4

@@ -184,3 +184,27 @@ def test_rotate_x_axis(hc):
         mine = r.copy()
         hc.hc_rotate_x_axis(P(mine))
         assert np.abs(mine - ref).max() < 1e-5  # f32 rotation matrices in the reference (utils.cpp:17)
+
+
+def test_board_pose_equals_cv2(hc, expected):
+    """N-point planar pose (solve_pnp_planar) vs cv2.solvePnP on the golden board corners, pixel and meter configs."""
+    import cv2
+    hc.hc_solve_pnp_planar.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p]
+    for name, cfgname, size in (("board", "board_pix", 1.0), ("chessboard", "chessboard_pix", 1.0), ("board", "board_meters", -1.0)):
+        g, cfg = expected["goldens"][name], expected["boards"][cfgname]
+        K, D = intrinsics(expected, name)
+        pts = {m["id"]: np.array(m["corners"], np.float32) for m in cfg["markers"]}
+        first = np.array(cfg["markers"][0]["corners"], np.float64)
+        mpp = size / np.linalg.norm(first[0] - first[1]) if cfg["mInfoType"] == 0 else 1.0
+        obj, img = [], []
+        for m in g["markers"]:
+            for p in range(4):
+                img.append(m["corners"][p])
+                obj.append((pts[m["id"]][p].astype(np.float64) * mpp).astype(np.float32))
+        obj, img = np.ascontiguousarray(np.array(obj, np.float32)), np.ascontiguousarray(np.array(img, np.float32))
+        r, t = np.zeros(3), np.zeros(3)
+        assert hc.hc_solve_pnp_planar(P(np.ascontiguousarray(K.ravel())), P(D), P(obj), P(img), len(obj), P(r), P(t)) == 1
+        _, rv, tv = cv2.solvePnP(obj, img.reshape(-1, 1, 2), K, D.reshape(1, 5))
+        assert np.abs(r - rv.ravel()).max() / np.abs(rv).max() < 1e-6 and np.abs(t - tv.ravel()).max() / np.abs(tv).max() < 1e-6
+        if cfg["mInfoType"] == 0:
+            assert np.abs(r - np.array(g["rvec"])).max() < 1e-4 and np.abs(t - np.array(g["tvec"])).max() < 1e-4

@@ -57,3 +57,16 @@ def test_bgr_golden_single(frames, expected):
     K, D = intrinsics(expected, "single")
     r = o.detect(frames["single_bgr"], Params(), K, D, 1.0)
     _check(r["markers"], expected["goldens"]["single"]["markers"], True)
+
+
+@needs_cv2
+@pytest.mark.parametrize("name,cfgname", [("board", "board_pix"), ("chessboard", "chessboard_pix")])
+def test_board_pose_golden_cv2_oracle(frames, expected, name, cfgname):
+    """Aruco.Board / Aruco.Multi (test/core_tests.cpp:164-228): markers without camera, then the board pose."""
+    from oracle import cv2_oracle as o
+    K, D = intrinsics(expected, name)
+    r = o.detect(frames[name], Params())
+    b = o.board_detect(r["markers"], expected["boards"][cfgname], K, D, 1.0)
+    g = expected["goldens"][name]
+    assert len(b["markers"]) == len(g["markers"])
+    assert np.abs(b["rvec"] - np.array(g["rvec"])).max() < GOLDEN_POSE_ATOL and np.abs(b["tvec"] - np.array(g["tvec"])).max() < GOLDEN_POSE_ATOL
