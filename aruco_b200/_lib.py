@@ -19,7 +19,8 @@ class ab_params(C.Structure):
     _fields_ = [("thres_method", C.c_int32), ("thres_param1", C.c_double), ("thres_param2", C.c_double),
                 ("corner_method", C.c_int32), ("min_size", C.c_float), ("max_size", C.c_float),
                 ("warp_size", C.c_int32), ("border_dist", C.c_float), ("locked_corners", C.c_int32),
-                ("erosion", C.c_int32), ("decoder", C.c_int32), ("set_y_perpendicular", C.c_int32)]
+                ("erosion", C.c_int32), ("decoder", C.c_int32), ("set_y_perpendicular", C.c_int32),
+                ("thres_param1_range", C.c_int32)]
 
 
 class ab_board_config(C.Structure):

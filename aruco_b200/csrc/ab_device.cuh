@@ -74,6 +74,7 @@ struct HrmDict {
 
 struct Batch {
     int W, H, B, wpr;
+    int n_t;  // threshold images per frame (2*range+1, setThresholdParamRange); bits/thres hold B*n_t virtual frames
     size_t bits_words;  // per frame
     const uint8_t* grey;
     size_t grey_row, grey_frame;

@@ -148,6 +148,7 @@ int ab_default_params(ab_params* p) {
     p->erosion = 0;
     p->decoder = AB_DECODER_FIDUCIDAL;
     p->set_y_perpendicular = 0;
+    p->thres_param1_range = 0;
     return AB_OK;
 }
 
@@ -216,6 +217,7 @@ int ab_set_params(ab_context* ctx, const ab_params* p) {
     if (p->thres_method < 0 || p->thres_method > 2) return set_err(ctx, AB_E_INVALID, "bad threshold method");
     if (p->corner_method < 0 || p->corner_method > 3) return set_err(ctx, AB_E_INVALID, "bad corner refinement method");
     if (p->decoder < 0 || p->decoder > 2) return set_err(ctx, AB_E_INVALID, "bad decoder kind");
+    if (p->thres_param1_range < 0 || p->thres_param1_range > 7) return set_err(ctx, AB_E_INVALID, "threshold param range outside 0..7");
     ctx->params = *p;
     return AB_OK;
 }
@@ -411,7 +413,7 @@ static Camera make_camera(const float* K, const float* D) {
     return c;
 }
 
-static int launch_threshold(ab_context* ctx, const Batch& b, int method, double p1, double p2) {
+static int launch_threshold(ab_context* ctx, const Batch& b, int method, double p1, double p2, int out_mul = 1, int out_off = 0) {
     cudaStream_t st = ctx->stream;
     if (method == AB_THRES_ADAPTIVE) {
         // thresHold: ensure an odd block size >= 3 (src/markerdetector.cpp:657-660)
@@ -438,6 +440,8 @@ static int launch_threshold(ab_context* ctx, const Batch& b, int method, double 
         int r = k / 2;
         a.R4 = (r + 3) & ~3;
         a.aligned4 = ((((uintptr_t)b.grey) | b.grey_row | b.grey_frame) & 3) == 0;
+        a.out_mul = out_mul;
+        a.out_off = out_off;
         int nth = (a.TWo + 2 * a.R4) / 4;
         nth = (nth + 31) & ~31;
         size_t SPAN = 4 * (size_t)nth;
@@ -447,7 +451,7 @@ static int launch_threshold(ab_context* ctx, const Batch& b, int method, double 
     } else if (method == AB_THRES_FIXED) {
         int thr = (int)floor(p1);
         k_threshold_fixed<<<ctx->sm_count * 8, 256, 0, st>>>(b.grey, b.grey_row, b.grey_frame, b.thres, b.bits, b.bits_words,
-                                                              b.W, b.H, b.wpr, thr, 0, b.B);
+                                                              b.W, b.H, b.wpr, thr, 0, b.B, out_mul, out_off);
     } else {
         return set_err(ctx, AB_E_INVALID, "ThresholdMethods::CANNY is not implemented on the device path");
     }
@@ -482,6 +486,7 @@ static int fill_batch(ab_context* ctx, Batch& b, const uint8_t* dgrey, size_t ro
     b.W = ctx->W;
     b.H = ctx->H;
     b.B = n;
+    b.n_t = 1;
     b.wpr = bit_words_per_row(ctx->W);
     b.bits_words = bit_image_words(ctx->W, ctx->H);
     b.grey = dgrey;
@@ -546,28 +551,44 @@ static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t f
         return set_err(ctx, AB_E_INVALID, "SUBPIX window %d outside 1..24", (int)P.thres_param1);
     if (P.locked_corners && ((int)P.thres_param1 < 1 || (int)P.thres_param1 > 24))
         return set_err(ctx, AB_E_INVALID, "locked-corner window %d outside 1..24", (int)P.thres_param1);
+    // setThresholdParamRange (markerdetector.h:152, cpp:322-334): 2*range+1 threshold images per frame, param1 =
+    // p1 - range + range*i (sic); they live as n_t consecutive "virtual frames" per frame for the
+    // threshold / contour / polygon stages and are merged per frame by k_polygon's quad keys.
+    const int n_t = 2 * P.thres_param1_range + 1;
+    if (n * n_t > ctx->maxB) return set_err(ctx, AB_E_STATE, "internal: %d virtual frames > reserved %d", n * n_t, ctx->maxB);
     Batch b;
     fill_batch(ctx, b, dgrey, row, frame, n, K, D, marker_size);
+    b.n_t = n_t;
+    b.cap_starts *= n_t;
+    b.cap_contours *= (unsigned)n_t;
+    b.cap_pool *= n_t;
+    b.cap_long *= (unsigned)n_t;
     cudaStream_t st = ctx->stream;
     const int sms = ctx->sm_count;
     if (ctx->timing) cudaEventRecord(ctx->ev[0], st);
     CK(cudaMemsetAsync(ctx->d_counters, 0, ctx->counters_bytes, st));
     if (ctx->timing) cudaEventRecord(ctx->kev[0], st);
-    int rc = launch_threshold(ctx, b, P.thres_method, P.thres_param1, P.thres_param2);
-    if (rc) return rc;
+    for (int ti = 0; ti < n_t; ti++) {
+        double p1 = n_t == 1 ? P.thres_param1 : P.thres_param1 - P.thres_param1_range + (double)P.thres_param1_range * ti;
+        int rc = launch_threshold(ctx, b, P.thres_method, p1, P.thres_param2, n_t, ti);
+        if (rc) return rc;
+    }
     if (ctx->timing) cudaEventRecord(ctx->kev[1], st);
+    Batch bv = b;  // the same buffers seen as n * n_t virtual frames
+    bv.B = n * n_t;
     if (P.erosion) {
-        k_erode<<<sms * 8, 256, 0, st>>>(b.bits, b.bits2, b.thres, b.bits_words, b.W, b.H, b.wpr, b.B);
+        k_erode<<<sms * 8, 256, 0, st>>>(bv.bits, bv.bits2, bv.thres, bv.bits_words, bv.W, bv.H, bv.wpr, bv.B);
+        std::swap(bv.bits, bv.bits2);
         std::swap(b.bits, b.bits2);
     }
     if (ctx->timing) cudaEventRecord(ctx->ev[1], st);
-    k_scan_starts<<<sms * 8, 256, 0, st>>>(b);
+    k_scan_starts<<<sms * 8, 256, 0, st>>>(bv);
     if (ctx->timing) cudaEventRecord(ctx->kev[2], st);
-    k_trace<false><<<sms * 8, 128, 0, st>>>(b);
-    k_trace<true><<<sms * 4, 128, 0, st>>>(b);
-    k_emit<<<sms * 8, 128, 0, st>>>(b);
+    k_trace<false><<<sms * 8, 128, 0, st>>>(bv);
+    k_trace<true><<<sms * 4, 128, 0, st>>>(bv);
+    k_emit<<<sms * 8, 128, 0, st>>>(bv);
     if (ctx->timing) cudaEventRecord(ctx->kev[3], st);
-    k_polygon<<<sms * 4, 128, 0, st>>>(b);
+    k_polygon<<<sms * 4, 128, 0, st>>>(bv);
     if (ctx->timing) cudaEventRecord(ctx->kev[4], st);
     k_frame_filter<<<n, 256, 0, st>>>(b);
     CK(cudaGetLastError());
@@ -654,7 +675,7 @@ int ab_enqueue_batch_device(ab_context* ctx, const uint8_t* dev_frames, int widt
                             size_t frame_stride, int n_frames, const float* K, const float* D, float marker_size) {
     if (!ctx || !dev_frames || n_frames < 1 || row_stride < (size_t)width) return set_err(ctx, AB_E_INVALID, "bad arguments");
     cudaSetDevice(ctx->device);
-    int rc = ensure_reserved(ctx, width, height, n_frames);
+    int rc = ensure_reserved(ctx, width, height, n_frames * (2 * ctx->params.thres_param1_range + 1));
     if (rc) return rc;
     return run_batch(ctx, dev_frames, row_stride, frame_stride, n_frames, K, D, marker_size);
 }
@@ -714,10 +735,11 @@ static int detect_host(ab_context* ctx, const uint8_t* frames, int width, int he
         return set_err(ctx, AB_E_INVALID, "bad arguments");
     cudaSetDevice(ctx->device);
     // chunk size: what was reserved for this geometry, else up to 32 frames
-    int chunk = (ctx->W == width && ctx->H == height && ctx->maxB > 0) ? std::min(ctx->maxB, n_frames) : std::min(n_frames, 32);
-    int rc = ensure_reserved(ctx, width, height, chunk);
+    const int n_t = 2 * ctx->params.thres_param1_range + 1;
+    int chunk = (ctx->W == width && ctx->H == height && ctx->maxB >= n_t) ? std::min(ctx->maxB / n_t, n_frames) : std::min(n_frames, 32);
+    int rc = ensure_reserved(ctx, width, height, chunk * n_t);
     if (rc) return rc;
-    chunk = std::min(ctx->maxB, n_frames);
+    chunk = std::min(ctx->maxB / n_t, n_frames);
     size_t fpx = (size_t)width * height;
     rc = ensure_grey(ctx, fpx * chunk);
     if (rc) return rc;
@@ -796,7 +818,8 @@ int ab_get_thresholded(ab_context* ctx, int frame, uint8_t* dst, size_t dst_stri
     cudaSetDevice(ctx->device);
     const Batch& b = ctx->last;
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy2D(dst, dst_stride, b.thres + (size_t)frame * b.W * b.H, b.W, b.W, b.H, cudaMemcpyDeviceToHost));
+    // `thres` = the middle threshold image (thres_images[n_param1 / 2], markerdetector.cpp:334)
+    CK(cudaMemcpy2D(dst, dst_stride, b.thres + ((size_t)frame * b.n_t + b.n_t / 2) * b.W * b.H, b.W, b.W, b.H, cudaMemcpyDeviceToHost));
     return AB_OK;
 }
 
@@ -926,7 +949,7 @@ int ab_detect_rectangles(ab_context* ctx, const uint8_t* thres, int width, int h
     fill_batch(ctx, b, ctx->d_grey[0], width, (size_t)width * height, 1, nullptr, nullptr, -1.f);
     CK(cudaMemsetAsync(ctx->d_counters, 0, ctx->counters_bytes, st));
     k_threshold_fixed<<<ctx->sm_count * 8, 256, 0, st>>>(b.grey, b.grey_row, b.grey_frame, b.thres, b.bits, b.bits_words, b.W, b.H,
-                                                          b.wpr, 0, 1, 1);
+                                                          b.wpr, 0, 1, 1, 1, 0);
     k_scan_starts<<<ctx->sm_count * 8, 256, 0, st>>>(b);
     k_trace<false><<<ctx->sm_count * 8, 128, 0, st>>>(b);
     k_trace<true><<<ctx->sm_count * 4, 128, 0, st>>>(b);

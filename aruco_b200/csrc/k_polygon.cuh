@@ -150,7 +150,10 @@ __global__ void __launch_bounds__(128) k_polygon(Batch b) {
             int cnt = dp_cleanup(ox, oy, nout, E);
             if (cnt == 4 && is_convex4(ox, oy)) {
                 // the reference's min-side>10 test (:542-552) indexes out of bounds and never rejects
-                unsigned int q = atomicAdd(&b.n_quads[rec.frame], 1u);
+                // reference order of the joined candidate list (:561-563): threshold image t ascending, then
+                // reverse discovery order inside an image
+                const unsigned rf = rec.frame / (unsigned)b.n_t, tt = rec.frame % (unsigned)b.n_t;
+                unsigned int q = atomicAdd(&b.n_quads[rf], 1u);
                 if (q >= (unsigned)b.cap_q) {
                     atomicOr(&b.cnt->err, ERR_QUADS_OVERFLOW);
                 } else {
@@ -159,9 +162,9 @@ __global__ void __launch_bounds__(128) k_polygon(Batch b) {
                         qr.x[i] = (short)ox[i];
                         qr.y[i] = (short)oy[i];
                     }
-                    qr.key = rec.key;
+                    qr.key = ((uint32_t)(b.n_t - 1 - (int)tt) << 28) | rec.key;
                     qr.contour = ci;
-                    b.quads[(size_t)rec.frame * b.cap_q + q] = qr;
+                    b.quads[(size_t)rf * b.cap_q + q] = qr;
                 }
             }
         }

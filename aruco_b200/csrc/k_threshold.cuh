@@ -25,6 +25,7 @@ struct ThrArgs {
     int k, idelta;
     int TWo, RH, R4;
     int aligned4;  // source rows allow 32-bit loads
+    int out_mul, out_off;  // output (virtual) frame = f * out_mul + out_off  (setThresholdParamRange: several images per frame)
 };
 
 __global__ void k_threshold_adaptive(ThrArgs a) {
@@ -37,8 +38,9 @@ __global__ void k_threshold_adaptive(ThrArgs a) {
     const int X0 = blockIdx.x * a.TWo, y0 = blockIdx.y * a.RH, f = blockIdx.z;
     const int c0 = X0 - a.R4 + 4 * t;
     const uint8_t* src = a.grey + (size_t)f * a.grey_frame;
-    uint8_t* dst = a.thres + (size_t)f * a.W * a.H;
-    uint32_t* bits = a.bits + (size_t)f * a.bits_words;
+    const size_t fo = (size_t)f * a.out_mul + a.out_off;
+    uint8_t* dst = a.thres + fo * a.W * a.H;
+    uint32_t* bits = a.bits + fo * a.bits_words;
     const bool fast = a.aligned4 && c0 >= 0 && c0 + 3 < a.W;
     int xc[4];
 #pragma unroll
@@ -112,7 +114,8 @@ __global__ void k_threshold_adaptive(ThrArgs a) {
 // FIXED_THRES and bit packing of an existing binary image: one thread per 32-pixel word.
 // mode 0: dst = src > thr ? 0 : 255 (threshold BINARY_INV);  mode 1: dst = src (non-zero = fg), pack only
 __global__ void k_threshold_fixed(const uint8_t* grey, size_t grey_row, size_t grey_frame, uint8_t* thres,
-                                  uint32_t* bits, size_t bits_words, int W, int H, int wpr, int thr, int mode, int B) {
+                                  uint32_t* bits, size_t bits_words, int W, int H, int wpr, int thr, int mode, int B,
+                                  int out_mul, int out_off) {
     int ww = (W + 31) >> 5;
     size_t total = (size_t)ww * H * B;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -120,7 +123,8 @@ __global__ void k_threshold_fixed(const uint8_t* grey, size_t grey_row, size_t g
         int y = (int)((i / ww) % H);
         int f = (int)(i / ((size_t)ww * H));
         const uint8_t* rowp = grey + (size_t)f * grey_frame + (size_t)y * grey_row;
-        uint8_t* orow = thres + ((size_t)f * H + y) * W;
+        const size_t fo = (size_t)f * out_mul + out_off;
+        uint8_t* orow = thres + (fo * H + y) * W;
         uint32_t word = 0;
         for (int j = 0; j < 32; j++) {
             int x = 32 * w + j;
@@ -131,7 +135,7 @@ __global__ void k_threshold_fixed(const uint8_t* grey, size_t grey_row, size_t g
             if (mode == 0) orow[x] = on ? 255 : 0;
             else if (orow + x != rowp + x) orow[x] = v;
         }
-        bits[(size_t)f * bits_words + (size_t)(y + 1) * wpr + BIT_PAD + w] = word;
+        bits[fo * bits_words + (size_t)(y + 1) * wpr + BIT_PAD + w] = word;
     }
 }
 

@@ -60,8 +60,9 @@ __global__ void __launch_bounds__(160) k_threshold_fast(ThrArgs a) {
     const bool store_vec = (c0 + 3 < a.W) && ((a.W & 3) == 0);
     // validity of the 4 columns as a nibble
     const uint32_t vmask = c0 >= a.W ? 0u : (c0 + 3 < a.W ? 15u : ((1u << (a.W - c0)) - 1u));
-    uint8_t* orow = a.thres + (size_t)f * a.W * a.H + (size_t)y0 * a.W + c0;
-    uint32_t* brow = a.bits + (size_t)f * a.bits_words + (size_t)(y0 + 1) * a.wpr + BIT_PAD + (X0 >> 5) + (t >> 3);
+    const size_t fo = (size_t)f * a.out_mul + a.out_off;
+    uint8_t* orow = a.thres + fo * a.W * a.H + (size_t)y0 * a.W + c0;
+    uint32_t* brow = a.bits + fo * a.bits_words + (size_t)(y0 + 1) * a.wpr + BIT_PAD + (X0 >> 5) + (t >> 3);
     const int cst = K2 * a.idelta - (K2 - 1) / 2;  // S >= K2*src + cst  <=>  src - mean <= -idelta
     const uint32_t M = 0x00FF00FFu;
     uint32_t ring[K];

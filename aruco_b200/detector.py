@@ -141,9 +141,9 @@ class MarkerDetector:
     def getThresholdParams(self):
         return self._p.thres_param1, self._p.thres_param2
 
-    def setThresholdParamRange(self, r1=0, r2=0):
-        if r1 != 0:
-            raise ArucoError(_lib.AB_E_INVALID, "setThresholdParamRange != 0 is not implemented (SURVEY 8f-3)")
+    def setThresholdParamRange(self, r1=0, r2=0):  # markerdetector.h:152 (r2 is unused by the reference too)
+        self._p.thres_param1_range = int(r1)
+        self._push()
 
     def enableLockedCornersMethod(self, enable: bool):  # markerdetector.cpp:291-295
         self._p.locked_corners = int(bool(enable))

@@ -149,6 +149,7 @@ public:
     ThresholdMethods getThresholdMethod() const { return (ThresholdMethods)p_.thres_method; }
     void setThresholdParams(double param1, double param2) { p_.thres_param1 = param1; p_.thres_param2 = param2; push(); }
     void getThresholdParams(double& param1, double& param2) const { param1 = p_.thres_param1; param2 = p_.thres_param2; }
+    void setThresholdParamRange(size_t r1 = 0, size_t /*r2*/ = 0) { p_.thres_param1_range = (int)r1; push(); }  // h:152
     void enableLockedCornersMethod(bool enable) {  // markerdetector.cpp:291-295
         p_.locked_corners = enable;
         if (enable) p_.corner_method = SUBPIX;

@@ -58,6 +58,7 @@ typedef struct ab_params {
     int32_t erosion;             /* enableErosion (API-compat extension, default 0)          */
     int32_t decoder;             /* AB_DECODER_*      (setMakerDetectorFunction, h:243)      */
     int32_t set_y_perpendicular; /* detect(..., setYPerpendicular) h:102                     */
+    int32_t thres_param1_range;  /* _thresParam1_range (setThresholdParamRange, h:152): 2r+1 threshold images */
 } ab_params;
 
 /* aruco::Marker (marker.h:46-141): 4 corners, id, ssize, Rvec/Tvec (f64). has_pose=0 => Rvec/Tvec empty. */

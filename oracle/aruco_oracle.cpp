@@ -273,15 +273,17 @@ struct Candidate {
 };
 
 // detectRectangles (src/markerdetector.cpp:496-635)
-void detect_rectangles(const uint8_t* thres, int W, int H, float min_size, float max_size, std::vector<Candidate>& out,
-                       int* n_contours) {
+void detect_rectangles(const std::vector<const uint8_t*>& thres_images, int W, int H, float min_size, float max_size,
+                       std::vector<Candidate>& out, int* n_contours) {
     int minSize = min_size * std::max(W, H) * 4;
     int maxSize = max_size * std::max(W, H) * 4;
-    std::vector<std::vector<Pt>> contours;
-    find_contours(thres, W, H, contours);
-    if (n_contours) *n_contours = (int)contours.size();
     std::vector<Candidate> cands;
     std::vector<Pt> approx;
+    if (n_contours) *n_contours = 0;
+    for (size_t ti = 0; ti < thres_images.size(); ti++) {  // one pass per threshold image (:506-560), joined in order
+    std::vector<std::vector<Pt>> contours;
+    find_contours(thres_images[ti], W, H, contours);
+    if (n_contours) *n_contours += (int)contours.size();
     for (size_t i = 0; i < contours.size(); i++) {
         if ((int)contours[i].size() <= minSize || (int)contours[i].size() >= maxSize) continue;
         approx_poly_dp(contours[i], double(contours[i].size()) * 0.05, approx);
@@ -295,6 +297,7 @@ void detect_rectangles(const uint8_t* thres, int W, int H, float min_size, float
         cd.id = -1;
         cd.nrot = 0;
         cands.push_back(std::move(cd));
+    }
     }
     std::vector<char> swapped(cands.size(), 0);
     for (size_t i = 0; i < cands.size(); i++) {
@@ -1114,6 +1117,7 @@ struct orc_params {
     int32_t warp_size;
     float border_dist;
     int32_t locked_corners, erosion, decoder, set_y_perpendicular;
+    int32_t p1_range;  // setThresholdParamRange
 };
 
 struct orc_marker {
@@ -1198,17 +1202,23 @@ int orc_solve_pnp(const float* K, const float* D, const float* corners, float si
 int orc_detect(const uint8_t* grey, int W, int H, const orc_params* P, const float* K, const float* D, float marker_size,
                const orc_dict* dict, orc_marker* out, int cap, orc_debug* dbg) {
     if (P->thres_method == 2) return -2;
-    std::vector<uint8_t> thres((size_t)W * H);
-    orc_threshold(grey, W, H, P->thres_method, P->p1, P->p2, thres.data());
-    if (P->erosion) {
-        std::vector<uint8_t> t2((size_t)W * H);
-        erode3x3(thres.data(), W, H, t2.data());
-        thres.swap(t2);
+    const int n_t = 2 * P->p1_range + 1;  // src/markerdetector.cpp:322-334
+    std::vector<std::vector<uint8_t>> thr(n_t, std::vector<uint8_t>((size_t)W * H));
+    std::vector<const uint8_t*> thr_ptr;
+    for (int i = 0; i < n_t; i++) {
+        double t1 = n_t == 1 ? P->p1 : P->p1 - P->p1_range + (double)P->p1_range * i;
+        orc_threshold(grey, W, H, P->thres_method, t1, P->p2, thr[i].data());
+        if (P->erosion) {
+            std::vector<uint8_t> t2((size_t)W * H);
+            erode3x3(thr[i].data(), W, H, t2.data());
+            thr[i].swap(t2);
+        }
+        thr_ptr.push_back(thr[i].data());
     }
-    if (dbg && dbg->thres) memcpy(dbg->thres, thres.data(), thres.size());
+    if (dbg && dbg->thres) memcpy(dbg->thres, thr[n_t / 2].data(), thr[n_t / 2].size());
     std::vector<Candidate> cands;
     int ncont = 0;
-    detect_rectangles(thres.data(), W, H, P->min_size, P->max_size, cands, &ncont);
+    detect_rectangles(thr_ptr, W, H, P->min_size, P->max_size, cands, &ncont);
     Cam cam;
     if (K) {
         cam.hasK = true;

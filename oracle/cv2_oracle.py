@@ -49,6 +49,7 @@ class Params:
     erosion: bool = False          # API-compat extension: cv2.erode(thres, None)
     decoder: int = DEC_FID
     set_y_perpendicular: bool = False
+    p1_range: int = 0              # _thresParam1_range (setThresholdParamRange, markerdetector.h:152)
 
 
 class HrmDictionary:
@@ -178,24 +179,30 @@ def size_limits(w: int, h: int, min_size: float, max_size: float):
     return mn, mx
 
 
-def detect_rectangles(thres: np.ndarray, min_size: float, max_size: float):
-    """MarkerDetector::detectRectangles, src/markerdetector.cpp:496-635.
+def detect_rectangles(thres, min_size: float, max_size: float):
+    """MarkerDetector::detectRectangles, src/markerdetector.cpp:496-635.  `thres`: one binary image or the list
+    of threshold images of setThresholdParamRange (candidates are joined in image order, :561-563).
     Returns list of dicts {corners (4,2) f32, contour (n,2) i32 (already reversed if swapped), idx}."""
-    h, w = thres.shape
+    images = thres if isinstance(thres, (list, tuple)) else [thres]
+    h, w = images[0].shape
     mn, mx = size_limits(w, h, min_size, max_size)
-    contours, _ = cv2.findContours(thres.copy(), cv2.RETR_LIST, cv2.CHAIN_APPROX_NONE)
     cands = []
-    for i, c in enumerate(contours):
-        n = c.shape[0]
-        if n <= mn or n >= mx:
-            continue
-        approx = cv2.approxPolyDP(c, float(n) * 0.05, True)
-        if approx.shape[0] != 4:
-            continue
-        if not cv2.isContourConvex(approx):
-            continue
-        # :542-552 min-side filter is an out-of-bounds no-op (Appendix B.2): always pass
-        cands.append({"corners": approx.reshape(4, 2).astype(np.float32), "contour": c.reshape(-1, 2), "idx": i})
+    n_contours_total = 0
+    for img in images:
+        contours, _ = cv2.findContours(img.copy(), cv2.RETR_LIST, cv2.CHAIN_APPROX_NONE)
+        n_contours_total += len(contours)
+        for i, c in enumerate(contours):
+            n = c.shape[0]
+            if n <= mn or n >= mx:
+                continue
+            approx = cv2.approxPolyDP(c, float(n) * 0.05, True)
+            if approx.shape[0] != 4:
+                continue
+            if not cv2.isContourConvex(approx):
+                continue
+            # :542-552 min-side filter is an out-of-bounds no-op (Appendix B.2): always pass
+            cands.append({"corners": approx.reshape(4, 2).astype(np.float32), "contour": c.reshape(-1, 2), "idx": i})
+    contours = [None] * n_contours_total
     swapped = []
     for cd in cands:
         c = cd["corners"]
@@ -500,10 +507,15 @@ def detect(image: np.ndarray, P: Params = None, K=None, D=None, marker_size: flo
         K = np.asarray(K, np.float32).reshape(3, 3)       # CameraParameters holds f32 (cameraparameters.cpp:204)
     if D is not None:
         D = np.asarray(D, np.float32).reshape(1, -1)
-    thres = threshold(grey, P.thres_method, P.p1, P.p2)
+    n_t = 2 * P.p1_range + 1
+    if n_t == 1:
+        images = [threshold(grey, P.thres_method, P.p1, P.p2)]
+    else:  # :328-332, param1 = p1 - range + range*i
+        images = [threshold(grey, P.thres_method, P.p1 - P.p1_range + P.p1_range * i, P.p2) for i in range(n_t)]
     if P.erosion:
-        thres = cv2.erode(thres, None)
-    cands, n_contours = detect_rectangles(thres, P.min_size, P.max_size)
+        images = [cv2.erode(t, None) for t in images]
+    thres = images[n_t // 2]
+    cands, n_contours = detect_rectangles(images, P.min_size, P.max_size)
     S = P.warp_size
     res = {"grey": grey, "thres": thres, "n_contours": n_contours, "candidates": [], "markers": []}
     decoded = []

@@ -18,7 +18,7 @@ class orc_params(C.Structure):
     _fields_ = [("thres_method", C.c_int32), ("p1", C.c_double), ("p2", C.c_double), ("corner_method", C.c_int32),
                 ("min_size", C.c_float), ("max_size", C.c_float), ("warp_size", C.c_int32), ("border_dist", C.c_float),
                 ("locked_corners", C.c_int32), ("erosion", C.c_int32), ("decoder", C.c_int32),
-                ("set_y_perpendicular", C.c_int32)]
+                ("set_y_perpendicular", C.c_int32), ("p1_range", C.c_int32)]
 
 
 class orc_marker(C.Structure):
@@ -69,7 +69,8 @@ def _p(a):
 def make_params(P) -> orc_params:
     """P: oracle.cv2_oracle.Params-like object (same field names)."""
     return orc_params(P.thres_method, float(P.p1), float(P.p2), P.corner_method, P.min_size, P.max_size, P.warp_size,
-                      P.border_dist, int(P.locked_corners), int(P.erosion), P.decoder, int(P.set_y_perpendicular))
+                      P.border_dist, int(P.locked_corners), int(P.erosion), P.decoder, int(P.set_y_perpendicular),
+                      int(getattr(P, "p1_range", 0)))
 
 
 def make_dict(codes, n, tau0, rate=1.0):

@@ -26,6 +26,7 @@ def configure(det, P, expected=None):
     det.setWarpSize(P.warp_size)
     det.enableErosion(P.erosion)
     det.setYPerpendicular(P.set_y_perpendicular)
+    det.setThresholdParamRange(getattr(P, "p1_range", 0))
     det.setMakerDetectorFunction(HighlyReliableMarkers.detect if P.decoder == 1 else FiducidalMarkers.detect)
 
 
@@ -101,6 +102,9 @@ GOLDEN_CASES = [
     ("board", dict(p1=21, p2=5), True), ("board", dict(warp_size=28, corner_method=0), False),
     ("chessboard", dict(), False), ("chessboard", dict(erosion=True, corner_method=2), True),
     ("chessboard", dict(thres_method=0, p1=90), True), ("chessboard", dict(min_size=0.01, max_size=0.9), True),
+    # setThresholdParamRange: 3 / 5 threshold images per frame (utils/aruco_test.cpp:134 uses range 2)
+    ("single", dict(p1_range=1), True), ("board", dict(p1_range=2), True), ("chessboard", dict(p1_range=2, corner_method=2), True),
+    ("single", dict(p1_range=1, thres_method=0, p1=100), True), ("board", dict(p1_range=1, erosion=True), False),
 ]
 
 
@@ -334,3 +338,22 @@ def test_synthetic_1080p_locked_corners_and_harris(det):
         finally:
             det.enableLockedCornersMethod(False)
             det.setCornerRefinementMethod(3)
+
+
+def test_threshold_range_batch_4k(det):
+    """Multi-threshold search on a batch: every frame equals its single-frame result and the oracle's ids."""
+    from aruco_b200 import synth
+    from oracle import native
+    P = P_(p1_range=1)
+    configure(det, P)
+    K, D = synth.camera_for(1920, 1080)
+    frames = np.stack([synth.render_frame(1920, 1080, 50, 60 + i, 2.0)[0] for i in range(3)])
+    try:
+        batch = det.detect_batch(frames, K, D, 0.05)
+        for f in range(3):
+            ref = native.detect(frames[f], P, K, D, 0.05, debug=False)["markers"]
+            assert [m.id for m in batch[f]] == [m["id"] for m in ref]
+            assert all(np.abs(a.corners - b["corners"]).max() < CORNER_TOL for a, b in zip(batch[f], ref))
+            assert (det.getThresholdedImage(f) == native.detect(frames[f], P)["thres"]).all()
+    finally:
+        det.setThresholdParamRange(0)
