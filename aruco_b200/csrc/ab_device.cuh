@@ -57,6 +57,7 @@ struct Counters {
     unsigned int err;
     unsigned int emit_work;
     unsigned int n_long, long_work;
+    unsigned int canny_changed, pad2;
     unsigned long long n_quads_total, n_cands_total, n_markers_total;
 };
 

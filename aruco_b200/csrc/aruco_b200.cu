@@ -13,6 +13,7 @@
 #include "ab_device.cuh"
 #include "k_threshold.cuh"
 #include "k_threshold_fast.cuh"
+#include "k_canny.cuh"
 #include "k_contours.cuh"
 #include "k_polygon.cuh"
 #include "k_decode.cuh"
@@ -453,7 +454,24 @@ static int launch_threshold(ab_context* ctx, const Batch& b, int method, double 
         k_threshold_fixed<<<ctx->sm_count * 8, 256, 0, st>>>(b.grey, b.grey_row, b.grey_frame, b.thres, b.bits, b.bits_words,
                                                               b.W, b.H, b.wpr, thr, 0, b.B, out_mul, out_off);
     } else {
-        return set_err(ctx, AB_E_INVALID, "ThresholdMethods::CANNY is not implemented on the device path");
+        // CANNY (src/markerdetector.cpp:669): cv::Canny(grey, out, 10, 220).  The map (0/1/2) is built in the
+        // virtual frames' thres slots; hysteresis passes repeat until a group of passes changes no tile -- the
+        // only place on the path where the host looks at a device flag mid-batch (the edge set is data dependent).
+        if (out_mul != 1) return set_err(ctx, AB_E_INVALID, "CANNY ignores threshold parameters: a parameter range makes no sense");
+        uint8_t* map = b.thres;
+        dim3 g1((b.W + 31) / 32, (b.H + 7) / 8, b.B);
+        k_canny_nms<<<g1, dim3(32, 8), 0, st>>>(b.grey, b.grey_row, b.grey_frame, map, b.W, b.H, 10, 220);
+        unsigned int* d_changed = &b.cnt->canny_changed;
+        dim3 g2((b.W + 31) / 32, (b.H + 31) / 32, b.B);
+        for (int group = 0; group < 4096; group++) {
+            CK(cudaMemsetAsync(d_changed, 0, sizeof(unsigned), st));
+            for (int pass = 0; pass < 4; pass++) k_canny_hyst<<<g2, 256, 0, st>>>(map, b.W, b.H, d_changed);
+            unsigned h_changed = 0;
+            CK(cudaMemcpyAsync(&h_changed, d_changed, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (!h_changed) break;
+        }
+        k_canny_finish<<<ctx->sm_count * 8, 256, 0, st>>>(b.thres, b.bits, b.bits_words, b.W, b.H, b.wpr, b.B, out_mul, out_off);
     }
     CK(cudaGetLastError());
     return AB_OK;

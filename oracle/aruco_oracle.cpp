@@ -57,6 +57,61 @@ void adaptive_threshold(const uint8_t* src, int W, int H, int k, double C, uint8
         }
 }
 
+// cv::Canny(src, dst, low, high), aperture 3, L1 gradient (src/markerdetector.cpp:669): Sobel with replicated border,
+// non-maximum suppression with OpenCV's fixed-point tangent tests, hysteresis with an explicit stack.
+void canny(const uint8_t* src, int W, int H, int low, int high, uint8_t* dst) {
+    std::vector<int> dxv((size_t)W * H), dyv((size_t)W * H), mag((size_t)(W + 2) * (H + 2), 0);
+    auto P = [&](int x, int y) { return (int)src[(size_t)std::min(std::max(y, 0), H - 1) * W + std::min(std::max(x, 0), W - 1)]; };
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            int dx = (P(x + 1, y - 1) - P(x - 1, y - 1)) + 2 * (P(x + 1, y) - P(x - 1, y)) + (P(x + 1, y + 1) - P(x - 1, y + 1));
+            int dy = (P(x - 1, y + 1) - P(x - 1, y - 1)) + 2 * (P(x, y + 1) - P(x, y - 1)) + (P(x + 1, y + 1) - P(x + 1, y - 1));
+            dxv[(size_t)y * W + x] = dx;
+            dyv[(size_t)y * W + x] = dy;
+            mag[(size_t)(y + 1) * (W + 2) + x + 1] = abs(dx) + abs(dy);
+        }
+    std::vector<uint8_t> map((size_t)(W + 2) * (H + 2), 0);  // 0 none, 1 candidate, 2 edge
+    std::vector<int> stack;
+    const int MS = W + 2;
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const int* mp = &mag[(size_t)(y + 1) * MS + x + 1];
+            int m = mp[0];
+            if (m <= low) continue;
+            int xs = dxv[(size_t)y * W + x], ys = dyv[(size_t)y * W + x];
+            long long ax = abs(xs), ay = (long long)abs(ys) << 15, tg22x = ax * 13573;
+            bool keep;
+            if (ay < tg22x) keep = m > mp[-1] && m >= mp[1];
+            else {
+                long long tg67x = tg22x + (ax << 16);
+                if (ay > tg67x) keep = m > mp[-MS] && m >= mp[MS];
+                else {
+                    int s = (xs ^ ys) < 0 ? -1 : 1;
+                    keep = m > mp[-MS - s] && m > mp[MS + s];
+                }
+            }
+            if (!keep) continue;
+            int idx = (y + 1) * MS + x + 1;
+            if (m > high) {
+                map[idx] = 2;
+                stack.push_back(idx);
+            } else
+                map[idx] = 1;
+        }
+    const int nb[8] = {-MS - 1, -MS, -MS + 1, -1, 1, MS - 1, MS, MS + 1};
+    while (!stack.empty()) {
+        int i = stack.back();
+        stack.pop_back();
+        for (int k = 0; k < 8; k++)
+            if (map[i + nb[k]] == 1) {
+                map[i + nb[k]] = 2;
+                stack.push_back(i + nb[k]);
+            }
+    }
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) dst[(size_t)y * W + x] = map[(size_t)(y + 1) * MS + x + 1] == 2 ? 255 : 0;
+}
+
 void erode3x3(const uint8_t* src, int W, int H, uint8_t* dst) {  // cv::erode(src, dst, Mat()): border = +inf
     for (int y = 0; y < H; y++)
         for (int x = 0; x < W; x++) {
@@ -1149,6 +1204,8 @@ void orc_threshold(const uint8_t* grey, int W, int H, int method, double p1, dou
     if (method == 0) {
         int thr = (int)floor(p1);
         for (size_t i = 0; i < (size_t)W * H; i++) out[i] = (int)grey[i] > thr ? 0 : 255;
+    } else if (method == 2) {
+        canny(grey, W, H, 10, 220, out);
     } else {
         if (p1 < 3) p1 = 3;
         else if (((int)p1) % 2 != 1) p1 = (int)(p1 + 1);
@@ -1201,7 +1258,6 @@ int orc_solve_pnp(const float* K, const float* D, const float* corners, float si
 // -2 for unsupported settings).
 int orc_detect(const uint8_t* grey, int W, int H, const orc_params* P, const float* K, const float* D, float marker_size,
                const orc_dict* dict, orc_marker* out, int cap, orc_debug* dbg) {
-    if (P->thres_method == 2) return -2;
     const int n_t = 2 * P->p1_range + 1;  // src/markerdetector.cpp:322-334
     std::vector<std::vector<uint8_t>> thr(n_t, std::vector<uint8_t>((size_t)W * H));
     std::vector<const uint8_t*> thr_ptr;

@@ -41,7 +41,7 @@ def test_defaults_and_setters_mirror_the_reference(built):
         d.warp(np.zeros((20, 20), np.uint8), 56, [[0, 0], [1, 0], [1, 1]])
 
 
-@pytest.mark.parametrize("method,p1,p2", [(1, 7, 7), (1, -1, -1), (1, 2, 7), (1, 8, 6.5), (1, 21, 7), (1, 35, 3), (1, 61, 0), (0, 100, 0), (0, 127.5, 0)])
+@pytest.mark.parametrize("method,p1,p2", [(1, 7, 7), (1, -1, -1), (1, 2, 7), (1, 8, 6.5), (1, 21, 7), (1, 35, 3), (1, 61, 0), (0, 100, 0), (0, 127.5, 0), (2, 0, 0)])
 def test_threshold_worker_bit_exact(det, frames, method, p1, p2):
     from oracle import native
     import ctypes as C

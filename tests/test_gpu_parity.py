@@ -105,6 +105,8 @@ GOLDEN_CASES = [
     # setThresholdParamRange: 3 / 5 threshold images per frame (utils/aruco_test.cpp:134 uses range 2)
     ("single", dict(p1_range=1), True), ("board", dict(p1_range=2), True), ("chessboard", dict(p1_range=2, corner_method=2), True),
     ("single", dict(p1_range=1, thres_method=0, p1=100), True), ("board", dict(p1_range=1, erosion=True), False),
+    # ThresholdMethods::CANNY (cv::Canny(10, 220), markerdetector.cpp:664-675)
+    ("single", dict(thres_method=2), True), ("board", dict(thres_method=2), True), ("chessboard", dict(thres_method=2, corner_method=2), True),
 ]
 
 

@@ -72,7 +72,8 @@ def test_approx_poly_matches_cv2(built, frames):
 CASES = [("single", Params(), True), ("single", Params(corner_method=SUBPIX), True), ("single", Params(corner_method=NONE), True),
          ("board", Params(erosion=True), False), ("chessboard", Params(thres_method=FIXED_THRES, p1=100), True),
          ("hrm", Params(p1=21, p2=7, warp_size=48, min_size=0.005, decoder=DEC_HRM), True),
-         ("single", Params(p1_range=1), True), ("board", Params(p1_range=2), False)]
+         ("single", Params(p1_range=1), True), ("board", Params(p1_range=2), False),
+         ("single", Params(thres_method=2), True), ("chessboard", Params(thres_method=2), False)]
 
 
 @pytest.mark.parametrize("name,prm,cam", CASES)
