@@ -150,3 +150,46 @@ def test_board_detector_goldens(built, frames, expected, name, cfgname):
     prob, board = bd.detect(markers, cfgm, K, D)
     refm = o.board_detect(ms, expected["boards"][cfgname.replace("_pix", "_meters")], K, D)
     assert rel_err(board.Rvec, refm["rvec"]) < 1e-4 and rel_err(board.Tvec, refm["tvec"]) < 1e-4
+
+
+def test_c_abi_strided_and_unaligned_frames(built, frames, expected):
+    """The C ABI takes caller strides: padded rows, gaps between frames and a base pointer that is not 4-byte
+    aligned (scalar load path of the threshold kernel) must give the result of the dense, aligned call."""
+    import ctypes as C
+    from aruco_b200 import MarkerDetector
+    from aruco_b200._lib import ab_marker
+    det = MarkerDetector(0)
+    K, D = intrinsics(expected, "single")
+    ref = [det.detect(frames[n], K, D, 1.0) for n in ("single", "board")]
+    H, W = 480, 640
+    row, gap = W + 37, 1234
+    fstride = row * H + gap
+    buf = np.zeros(1 + 2 * fstride, np.uint8)
+    for off in (0, 1):  # aligned / unaligned base
+        view = buf[off:]
+        for i, n in enumerate(("single", "board")):
+            for y in range(H):
+                view[i * fstride + y * row:i * fstride + y * row + W] = frames[n][y]
+        out = (ab_marker * (2 * 64))()
+        cnt = (C.c_int32 * 2)()
+        Kf, Df = np.ascontiguousarray(K.reshape(9)), np.ascontiguousarray(D)
+        rc = det._lib.ab_detect_batch(det._h, C.c_void_p(view.ctypes.data), W, H, row, fstride, 2, Kf.ctypes.data_as(C.c_void_p),
+                                      Df.ctypes.data_as(C.c_void_p), 1.0, out, 64, cnt)
+        assert rc == 0, det._lib.ab_last_error(det._h)
+        for i in range(2):
+            assert cnt[i] == len(ref[i])
+            for j, m in enumerate(ref[i]):
+                o = out[i * 64 + j]
+                assert o.id == m.id and (np.array(o.corners, np.float32).reshape(4, 2) == m.corners).all()
+                assert (np.array(o.rvec) == m.Rvec).all()
+    # device-resident frames with a row stride
+    import torch
+    dev = torch.zeros((2, H, row), dtype=torch.uint8, device="cuda")
+    dev[0, :, :W] = torch.from_numpy(frames["single"]).cuda()
+    dev[1, :, :W] = torch.from_numpy(frames["board"]).cuda()
+    torch.cuda.synchronize()
+    det.enqueue_device(dev.data_ptr(), W, H, 2, K, D, 1.0, row_stride=row, frame_stride=row * H)
+    res = det.fetch(2, 64)
+    for i in range(2):
+        assert [m.id for m in res[i]] == [m.id for m in ref[i]]
+        assert all((a.corners == b.corners).all() for a, b in zip(res[i], ref[i]))
