@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libaruco_b200.so")
+# ARUCO_B200_LIB selects an alternative build of the same library (kernel-variant experiments)
+LIB_PATH = os.environ.get("ARUCO_B200_LIB") or os.path.join(_HERE, "lib", "libaruco_b200.so")
 
 AB_OK, AB_E_INVALID, AB_E_CUDA, AB_E_CAPACITY, AB_E_NO_DEVICE, AB_E_STATE = 0, -1, -2, -3, -4, -5
 
