@@ -40,6 +40,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner to stdout) must not be
+# able to add to it: fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -143,7 +153,7 @@ def run_reference(args):
                                        "unbuildable: no OpenCV C++)" % (sample, args.steps)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "markers_per_frame": nm / (args.steps * sample), "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -335,7 +345,7 @@ def main():
             "markers_per_frame": n_markers / (args.steps * B), "parity": parity, "clocks": clocks, "e2e": e2e,
             "gpu_launches": KERNELS_PER_BATCH * args.steps, "roofline": roofline, "cpu_baseline": cpu,
             "target_frames_per_s": 2000}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
