@@ -55,47 +55,6 @@ AB_HD uint32_t neighbours8(const BitImage& im, int x, int y) {
            ((b & 1u) << 5) | (((b >> 1) & 1u) << 6) | (((b >> 2) & 1u) << 7);
 }
 
-AB_HD uint32_t nb_from_rows(uint32_t t, uint32_t m, uint32_t b) {
-    return ((m >> 2) & 1u) | (((t >> 2) & 1u) << 1) | (((t >> 1) & 1u) << 2) | ((t & 1u) << 3) | ((m & 1u) << 4) |
-           ((b & 1u) << 5) | (((b >> 1) & 1u) << 6) | (((b >> 2) & 1u) << 7);
-}
-
-// Register-resident 3-row x 64-pixel window of the packed image around a walker.  The walkers are bound by the
-// number of memory transactions (every lane walks its own border: each 4-byte load is its own L1 wavefront),
-// so the six loads of neighbours8() are replaced by: nothing for a horizontal step inside the window, one
-// 64-bit row for a vertical/diagonal step, a full reload (three rows) only when the window is left.
-struct NbCache {
-    uint64_t r0, r1, r2;  // rows y-1, y, y+1: padded words wb, wb+1
-    int wb, y;            // wb < 0: empty
-};
-
-AB_HD uint64_t cache_row(const BitImage& im, int y, int wb) {
-    const uint32_t* r = im.row(y) + wb;
-    return (uint64_t)r[0] | ((uint64_t)r[1] << 32);
-}
-
-AB_HD uint32_t neighbours8_cached(const BitImage& im, NbCache& c, int x, int y) {
-    const int p = x - 1 + 32 * BIT_PAD;  // padded bit of pixel x-1; the window must hold bits p .. p+2
-    const int w0 = p >> 5, w1 = (p + 2) >> 5;
-    if (c.wb < 0 || w0 < c.wb || w1 > c.wb + 1 || y > c.y + 1 || y < c.y - 1) {
-        c.wb = (w1 != w0) ? w0 : (((p & 31) < 16) ? w0 - 1 : w0);  // keep the walker away from the window edge
-        c.r0 = cache_row(im, y - 1, c.wb);
-        c.r1 = cache_row(im, y, c.wb);
-        c.r2 = cache_row(im, y + 1, c.wb);
-    } else if (y == c.y + 1) {
-        c.r0 = c.r1;
-        c.r1 = c.r2;
-        c.r2 = cache_row(im, y + 1, c.wb);
-    } else if (y == c.y - 1) {
-        c.r2 = c.r1;
-        c.r1 = c.r0;
-        c.r0 = cache_row(im, y - 1, c.wb);
-    }
-    c.y = y;
-    const int sh = p - 32 * c.wb;
-    return nb_from_rows((uint32_t)(c.r0 >> sh) & 7u, (uint32_t)(c.r1 >> sh) & 7u, (uint32_t)(c.r2 >> sh) & 7u);
-}
-
 AB_HD int dir_dx(int d) { return (d == 0 || d == 1 || d == 7) ? 1 : ((d >= 3 && d <= 5) ? -1 : 0); }
 AB_HD int dir_dy(int d) { return (d >= 1 && d <= 3) ? -1 : ((d >= 5) ? 1 : 0); }
 
@@ -180,17 +139,6 @@ AB_HD uint32_t walk_backward(const BitImage& im, WalkState& s) {
     int qx = s.x + dir_dx(s.b), qy = s.y + dir_dy(s.b);
     int d = (s.b + 4) & 7;  // direction from the predecessor pixel to the current one
     uint32_t nbq = neighbours8(im, qx, qy);
-    s.b = first_clockwise(nbq, d);
-    s.x = qx;
-    s.y = qy;
-    return nbq;
-}
-
-// walk_backward through the register window of the backward walker
-AB_HD uint32_t walk_backward_cached(const BitImage& im, NbCache& c, WalkState& s) {
-    int qx = s.x + dir_dx(s.b), qy = s.y + dir_dy(s.b);
-    int d = (s.b + 4) & 7;
-    uint32_t nbq = neighbours8_cached(im, c, qx, qy);
     s.b = first_clockwise(nbq, d);
     s.x = qx;
     s.y = qy;

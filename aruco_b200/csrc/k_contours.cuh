@@ -106,7 +106,6 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
     TraceStart st{0, 0, 0, 0};
     WalkState fw{0, 0, 0}, bw{0, 0, 0};
     uint32_t nb_fw = 0, type_bit = 0;
-    NbCache cf{0, 0, 0, -1, 0}, cb{0, 0, 0, -1, 0};  // register windows of the forward / backward walker
     int nf = 0, ng = 0, frame = 0;
     for (;;) {
         unsigned idle = __ballot_sync(FULL, !active && !exhausted);
@@ -132,8 +131,7 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                     bw = WalkState{(int)(q.bxy & 0xFFFFu), (int)(q.bxy >> 16), (int)((q.dirs >> 4) & 7u)};
                     nf = (int)q.nf;
                     ng = (int)q.ng;
-                    cf.wb = cb.wb = -1;
-                    nb_fw = neighbours8_cached(im, cf, fw.x, fw.y);
+                    nb_fw = neighbours8(im, fw.x, fw.y);
                     active = true;
                 } else {
                     uint2 rec = b.starts[i];
@@ -143,8 +141,7 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                     if (make_start(im, (int)(rec.x >> 31), (int)(rec.y & 0xFFFFu), (int)(rec.y >> 16), st)) {
                         fw = WalkState{st.x, st.y, st.b};
                         bw = fw;
-                        cf.wb = cb.wb = -1;
-                        nb_fw = neighbours8_cached(im, cf, fw.x, fw.y);
+                        nb_fw = neighbours8(im, fw.x, fw.y);
                         nf = ng = 0;
                         nodefer = false;
                         active = true;
@@ -164,9 +161,9 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                 // is only COMMITTED if the forward step neither closed the cycle nor hit a smaller start
                 const WalkState bw0 = bw;
                 walk_forward(fw, nb_fw);
-                nb_fw = neighbours8_cached(im, cf, fw.x, fw.y);
+                nb_fw = neighbours8(im, fw.x, fw.y);
                 WalkState bw1 = bw0;
-                const uint32_t nb_bw = walk_backward_cached(im, cb, bw1);
+                const uint32_t nb_bw = walk_backward(im, bw1);
                 nf++;
                 if (same_state(fw, bw0)) {
                     closed = true;
@@ -237,7 +234,6 @@ __global__ void __launch_bounds__(128) k_emit(Batch b) {
     bool active = false, exhausted = false, backward = false;
     BitImage im = b.bit_image(0);
     WalkState w{0, 0, 0};
-    NbCache cw{0, 0, 0, -1, 0};
     uint32_t nb = 0;
     int remaining = 0;
     uint32_t* out = nullptr;
@@ -262,11 +258,10 @@ __global__ void __launch_bounds__(128) k_emit(Batch b) {
                         w = WalkState{st.x, st.y, st.b};
                         const int h0 = (n + 1) >> 1;
                         backward = (i & 1u) != 0;
-                        cw.wb = -1;
                         if (!backward) {
                             out = b.pool + rec.off;  // positions 0 .. h0-1, ascending
                             remaining = h0;
-                            nb = neighbours8_cached(im, cw, w.x, w.y);
+                            nb = neighbours8(im, w.x, w.y);
                         } else {
                             out = b.pool + rec.off + n - 1;  // positions n-1 .. h0, descending
                             remaining = n - h0;
@@ -289,11 +284,11 @@ __global__ void __launch_bounds__(128) k_emit(Batch b) {
                         break;
                     }
                     walk_forward(w, nb);
-                    nb = neighbours8_cached(im, cw, w.x, w.y);
+                    nb = neighbours8(im, w.x, w.y);
                 }
             } else {
                 for (int r = 0; r < STEPS; r++) {
-                    walk_backward_cached(im, cw, w);
+                    walk_backward(im, w);
                     *out-- = (uint32_t)w.x | ((uint32_t)w.y << 16);
                     if (--remaining == 0) {
                         active = false;

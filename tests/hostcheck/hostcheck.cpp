@@ -245,33 +245,3 @@ extern "C" int hc_solve_pnp_planar(const float* K, const float* D, const float* 
     ab::Camera c = make_cam(K, D);
     return ab::solve_pnp_planar(c, obj, img, N, rvec, tvec) ? 1 : 0;
 }
-
-// the register-window neighbourhood (neighbours8_cached) against the plain one along real border walks
-extern "C" long long hc_check_nb_cache(const uint8_t* img, int W, int H) {
-    std::vector<uint32_t> bits(ab::bit_image_words(W, H));
-    hc_pack_bits(img, W, H, bits.data());
-    ab::BitImage im{bits.data(), ab::bit_words_per_row(W), W, H};
-    long long bad = 0, steps = 0;
-    for (int y = 0; y < H; y++)
-        for (int x = 0; x < W; x++) {
-            uint32_t nb = ab::neighbours8(im, x, y);
-            bool fg = img[(size_t)y * W + x] != 0;
-            if (!(fg && ab::is_outer_candidate(nb))) continue;
-            ab::TraceStart st;
-            if (!ab::make_start(im, 0, x, y, st)) continue;
-            ab::WalkState fw{st.x, st.y, st.b}, bw = fw;
-            ab::NbCache cf{0, 0, 0, -1, 0}, cb{0, 0, 0, -1, 0};
-            uint32_t nf = ab::neighbours8_cached(im, cf, fw.x, fw.y);
-            for (int k = 0; k < 400; k++) {
-                if (nf != ab::neighbours8(im, fw.x, fw.y)) bad++;
-                ab::walk_forward(fw, nf);
-                nf = ab::neighbours8_cached(im, cf, fw.x, fw.y);
-                ab::WalkState b2 = bw;
-                uint32_t n1 = ab::walk_backward_cached(im, cb, bw);
-                uint32_t n2 = ab::walk_backward(im, b2);
-                if (n1 != n2 || !ab::same_state(bw, b2)) bad++;
-                steps++;
-            }
-        }
-    return bad * 1000000000LL + steps;
-}
