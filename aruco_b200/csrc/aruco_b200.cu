@@ -22,6 +22,8 @@
 
 using namespace ab;
 
+constexpr int MAX_SUB = 4;  // sub-batches (streams) a batch can be pipelined over
+
 #define AB_VERSION "aruco_b200 0.1 (sm_100a)"
 
 struct ab_context {
@@ -30,6 +32,10 @@ struct ab_context {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t sub_stream[MAX_SUB] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
+    int n_sub_streams = 2;
+    int last_nsub = 1;
     ab_params params;
     std::string err;
     // reserved geometry
@@ -172,6 +178,12 @@ int ab_create(int device, ab_context** out) {
         delete ctx;
         return AB_E_CUDA;
     }
+    for (int i = 0; i < MAX_SUB; i++) {
+        cudaStreamCreateWithFlags(&ctx->sub_stream[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    if (const char* e = getenv("ARUCO_B200_SUBBATCHES")) ctx->n_sub_streams = std::max(1, std::min(MAX_SUB, atoi(e)));
     for (int i = 0; i < 6; i++) cudaEventCreate(&ctx->ev[i]);
     for (int i = 0; i < 10; i++) cudaEventCreate(&ctx->kev[i]);
     for (int i = 0; i < 2; i++) {
@@ -203,6 +215,11 @@ void ab_destroy(ab_context* ctx) {
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
     }
+    for (int i = 0; i < MAX_SUB; i++) {
+        if (ctx->sub_stream[i]) cudaStreamDestroy(ctx->sub_stream[i]);
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -377,7 +394,7 @@ int ab_reserve(ab_context* ctx, int width, int height, int max_batch, int max_qu
     CK(cudaMalloc(&ctx->d_cands, B * capC * sizeof(CandRec)));
     CK(cudaMalloc(&ctx->d_canon, B * capC * (size_t)ctx->S_alloc * ctx->S_alloc));
     CK(cudaMalloc(&ctx->d_markers, B * capC * sizeof(ab_marker)));
-    ctx->counters_bytes = sizeof(Counters) + 3 * B * sizeof(unsigned);
+    ctx->counters_bytes = MAX_SUB * sizeof(Counters) + 3 * B * sizeof(unsigned);
     CK(cudaMalloc(&ctx->d_counters, ctx->counters_bytes));
     CK(cudaMallocHost(&ctx->h_counters, ctx->counters_bytes));
     return AB_OK;
@@ -414,8 +431,9 @@ static Camera make_camera(const float* K, const float* D) {
     return c;
 }
 
-static int launch_threshold(ab_context* ctx, const Batch& b, int method, double p1, double p2, int out_mul = 1, int out_off = 0) {
-    cudaStream_t st = ctx->stream;
+static int launch_threshold(ab_context* ctx, const Batch& b, int method, double p1, double p2, int out_mul = 1, int out_off = 0,
+                            cudaStream_t st_in = nullptr) {
+    cudaStream_t st = st_in ? st_in : ctx->stream;
     if (method == AB_THRES_ADAPTIVE) {
         // thresHold: ensure an odd block size >= 3 (src/markerdetector.cpp:657-660)
         if (p1 < 3) p1 = 3;
@@ -528,7 +546,7 @@ static int fill_batch(ab_context* ctx, Batch& b, const uint8_t* dgrey, size_t ro
     b.canon = ctx->d_canon;
     b.markers = ctx->d_markers;
     b.cnt = (Counters*)ctx->d_counters;
-    b.n_quads = (unsigned*)(ctx->d_counters + sizeof(Counters));
+    b.n_quads = (unsigned*)(ctx->d_counters + MAX_SUB * sizeof(Counters));
     b.n_cands = b.n_quads + ctx->maxB;
     b.n_markers = b.n_cands + ctx->maxB;
     // contour length limits (src/markerdetector.cpp:500-501): f32 product truncated to int
@@ -556,42 +574,48 @@ static int fill_batch(ab_context* ctx, Batch& b, const uint8_t* dgrey, size_t ro
 }
 
 // launches the whole path for frames resident at `dgrey`
-static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t frame, int n, const float* K,
-                     const float* D, float marker_size) {
+// view of frames [f0, f0+nf) of a batch as sub-batch s: per-frame buffers are offset, the append lists are
+// partitioned by the per-frame capacities, counters are per sub-batch
+static Batch sub_view(ab_context* ctx, const Batch& w, int f0, int nf, int s) {
+    Batch v = w;
+    const size_t vt = (size_t)w.n_t;  // virtual frames per frame
+    v.B = nf;
+    v.grey = w.grey + (size_t)f0 * w.grey_frame;
+    v.thres = w.thres + (size_t)f0 * vt * w.W * w.H;
+    v.bits = w.bits + (size_t)f0 * vt * w.bits_words;
+    v.bits2 = w.bits2 + (size_t)f0 * vt * w.bits_words;
+    v.starts = w.starts + (size_t)ctx->capStartsPF * vt * f0;
+    v.cap_starts = (unsigned long long)ctx->capStartsPF * vt * nf;
+    v.contours = w.contours + (size_t)ctx->capContoursPF * vt * f0;
+    v.cap_contours = ctx->capContoursPF * (unsigned)(vt * nf);
+    v.pool = w.pool + (size_t)ctx->capPoolPF * vt * f0;
+    v.cap_pool = (unsigned long long)ctx->capPoolPF * vt * nf;
+    v.longq = w.longq + (size_t)ctx->capLongPF * vt * f0;
+    v.cap_long = ctx->capLongPF * (unsigned)(vt * nf);
+    v.quads = w.quads + (size_t)f0 * w.cap_q;
+    v.cands = w.cands + (size_t)f0 * w.cap_c;
+    v.canon = w.canon + (size_t)f0 * w.cap_c * (size_t)(w.S * w.S);
+    v.markers = w.markers + (size_t)f0 * w.cap_c;
+    v.cnt = w.cnt + s;
+    v.n_quads = w.n_quads + f0;
+    v.n_cands = w.n_cands + f0;
+    v.n_markers = w.n_markers + f0;
+    return v;
+}
+
+// one sub-batch (a view of the batch buffers) on one stream: every stage of the path
+static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
     const ab_params& P = ctx->params;
-    if (P.decoder == AB_DECODER_HRM && !ctx->have_dict)
-        return set_err(ctx, AB_E_STATE, "HRM decoder selected but no dictionary loaded (ab_load_hrm_dictionary)");
-    if (P.decoder == AB_DECODER_HOST_CALLBACK && !ctx->cb)
-        return set_err(ctx, AB_E_STATE, "host-callback decoder selected but no callback set");
-    if (P.decoder == AB_DECODER_HRM && (ctx->dict.n + 2) > P.warp_size)
-        return set_err(ctx, AB_E_INVALID, "warp size too small for the dictionary");
-    if (P.corner_method == AB_CORNER_SUBPIX && ((int)P.thres_param1 < 1 || (int)P.thres_param1 > 24))
-        return set_err(ctx, AB_E_INVALID, "SUBPIX window %d outside 1..24", (int)P.thres_param1);
-    if (P.locked_corners && ((int)P.thres_param1 < 1 || (int)P.thres_param1 > 24))
-        return set_err(ctx, AB_E_INVALID, "locked-corner window %d outside 1..24", (int)P.thres_param1);
-    // setThresholdParamRange (markerdetector.h:152, cpp:322-334): 2*range+1 threshold images per frame, param1 =
-    // p1 - range + range*i (sic, SURVEY B.6); they live as n_t consecutive "virtual frames" per frame for the
-    // threshold / contour / polygon stages and are merged per frame by k_polygon's quad keys.
-    const int n_t = 2 * P.thres_param1_range + 1;
-    if (n * n_t > ctx->maxB) return set_err(ctx, AB_E_STATE, "internal: %d virtual frames > reserved %d", n * n_t, ctx->maxB);
-    Batch b;
-    fill_batch(ctx, b, dgrey, row, frame, n, K, D, marker_size);
-    b.n_t = n_t;
-    b.cap_starts *= n_t;
-    b.cap_contours *= (unsigned)n_t;
-    b.cap_pool *= n_t;
-    b.cap_long *= (unsigned)n_t;
-    cudaStream_t st = ctx->stream;
+    const int n = b.B, n_t = b.n_t;
     const int sms = ctx->sm_count;
-    if (ctx->timing) cudaEventRecord(ctx->ev[0], st);
-    CK(cudaMemsetAsync(ctx->d_counters, 0, ctx->counters_bytes, st));
-    if (ctx->timing) cudaEventRecord(ctx->kev[0], st);
+    if (timing) cudaEventRecord(ctx->ev[0], st);
+    if (timing) cudaEventRecord(ctx->kev[0], st);
     for (int ti = 0; ti < n_t; ti++) {
         double p1 = n_t == 1 ? P.thres_param1 : P.thres_param1 - P.thres_param1_range + (double)P.thres_param1_range * ti;
-        int rc = launch_threshold(ctx, b, P.thres_method, p1, P.thres_param2, n_t, ti);
+        int rc = launch_threshold(ctx, b, P.thres_method, p1, P.thres_param2, n_t, ti, st);
         if (rc) return rc;
     }
-    if (ctx->timing) cudaEventRecord(ctx->kev[1], st);
+    if (timing) cudaEventRecord(ctx->kev[1], st);
     Batch bv = b;  // the same buffers seen as n * n_t virtual frames
     bv.B = n * n_t;
     if (P.erosion) {
@@ -599,19 +623,19 @@ static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t f
         std::swap(bv.bits, bv.bits2);
         std::swap(b.bits, b.bits2);
     }
-    if (ctx->timing) cudaEventRecord(ctx->ev[1], st);
+    if (timing) cudaEventRecord(ctx->ev[1], st);
     k_scan_starts<<<sms * 8, 256, 0, st>>>(bv);
-    if (ctx->timing) cudaEventRecord(ctx->kev[2], st);
+    if (timing) cudaEventRecord(ctx->kev[2], st);
     k_trace<false><<<sms * 8, 128, 0, st>>>(bv);
     k_trace<true><<<sms * 4, 128, 0, st>>>(bv);
     k_emit<<<sms * 8, 128, 0, st>>>(bv);
-    if (ctx->timing) cudaEventRecord(ctx->kev[3], st);
+    if (timing) cudaEventRecord(ctx->kev[3], st);
     k_polygon<<<sms * 4, 128, 0, st>>>(bv);
-    if (ctx->timing) cudaEventRecord(ctx->kev[4], st);
+    if (timing) cudaEventRecord(ctx->kev[4], st);
     k_frame_filter<<<n, 256, 0, st>>>(b);
     CK(cudaGetLastError());
-    if (ctx->timing) cudaEventRecord(ctx->kev[5], st);
-    if (ctx->timing) cudaEventRecord(ctx->ev[2], st);
+    if (timing) cudaEventRecord(ctx->kev[5], st);
+    if (timing) cudaEventRecord(ctx->ev[2], st);
     dim3 gcand(b.cap_c, n);
     dim3 gdec((b.cap_c + DECODE_WARPS - 1) / DECODE_WARPS, n);
     const size_t dec_smem = DECODE_WARPS * decode_smem_per_warp(b.S);
@@ -645,8 +669,8 @@ static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t f
         k_decode<<<gdec, 32 * DECODE_WARPS, dec_smem, st>>>(b, 0);
         CK(cudaGetLastError());
     }
-    if (ctx->timing) cudaEventRecord(ctx->kev[6], st);
-    if (ctx->timing) cudaEventRecord(ctx->ev[3], st);
+    if (timing) cudaEventRecord(ctx->kev[6], st);
+    if (timing) cudaEventRecord(ctx->ev[3], st);
     if (P.locked_corners && (P.corner_method == AB_CORNER_HARRIS || P.corner_method == AB_CORNER_SUBPIX)) {
         // findCornerMaxima before the refiner (src/markerdetector.cpp:397-398)
         int w = b.subpix_win;
@@ -665,15 +689,68 @@ static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t f
         k_refine_subpix<<<dim3(b.cap_c, n), 128, smem, st>>>(b);
     }
     CK(cudaGetLastError());
-    if (ctx->timing) cudaEventRecord(ctx->kev[7], st);
-    if (ctx->timing) cudaEventRecord(ctx->ev[4], st);
+    if (timing) cudaEventRecord(ctx->kev[7], st);
+    if (timing) cudaEventRecord(ctx->ev[4], st);
     k_finalize<<<n, 128, 0, st>>>(b);
     CK(cudaGetLastError());
-    if (ctx->timing) cudaEventRecord(ctx->kev[8], st);
-    if (ctx->timing) cudaEventRecord(ctx->ev[5], st);
+    if (timing) cudaEventRecord(ctx->kev[8], st);
+    if (timing) cudaEventRecord(ctx->ev[5], st);
+    return AB_OK;
+}
+
+static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t frame, int n, const float* K,
+                     const float* D, float marker_size) {
+    const ab_params& P = ctx->params;
+    if (P.decoder == AB_DECODER_HRM && !ctx->have_dict)
+        return set_err(ctx, AB_E_STATE, "HRM decoder selected but no dictionary loaded (ab_load_hrm_dictionary)");
+    if (P.decoder == AB_DECODER_HOST_CALLBACK && !ctx->cb)
+        return set_err(ctx, AB_E_STATE, "host-callback decoder selected but no callback set");
+    if (P.decoder == AB_DECODER_HRM && (ctx->dict.n + 2) > P.warp_size)
+        return set_err(ctx, AB_E_INVALID, "warp size too small for the dictionary");
+    if (P.corner_method == AB_CORNER_SUBPIX && ((int)P.thres_param1 < 1 || (int)P.thres_param1 > 24))
+        return set_err(ctx, AB_E_INVALID, "SUBPIX window %d outside 1..24", (int)P.thres_param1);
+    if (P.locked_corners && ((int)P.thres_param1 < 1 || (int)P.thres_param1 > 24))
+        return set_err(ctx, AB_E_INVALID, "locked-corner window %d outside 1..24", (int)P.thres_param1);
+    // setThresholdParamRange (markerdetector.h:152, cpp:322-334): 2*range+1 threshold images per frame, param1 =
+    // p1 - range + range*i (sic, SURVEY B.6); they live as n_t consecutive "virtual frames" per frame for the
+    // threshold / contour / polygon stages and are merged per frame by k_polygon's quad keys.
+    const int n_t = 2 * P.thres_param1_range + 1;
+    if (n * n_t > ctx->maxB) return set_err(ctx, AB_E_STATE, "internal: %d virtual frames > reserved %d", n * n_t, ctx->maxB);
+    Batch b;
+    fill_batch(ctx, b, dgrey, row, frame, n, K, D, marker_size);
+    b.n_t = n_t;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemsetAsync(ctx->d_counters, 0, ctx->counters_bytes, st));
+    // Sub-batch pipelining: several stages (long border walks, point emission, polygon fit, refinement, pose) are
+    // bound by dependent-load latency with few resident warps, others by instruction issue.  Two (or more) halves
+    // of the batch on separate streams let the latency-bound kernels of one half run under the issue-bound
+    // kernels of the other.  Every buffer is indexed by frame, so a sub-batch is just an offset view; the global
+    // append lists are partitioned by the per-frame capacities.  Per-kernel timing needs a single stream.
+    int nsub = 1;
+    if (!ctx->timing && P.decoder != AB_DECODER_HOST_CALLBACK && P.thres_method != AB_THRES_CANNY) {
+        nsub = ctx->n_sub_streams;
+        while (nsub > 1 && n < 8 * nsub) nsub--;
+    }
+    if (nsub > 1) {
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        for (int s = 0; s < nsub; s++) CK(cudaStreamWaitEvent(ctx->sub_stream[s], ctx->ev_fork, 0));
+    }
+    for (int s = 0; s < nsub; s++) {
+        const int f0 = (int)((long long)s * n / nsub), nf = (int)((long long)(s + 1) * n / nsub) - f0;
+        Batch v = sub_view(ctx, b, f0, nf, s);
+        int rc = run_sub(ctx, v, nsub > 1 ? ctx->sub_stream[s] : st, ctx->timing && nsub == 1);
+        if (rc) return rc;
+    }
+    if (nsub > 1) {
+        for (int s = 0; s < nsub; s++) {
+            CK(cudaEventRecord(ctx->ev_join[s], ctx->sub_stream[s]));
+            CK(cudaStreamWaitEvent(st, ctx->ev_join[s], 0));
+        }
+    }
     ctx->last = b;
     ctx->have_last = true;
     ctx->last_n = n;
+    ctx->last_nsub = nsub;
     return AB_OK;
 }
 
@@ -716,10 +793,11 @@ static int fetch_into(ab_context* ctx, ab_marker* out, int cap, int32_t* counts)
         CK(cudaMemcpy2DAsync(ctx->h_markers, (size_t)ncopy * sizeof(ab_marker), b.markers, (size_t)b.cap_c * sizeof(ab_marker),
                              (size_t)ncopy * sizeof(ab_marker), n, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    const Counters* c = (const Counters*)ctx->h_counters;
-    int rc = check_device_errors(ctx, c);
+    Counters csum = *(const Counters*)ctx->h_counters;
+    for (int s2 = 1; s2 < MAX_SUB; s2++) csum.err |= ((const Counters*)ctx->h_counters)[s2].err;
+    int rc = check_device_errors(ctx, &csum);
     if (rc) return rc;
-    const unsigned* nm = (const unsigned*)(ctx->h_counters + sizeof(Counters)) + 2 * (size_t)ctx->maxB;
+    const unsigned* nm = (const unsigned*)(ctx->h_counters + MAX_SUB * sizeof(Counters)) + 2 * (size_t)ctx->maxB;
     for (int f = 0; f < n; f++) {
         if ((int)nm[f] > cap && out)
             return set_err(ctx, AB_E_CAPACITY, "frame %d has %u markers but cap_per_frame is %d", f, nm[f], cap);
@@ -889,12 +967,18 @@ int ab_get_contour(ab_context* ctx, int frame, int candidate, int32_t* xy, int c
     CK(cudaStreamSynchronize(ctx->stream));
     CandRec cr;
     CK(cudaMemcpy(&cr, b.cands + (size_t)frame * b.cap_c + candidate, sizeof(CandRec), cudaMemcpyDeviceToHost));
+    // contour indices are relative to the list of the sub-batch that processed the frame
+    int sb = 0;
+    while (sb + 1 < ctx->last_nsub && frame >= (int)((long long)(sb + 1) * ctx->last_n / ctx->last_nsub)) sb++;
+    const int sf0 = (int)((long long)sb * ctx->last_n / ctx->last_nsub);
+    const ContourRec* cbase = b.contours + (size_t)ctx->capContoursPF * b.n_t * sf0;
+    const uint32_t* pbase = b.pool + (size_t)ctx->capPoolPF * b.n_t * sf0;
     ContourRec rec;
-    CK(cudaMemcpy(&rec, b.contours + cr.contour, sizeof(ContourRec), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&rec, cbase + cr.contour, sizeof(ContourRec), cudaMemcpyDeviceToHost));
     *n = (int32_t)rec.n;
     if ((int)rec.n > cap_points) return set_err(ctx, AB_E_CAPACITY, "contour has %u points > cap %d", rec.n, cap_points);
     std::vector<uint32_t> p(rec.n);
-    CK(cudaMemcpy(p.data(), b.pool + rec.off, sizeof(uint32_t) * rec.n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(p.data(), pbase + rec.off, sizeof(uint32_t) * rec.n, cudaMemcpyDeviceToHost));
     for (uint32_t i = 0; i < rec.n; i++) {
         uint32_t v = cr.swapped ? p[rec.n - 1 - i] : p[i];  // the reference reverses swapped contours (:622-625)
         xy[2 * i] = (int32_t)(v & 0xFFFFu);
@@ -907,10 +991,18 @@ int ab_get_counters(ab_context* ctx, int64_t* counters, int n) {
     if (!ctx || !ctx->have_last || !counters) return set_err(ctx, AB_E_INVALID, "no batch");
     cudaSetDevice(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
-    Counters c;
-    CK(cudaMemcpy(&c, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost));
-    int64_t v[6] = {(int64_t)c.n_starts, (int64_t)c.n_contours, (int64_t)c.pool_used, (int64_t)c.n_quads_total,
-                    (int64_t)c.n_cands_total, (int64_t)c.n_markers_total};
+    Counters cs[MAX_SUB];
+    CK(cudaMemcpy(cs, ctx->d_counters, sizeof(cs), cudaMemcpyDeviceToHost));
+    int64_t v[6] = {0, 0, 0, 0, 0, 0};
+    for (int s2 = 0; s2 < MAX_SUB; s2++) {
+        const Counters& c = cs[s2];
+        v[0] += (int64_t)c.n_starts;
+        v[1] += (int64_t)c.n_contours;
+        v[2] += (int64_t)c.pool_used;
+        v[3] += (int64_t)c.n_quads_total;
+        v[4] += (int64_t)c.n_cands_total;
+        v[5] += (int64_t)c.n_markers_total;
+    }
     for (int i = 0; i < n && i < 6; i++) counters[i] = v[i];
     return AB_OK;
 }
@@ -978,6 +1070,7 @@ int ab_detect_rectangles(ab_context* ctx, const uint8_t* thres, int width, int h
     ctx->last = b;
     ctx->have_last = true;
     ctx->last_n = 1;
+    ctx->last_nsub = 1;
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, ctx->counters_bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     rc = check_device_errors(ctx, (const Counters*)ctx->h_counters);

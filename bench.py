@@ -202,7 +202,6 @@ def main():
     det = MarkerDetector(local)
     det.set_stream(stream.cuda_stream)
     det.reserve(W, H, B)
-    det.enable_timing(True)
     cap = 128
 
     def step():
@@ -249,12 +248,19 @@ def main():
     for _ in range(args.steps):
         _, counts = step()
         n_markers += sum(counts)
-        for k, v in det.kernel_ms().items():
-            kernel_ms[k] += v / args.steps
     e1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
+    # per-kernel durations (for the roofline): a separate, untimed pass -- the library pipelines sub-batches over
+    # several streams in the timed loop, per-kernel CUDA events need everything on one stream
+    det.enable_timing(True)
+    step()
+    for _ in range(3):
+        step()
+        for k, v in det.kernel_ms().items():
+            kernel_ms[k] += v / 3
+    det.enable_timing(False)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
