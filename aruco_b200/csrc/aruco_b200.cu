@@ -34,7 +34,7 @@ struct ab_context {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t sub_stream[MAX_SUB] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
-    int n_sub_streams = 2;
+    int n_sub_streams = 1;  // measured on B200: no gain from 2-4 sub-batches (full grids leave no room to co-schedule)
     int last_nsub = 1;
     ab_params params;
     std::string err;
@@ -627,10 +627,10 @@ static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
     k_scan_starts<<<sms * 8, 256, 0, st>>>(bv);
     if (timing) cudaEventRecord(ctx->kev[2], st);
     k_trace<false><<<sms * 8, 128, 0, st>>>(bv);
-    k_trace<true><<<sms * 4, 128, 0, st>>>(bv);
+    k_trace<true><<<sms * 8, 128, 0, st>>>(bv);
     k_emit<<<sms * 8, 128, 0, st>>>(bv);
     if (timing) cudaEventRecord(ctx->kev[3], st);
-    k_polygon<<<sms * 4, 128, 0, st>>>(bv);
+    k_polygon<<<sms * 8, 128, 0, st>>>(bv);
     if (timing) cudaEventRecord(ctx->kev[4], st);
     k_frame_filter<<<n, 256, 0, st>>>(b);
     CK(cudaGetLastError());
