@@ -627,7 +627,7 @@ static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
     k_scan_starts<<<sms * 8, 256, 0, st>>>(bv);
     if (timing) cudaEventRecord(ctx->kev[2], st);
     k_trace<false><<<sms * 8, 128, 0, st>>>(bv);
-    k_trace<true><<<sms * 8, 128, 0, st>>>(bv);
+    k_trace<true><<<sms * 4, 128, 0, st>>>(bv);
     k_emit<<<sms * 8, 128, 0, st>>>(bv);
     if (timing) cudaEventRecord(ctx->kev[3], st);
     k_polygon<<<sms * 8, 128, 0, st>>>(bv);

@@ -249,7 +249,9 @@ __global__ void __launch_bounds__(128) k_emit(Batch b) {
                 if (i >= n_items) {
                     exhausted = true;
                 } else {
-                    const ContourRec rec = b.contours[i >> 1];
+                    // items [0, ncont) walk forwards, [ncont, 2 ncont) backwards: warps stay homogeneous, so a round
+                    // costs one dependent load round trip instead of two (forward lanes, then backward lanes)
+                    const ContourRec rec = b.contours[i < ncont ? i : i - ncont];
                     const int n = (int)rec.n;
                     if (n > 0) {
                         im = b.bit_image((int)(rec.frame & 0x7FFFFFFFu));
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(128) k_emit(Batch b) {
                         make_start(im, (int)(rec.frame >> 31), (int)(rec.key % (uint32_t)b.W), (int)(rec.key / (uint32_t)b.W), st);
                         w = WalkState{st.x, st.y, st.b};
                         const int h0 = (n + 1) >> 1;
-                        backward = (i & 1u) != 0;
+                        backward = i >= ncont;
                         if (!backward) {
                             out = b.pool + rec.off;  // positions 0 .. h0-1, ascending
                             remaining = h0;
