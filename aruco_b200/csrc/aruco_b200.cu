@@ -12,7 +12,7 @@
 
 #include "ab_device.cuh"
 #include "k_threshold.cuh"
-#include "k_threshold_fast.cuh"
+#include "k_threshold_pair.cuh"
 #include "k_canny.cuh"
 #include "k_contours.cuh"
 #include "k_polygon.cuh"
@@ -466,7 +466,7 @@ static int launch_threshold(ab_context* ctx, const Batch& b, int method, double 
         size_t SPAN = 4 * (size_t)nth;
         size_t smem = (((size_t)k * SPAN + 15) & ~(size_t)15) + 4 * SPAN + nth;
         dim3 grid((b.W + a.TWo - 1) / a.TWo, (b.H + a.RH - 1) / a.RH, b.B);
-        if (!launch_threshold_fast(a, b.B, st)) k_threshold_adaptive<<<grid, nth, smem, st>>>(a);
+        if (!launch_threshold_pair(a, b.B, st) && !launch_threshold_fast(a, b.B, st)) k_threshold_adaptive<<<grid, nth, smem, st>>>(a);
     } else if (method == AB_THRES_FIXED) {
         int thr = (int)floor(p1);
         k_threshold_fixed<<<ctx->sm_count * 8, 256, 0, st>>>(b.grey, b.grey_row, b.grey_frame, b.thres, b.bits, b.bits_words,
