@@ -44,10 +44,15 @@ template <int K, int TO>
 __global__ void __launch_bounds__(TO + 32) k_threshold_pair(ThrArgs a) {
     constexpr int R = K / 2, R4 = (R + 3) & ~3, HT = R4 / 4, NV = 4 + 2 * R4, HO = 4 * TO, TW = 2 * HO, CSW = HO + 2 * R4, K2 = K * K;
     constexpr uint32_t BUF_BYTES = CSW * 4;
+    constexpr int NT = TO + 2 * HT;              // working threads
+    constexpr int DEPTH = 8;                     // source rows in flight (cp.async groups)
+    constexpr uint32_t STAGE_ROW = NT * 8;       // bytes of one staged row: 2 words per thread
     constexpr int RH = (THR_RH / K) * K;  // rows per CTA: whole turns of the ring, so the unrolled loop has no exits
     __shared__ __align__(16) uint32_t cs[2][CSW];
+    __shared__ __align__(16) uint2 stage[DEPTH][NT];  // ncu r1j: with loads held in registers two of the K unrolled steps
+                                                      // waited ~1 row on the scoreboard; cp.async groups decouple them
     const int t = threadIdx.x;
-    if (t >= TO + 2 * HT) return;  // spare lanes of the halo warp
+    if (t >= NT) return;  // spare lanes of the halo warp
     const int X0 = blockIdx.x * TW, y0 = blockIdx.y * RH, f = blockIdx.z;
     const bool is_out = t < TO;
     // ci: index into a row of cs.  cs[ci] = (V[X0 - R4 + ci], V[X0 + HO - R4 + ci])
@@ -78,27 +83,40 @@ __global__ void __launch_bounds__(TO + 32) k_threshold_pair(ThrArgs a) {
     const int nib_shift = 4 * (t & 3);
     uint32_t boff = 0;
 
-    auto load_row = [&]() -> uint2 {
+    const int nrows = nout + 2 * R;  // ring steps this CTA consumes
+    const uint32_t s_stage = (uint32_t)__cvta_generic_to_shared(&stage[0][t]);
+    uint32_t soff = 0;
+    int issued = 0;
+    auto issue_row = [&](uint32_t off) {  // async copy of the next source row into stage slot `off`
+        if (issued < nrows) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_stage + off), "l"(pa) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_stage + off + 4u), "l"(pb) : "memory");
+            const size_t inc = ((unsigned)yraw < (unsigned)(a.H - 1)) ? a.grey_row : (size_t)0;
+            pa += inc;
+            pb += inc;
+            yraw++;
+        }
+        issued++;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto load_row = [&]() -> uint2 {  // oldest staged row; its slot is refilled with the row DEPTH steps ahead
         uint2 p;
-        p.x = __ldg(reinterpret_cast<const uint32_t*>(pa));
-        p.y = __ldg(reinterpret_cast<const uint32_t*>(pb));
-        const size_t inc = ((unsigned)yraw < (unsigned)(a.H - 1)) ? a.grey_row : (size_t)0;
-        pa += inc;
-        pb += inc;
-        yraw++;
+        asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(p.x), "=r"(p.y) : "r"(s_stage + soff) : "memory");
+        issue_row(soff);
+        soff = soff + STAGE_ROW == DEPTH * STAGE_ROW ? 0u : soff + STAGE_ROW;
         return p;
     };
+#pragma unroll
+    for (int d = 0; d < DEPTH; d++) issue_row(d * STAGE_ROW);
 
     uint32_t ring[K][4];
 #pragma unroll
     for (int j = 0; j < K; j++) ring[j][0] = ring[j][1] = ring[j][2] = ring[j][3] = 0u;
     uint32_t V0 = 0u, V1 = 0u, V2 = 0u, V3 = 0u;
-    uint2 p_next = load_row(), p_next2 = load_row();
     // one ring step: the packed row enters slot j, the row K steps older leaves the vertical sums
     auto accumulate = [&](uint32_t* slot) {
-        const uint2 p = p_next;
-        p_next = p_next2;
-        p_next2 = load_row();
+        const uint2 p = load_row();
         const uint32_t P0 = prmt_r(p.x, p.y, sel[0]) & M, P1 = prmt_r(p.x, p.y, sel[1]) & M, P2 = prmt_r(p.x, p.y, sel[2]) & M,
                        P3 = prmt_r(p.x, p.y, sel[3]) & M;
         V0 = V0 + P0 - slot[0];
@@ -152,6 +170,7 @@ __global__ void __launch_bounds__(TO + 32) k_threshold_pair(ThrArgs a) {
             boff = BUF_BYTES - boff;
         }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 // host-side dispatch: returns false when (K, idelta) is outside the 15-bit lane budget
