@@ -48,6 +48,13 @@ struct CandRec {
     int32_t nrot;
 };
 
+// per-candidate scratch of the identification stage (k_decode.cuh)
+struct CandAux {
+    double Mi[9];  // canonical -> image homography (inverse of getPerspectiveTransform)
+    int32_t ok;    // 0: degenerate quad
+    int32_t thr;   // Otsu threshold of the canonical image
+};
+
 // counters zeroed at the start of every batch
 struct Counters {
     unsigned long long n_starts;
@@ -95,6 +102,8 @@ struct Batch {
     CandRec* cands;  // [B][cap_c]
     int cap_c;
     uint8_t* canon;  // [B][cap_c][S*S]
+    CandAux* aux;    // [B][cap_c]
+    unsigned short* hist;  // [B][cap_c][256] histogram of the canonical image
     ab_marker* markers;  // [B][cap_c]
     Counters* cnt;
     unsigned int* n_quads;    // [B]

@@ -57,6 +57,8 @@ struct ab_context {
     QuadRec* d_quads = nullptr;
     CandRec* d_cands = nullptr;
     uint8_t* d_canon = nullptr;
+    CandAux* d_aux = nullptr;
+    unsigned short* d_hist = nullptr;
     ab_marker* d_markers = nullptr;
     uint8_t* d_counters = nullptr;  // Counters + 3*maxB uints
     size_t counters_bytes = 0;
@@ -122,6 +124,8 @@ static void free_buffers(ab_context* c) {
     F(c->d_quads);
     F(c->d_cands);
     F(c->d_canon);
+    F(c->d_aux);
+    F(c->d_hist);
     F(c->d_markers);
     F(c->d_counters);
     if (c->h_markers) cudaFreeHost(c->h_markers);
@@ -393,6 +397,8 @@ int ab_reserve(ab_context* ctx, int width, int height, int max_batch, int max_qu
     CK(cudaMalloc(&ctx->d_quads, B * capQ * sizeof(QuadRec)));
     CK(cudaMalloc(&ctx->d_cands, B * capC * sizeof(CandRec)));
     CK(cudaMalloc(&ctx->d_canon, B * capC * (size_t)ctx->S_alloc * ctx->S_alloc));
+    CK(cudaMalloc(&ctx->d_aux, B * capC * sizeof(CandAux)));
+    CK(cudaMalloc(&ctx->d_hist, B * capC * 256 * sizeof(unsigned short)));
     CK(cudaMalloc(&ctx->d_markers, B * capC * sizeof(ab_marker)));
     ctx->counters_bytes = MAX_SUB * sizeof(Counters) + 3 * B * sizeof(unsigned);
     CK(cudaMalloc(&ctx->d_counters, ctx->counters_bytes));
@@ -544,6 +550,8 @@ static int fill_batch(ab_context* ctx, Batch& b, const uint8_t* dgrey, size_t ro
     b.cands = ctx->d_cands;
     b.cap_c = ctx->capC;
     b.canon = ctx->d_canon;
+    b.aux = ctx->d_aux;
+    b.hist = ctx->d_hist;
     b.markers = ctx->d_markers;
     b.cnt = (Counters*)ctx->d_counters;
     b.n_quads = (unsigned*)(ctx->d_counters + MAX_SUB * sizeof(Counters));
@@ -595,6 +603,8 @@ static Batch sub_view(ab_context* ctx, const Batch& w, int f0, int nf, int s) {
     v.quads = w.quads + (size_t)f0 * w.cap_q;
     v.cands = w.cands + (size_t)f0 * w.cap_c;
     v.canon = w.canon + (size_t)f0 * w.cap_c * (size_t)(w.S * w.S);
+    v.aux = w.aux + (size_t)f0 * w.cap_c;
+    v.hist = w.hist + (size_t)f0 * w.cap_c * 256;
     v.markers = w.markers + (size_t)f0 * w.cap_c;
     v.cnt = w.cnt + s;
     v.n_quads = w.n_quads + f0;
@@ -638,10 +648,11 @@ static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
     if (timing) cudaEventRecord(ctx->ev[2], st);
     dim3 gcand(b.cap_c, n);
     dim3 gdec((b.cap_c + DECODE_WARPS - 1) / DECODE_WARPS, n);
-    const size_t dec_smem = DECODE_WARPS * decode_smem_per_warp(b.S);
-    if (dec_smem > 48 * 1024) cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
+    const size_t dec_smem = DECODE_WARPS * identify_smem_per_warp(b.S);
+    if (dec_smem > 48 * 1024) cudaFuncSetAttribute(k_identify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
+    k_homography<<<dim3((b.cap_c + 63) / 64, n), 64, 0, st>>>(b);
+    k_sample<<<gdec, 32 * DECODE_WARPS, 0, st>>>(b);
     if (P.decoder == AB_DECODER_HOST_CALLBACK) {
-        k_decode<<<gdec, 32 * DECODE_WARPS, dec_smem, st>>>(b, 1);
         CK(cudaGetLastError());
         // MarkerdetectorFunc plugin hook (markerdetector.h:78,243): canonical images go to the host, the
         // user function runs per candidate in the reference's order, ids/rotations come back.
@@ -666,7 +677,8 @@ static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
         CK(cudaStreamSynchronize(st));
         cudaFree(d_idrot);
     } else {
-        k_decode<<<gdec, 32 * DECODE_WARPS, dec_smem, st>>>(b, 0);
+        k_otsu<<<dim3((b.cap_c + 31) / 32, n), 32, 0, st>>>(b);
+        k_identify<<<gdec, 32 * DECODE_WARPS, dec_smem, st>>>(b);
         CK(cudaGetLastError());
     }
     if (timing) cudaEventRecord(ctx->kev[6], st);

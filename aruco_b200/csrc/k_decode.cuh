@@ -1,11 +1,11 @@
-// Stage 3: per-candidate identification (src/markerdetector.cpp:350-356).
-// One WARP per candidate (4 candidates per CTA): getPerspectiveTransform + warpPerspective(INTER_NEAREST) into
-// shared memory (MarkerDetector::warp, :684-697), 256-bin histogram -> Otsu (cv::threshold BINARY|OTSU),
-// majority vote per cell, then FiducidalMarkers::detect (src/arucofidmarkers.cpp:438-452) or
-// HighlyReliableMarkers::detect (src/highlyreliablemarkers.cpp:332-383).  The serial f64 pieces (8x8 LU, the
-// Otsu recurrence -- both must follow OpenCV's operation order to stay bit-exact) run on lane 0; giving every
-// candidate its own warp keeps ~48 of those chains in flight per SM instead of 6 with a CTA per candidate.
-// The canonical image is also written out (getCandidates / host-callback decoders need it).
+// Stage 3: per-candidate identification (src/markerdetector.cpp:350-356), four kernels:
+//   k_homography (thread / candidate)  getPerspectiveTransform + inverse            (MarkerDetector::warp, :684-697)
+//   k_sample     (warp / candidate)    warpPerspective(INTER_NEAREST) -> canonical image + 256-bin histogram
+//   k_otsu       (thread / candidate)  cv::threshold(BINARY|OTSU) threshold search
+//   k_identify   (warp / candidate)    majority vote per cell, FiducidalMarkers::detect (src/arucofidmarkers.cpp:438-452)
+//                                      or HighlyReliableMarkers::detect (src/highlyreliablemarkers.cpp:332-383)
+// The serial f64 chains (8x8 LU, the Otsu recurrence -- both must follow OpenCV's operation order to stay bit-exact)
+// get a lane each instead of a warp each; the pixel-parallel parts get a warp per candidate.
 #pragma once
 #include "ab_device.cuh"
 
@@ -65,205 +65,208 @@ __device__ __forceinline__ int hrm_decode(const HrmDict& D, const uint8_t* cells
     return -1;
 }
 
-// cv::threshold(OTSU) threshold, same arithmetic per bin as otsu_threshold() in ab_math.cuh.  Only
-// the recurrence of (q1, mu1) is inherently sequential (its rounding sequence must be reproduced); it runs on
-// lane 0 in chunks of 32 bins, the other lanes then evaluate mu2 / sigma of "their" bin, and the first strict
-// maximum is found by a warp reduction.  Leading empty bins and the bins after q1 saturates are skipped: both
-// are exact no-ops of the sequential loop.  `scratch` = 64 doubles of shared memory.
-__device__ __forceinline__ int otsu_threshold_warp(const int* h, int N, double* scratch, int lane) {
-    const unsigned FULL = 0xFFFFFFFFu;
-    // mu = sum i*h[i] / N : integer valued partial sums are exact in f64, so the order is free
-    long long part = 0;
-    for (int i = lane; i < 256; i += 32) part += (long long)i * h[i];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(FULL, part, d);
-    const double scale = 1. / N;
-    const double mu = (double)part * scale;
-    double* s_q = scratch;
-    double* s_m = scratch + 32;
-    double mu1 = 0, q1 = 0;  // lane 0 only
-    bool done = false;
-    double best_sigma = 0;
-    int best_i = 0;
-    for (int c = 0; c < 8; c++) {
-        if (lane == 0) {
-            for (int k = 0; k < 32; k++) {
-                const int i = 32 * c + k;
-                double q = -1.0, m = 0;
-                if (!done) {
-                    const double p_i = h[i] * scale;
-                    mu1 *= q1;
-                    q1 += p_i;
-                    const double q2 = 1. - q1;
-                    const double mn = q1 < q2 ? q1 : q2, mx = q1 < q2 ? q2 : q1;
-                    if (mx > 1. - FLT_EPSILON && q1 > q2) {
-                        done = true;  // q1 only grows: every later bin is skipped by the same test
-                    } else if (!(mn < FLT_EPSILON || mx > 1. - FLT_EPSILON)) {
-                        mu1 = (mu1 + i * p_i) / q1;
-                        q = q1;
-                        m = mu1;
-                    }
-                }
-                s_q[k] = q;
-                s_m[k] = m;
-            }
-        }
-        __syncwarp();
-        const double q = s_q[lane], m = s_m[lane];
-        if (q >= 0) {
-            const double q2 = 1. - q;
-            const double mu2 = (mu - q * m) / q2;
-            const double sigma = q * q2 * (m - mu2) * (m - mu2);
-            if (sigma > best_sigma) {  // within a lane bins come in increasing order: first strict maximum
-                best_sigma = sigma;
-                best_i = 32 * c + lane;
-            }
-        }
-        __syncwarp();
-    }
-    // across lanes: larger sigma wins, ties go to the smaller bin index
-    unsigned long long sb = (unsigned long long)__double_as_longlong(best_sigma);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        unsigned long long os = __shfl_xor_sync(FULL, sb, d);
-        int oi = __shfl_xor_sync(FULL, best_i, d);
-        if (os > sb || (os == sb && oi < best_i)) {
-            sb = os;
-            best_i = oi;
-        }
-    }
-    return sb ? best_i : 0;
+// ---------------------------------------------------------------------------------------------------
+// 1. k_homography: one THREAD per candidate.  getPerspectiveTransform's 8x8 LU and the 3x3 inverse are serial
+//    f64 chains that must follow OpenCV's operation order; one per lane keeps 32 of them busy per warp (ncu r1k:
+//    as a lane-0 prologue of the warp-per-candidate kernel they were 16 % of its stall samples).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_homography(Batch b) {
+    const int f = blockIdx.y, ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= (int)b.n_cands[f] || ci >= b.cap_c) return;
+    const int S = b.S;
+    const CandRec* cand = b.cands + (size_t)f * b.cap_c + ci;
+    CandAux* ax = b.aux + (size_t)f * b.cap_c + ci;
+    float src[8];
+    for (int i = 0; i < 8; i++) src[i] = cand->c[i];
+    const float dst[8] = {0.f, 0.f, (float)(S - 1), 0.f, (float)(S - 1), (float)(S - 1), 0.f, (float)(S - 1)};
+    double M[9], Mi[9];
+    const bool ok = perspective_transform(src, dst, M) && invert3(M, Mi);
+    for (int i = 0; i < 9; i++) ax->Mi[i] = ok ? Mi[i] : 0.0;
+    ax->ok = ok;
+    ax->thr = 0;
 }
 
-inline size_t decode_smem_per_warp(int S) {
-    return (((size_t)S * S + 15) & ~(size_t)15) + 256 * sizeof(int) + MAX_CELLS * sizeof(int) + 112 + 9 * sizeof(double) + 8 +
-           DECODE_LIST * sizeof(unsigned short);
-}
-
-// mode 0: warp + decode; mode 1: warp only (host-callback decoder).  grid = (ceil(cap_c / DECODE_WARPS), B)
-__global__ void __launch_bounds__(32 * DECODE_WARPS) k_decode(Batch b, int mode) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
+// ---------------------------------------------------------------------------------------------------
+// 2. k_sample: one WARP per candidate: warpPerspective(INTER_NEAREST) into the canonical image (global; getCandidates,
+//    host-callback decoders and k_identify read it) and its 256-bin histogram.
+//    Filtered arithmetic: OpenCV's source coordinate is rint() of an f64 expression.  An f32 evaluation (error
+//    << 0.05 px for |coord| < 32768) decides every pixel whose coordinate is not within its error bound of a rounding
+//    boundary -- the integer it rounds to is then provably the same; the rest (~10 %) is collected by ballot
+//    compaction and redone densely with the exact f64 sequence.  A lane owns 4 adjacent destination pixels per
+//    step: their 4 gathers are in flight together (r1k: 23 % of the stall samples sat on the single gather) and
+//    the canonical image is written as 32-bit words.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * DECODE_WARPS) k_sample(Batch b) {
+    __shared__ int s_hist_all[DECODE_WARPS][256];
+    __shared__ unsigned short s_list_all[DECODE_WARPS][DECODE_LIST];
     const int f = blockIdx.y, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int ci = blockIdx.x * DECODE_WARPS + wib;
     if (ci >= (int)b.n_cands[f] || ci >= b.cap_c) return;  // whole warp leaves; only warp-level sync below
-    const int S = b.S;
-    const size_t img_bytes = ((size_t)S * S + 15) & ~(size_t)15;
-    const size_t per_warp = img_bytes + 256 * sizeof(int) + MAX_CELLS * sizeof(int) + 112 + 9 * sizeof(double) + 8 + DECODE_LIST * sizeof(unsigned short);
-    unsigned char* base = s_raw + (size_t)wib * per_warp;
-    uint8_t* s_img = base;
-    int* s_hist = reinterpret_cast<int*>(base + img_bytes);
-    int* s_cnt = s_hist + 256;
-    uint8_t* s_cells = reinterpret_cast<uint8_t*>(s_cnt + MAX_CELLS);
-    double* s_Mi = reinterpret_cast<double*>(base + img_bytes + 256 * sizeof(int) + MAX_CELLS * sizeof(int) + 112);
-    unsigned short* s_list = reinterpret_cast<unsigned short*>(s_Mi + 10);
-    CandRec* cand = b.cands + (size_t)f * b.cap_c + ci;
-    int ok_i = 0;
-    if (lane == 0) {
-        float dst[8] = {0.f, 0.f, (float)(S - 1), 0.f, (float)(S - 1), (float)(S - 1), 0.f, (float)(S - 1)};
-        double M[9], Mi[9];
-        bool ok = perspective_transform(cand->c, dst, M) && invert3(M, Mi);
-        ok_i = ok;
-        if (ok)
-            for (int i = 0; i < 9; i++) s_Mi[i] = Mi[i];
-    }
-    for (int i = lane; i < 256; i += 32) s_hist[i] = 0;
-    for (int i = lane; i < MAX_CELLS; i += 32) s_cnt[i] = 0;
-    ok_i = __shfl_sync(0xFFFFFFFFu, ok_i, 0);
-    __syncwarp();
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int S = b.S, SS = S * S;
+    int* s_hist = s_hist_all[wib];
+    unsigned short* s_list = s_list_all[wib];
+    const size_t slot = (size_t)f * b.cap_c + ci;
+    const CandAux* ax = b.aux + slot;
     const uint8_t* grey = b.grey + (size_t)f * b.grey_frame;
-    uint8_t* canon = b.canon + ((size_t)f * b.cap_c + ci) * (size_t)(S * S);
+    uint8_t* canon = b.canon + slot * (size_t)SS;
     const int bw = warp_block_width(S);
-    const bool ok = ok_i != 0;
-    // Filtered arithmetic: OpenCV's source coordinate is rint() of an f64 expression.  An f32 evaluation
-    // (error << 0.05 px for |coord| < 32768) decides every pixel whose coordinate is not within 0.05 px of a
-    // rounding boundary -- the integer it rounds to is then provably the same; the remaining ~10 % are
-    // collected (ballot compaction) and redone densely with the exact f64 sequence.  FP64 issue rate, not
-    // memory, was the limiter of this kernel (ncu r1d).
-    float Mf[9];
+    const bool ok = ax->ok != 0;
+    for (int i = lane; i < 256; i += 32) s_hist[i] = 0;
+    __syncwarp();
+    if (!ok) {  // degenerate quad: the reference warps nothing useful either; an all-zero image decodes to "no marker"
+        for (int i = lane; i < SS; i += 32) canon[i] = 0;
+        if (lane == 0) s_hist[0] = SS;
+    } else {
+        float Mf[9];
 #pragma unroll
-    for (int q = 0; q < 9; q++) Mf[q] = ok ? (float)s_Mi[q] : 0.f;
-    int nunc = 0;
-    int px = lane % S, py = lane / S;  // pixel (x,y) of index i = i0 + lane, advanced incrementally
-    for (int i0 = 0; i0 < S * S; i0 += 32) {
-        const int i = i0 + lane;
-        bool unc = false;
-        const int x = px, y = py;
-        px += 32;
-        while (px >= S) {
-            px -= S;
-            py++;
-        }
-        if (i < S * S) {
-            if (!ok) {
-                s_img[i] = 0;
-                canon[i] = 0;
+        for (int q = 0; q < 9; q++) Mf[q] = (float)ax->Mi[q];
+        const float aM0 = fabsf(Mf[0]), aM1 = fabsf(Mf[1]), aM2 = fabsf(Mf[2]), aM3 = fabsf(Mf[3]), aM4 = fabsf(Mf[4]), aM5 = fabsf(Mf[5]);
+        const float invS = 1.0f / (float)S;
+        const bool words = (SS & 3) == 0;
+        int nunc = 0;
+        for (int i0 = 0; i0 < SS; i0 += 128) {
+            uint32_t v[4];
+            bool unc[4], act[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + 4 * lane + u;
+                act[u] = i < SS;
+                unc[u] = false;
+                v[u] = 0;
+                if (act[u]) {
+                    const int y = (int)(((float)i + 0.5f) * invS), x = i - y * S;  // exact: the fraction is >= 0.5/S away from an integer
+                    const float fxp = (float)x, fyp = (float)y;
+                    const float den = __fmaf_rn(Mf[6], fxp, __fmaf_rn(Mf[7], fyp, Mf[8]));
+                    const float iden = __frcp_rn(den);
+                    const float fx = __fmaf_rn(Mf[0], fxp, __fmaf_rn(Mf[1], fyp, Mf[2])) * iden;
+                    const float fy = __fmaf_rn(Mf[3], fxp, __fmaf_rn(Mf[4], fyp, Mf[5])) * iden;
+                    const float rx = rintf(fx), ry = rintf(fy);
+                    // forward error bound of the f32 evaluation (unit roundoff 6e-8; 1e-6 leaves > 3x slack), doubled
+                    const float iad = fabsf(iden);
+                    const float ex = __fmaf_rn(2e-6f, __fmaf_rn(__fmaf_rn(aM0, fxp, __fmaf_rn(aM1, fyp, aM2)), iad, fabsf(fx)), 2e-4f);
+                    const float ey = __fmaf_rn(2e-6f, __fmaf_rn(__fmaf_rn(aM3, fxp, __fmaf_rn(aM4, fyp, aM5)), iad, fabsf(fy)), 2e-4f);
+                    unc[u] = !(fabsf(fx) < 32768.f && fabsf(fy) < 32768.f) || !(0.5f - fabsf(fx - rx) > ex) || !(0.5f - fabsf(fy - ry) > ey);
+                    if (!unc[u]) {
+                        const int sx = (int)rx, sy = (int)ry;
+                        if (sx >= 0 && sy >= 0 && sx < b.W && sy < b.H) v[u] = grey[(size_t)sy * b.grey_row + sx];
+                    }
+                }
+            }
+            if (words) {
+                if (act[0]) *reinterpret_cast<uint32_t*>(canon + i0 + 4 * lane) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
             } else {
-                const float fxp = (float)x, fyp = (float)y;
-                const float den = Mf[6] * fxp + Mf[7] * fyp + Mf[8];
-                const float iden = __frcp_rn(den);
-                const float fx = (Mf[0] * fxp + Mf[1] * fyp + Mf[2]) * iden, fy = (Mf[3] * fxp + Mf[4] * fyp + Mf[5]) * iden;
-                const float rx = rintf(fx), ry = rintf(fy);
-                // forward error bound of the f32 evaluation (unit roundoff 6e-8; 1e-6 leaves > 3x slack), doubled
-                const float iad = fabsf(iden);
-                const float ex = 2e-6f * ((fabsf(Mf[0] * fxp) + fabsf(Mf[1] * fyp) + fabsf(Mf[2])) * iad + fabsf(fx)) + 2e-4f;
-                const float ey = 2e-6f * ((fabsf(Mf[3] * fxp) + fabsf(Mf[4] * fyp) + fabsf(Mf[5])) * iad + fabsf(fy)) + 2e-4f;
-                unc = !(fabsf(fx) < 32768.f && fabsf(fy) < 32768.f) || !(0.5f - fabsf(fx - rx) > ex) || !(0.5f - fabsf(fy - ry) > ey);
-                if (!unc) {
-                    const int sx = (int)rx, sy = (int)ry;
-                    uint8_t v = 0;
-                    if (sx >= 0 && sy >= 0 && sx < b.W && sy < b.H) v = grey[(size_t)sy * b.grey_row + sx];
-                    s_img[i] = v;
-                    canon[i] = v;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (act[u] && !unc[u]) canon[i0 + 4 * lane + u] = (uint8_t)v[u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                // histogram: lanes holding the same grey level are matched, one of them adds the group size
+                // (shared-memory atomics on a bimodal image serialise almost completely: 18 % of the stall samples in r1e)
+                const bool cnt = act[u] && !unc[u];
+                const unsigned key = cnt ? v[u] : 0x100u + (unsigned)lane;
+                const unsigned peers = __match_any_sync(FULL, key);
+                if (cnt && lane == __ffs((int)peers) - 1) s_hist[key] += __popc(peers);
+                const unsigned m = __ballot_sync(FULL, unc[u]);
+                if (m) {
+                    const int pos = nunc + __popc(m & ((1u << lane) - 1u));
+                    if (unc[u]) {
+                        const int i = i0 + 4 * lane + u;
+                        if (pos < DECODE_LIST) {
+                            s_list[pos] = (unsigned short)i;
+                        } else {  // list full (cannot happen unless the map is degenerate): do it now
+                            const int y = i / S, x = i - y * S;
+                            int sx, sy;
+                            warp_src_coord(ax->Mi, x, y, bw, &sx, &sy);
+                            uint8_t vv = 0;
+                            if (sx >= 0 && sy >= 0 && sx < b.W && sy < b.H) vv = grey[(size_t)sy * b.grey_row + sx];
+                            canon[i] = vv;
+                            atomicAdd(&s_hist[vv], 1);
+                        }
+                    }
+                    nunc += __popc(m);
                 }
             }
         }
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, unc);
-        if (m) {
-            const int pos = nunc + __popc(m & ((1u << lane) - 1u));
-            if (unc) {
-                if (pos < DECODE_LIST) {
-                    s_list[pos] = (unsigned short)i;
-                } else {  // list full (cannot happen for guard 0.05 unless the map is degenerate): do it now
-                    const int y = i / S, x = i - y * S;
-                    int sx, sy;
-                    warp_src_coord(s_Mi, x, y, bw, &sx, &sy);
-                    uint8_t v = 0;
-                    if (sx >= 0 && sy >= 0 && sx < b.W && sy < b.H) v = grey[(size_t)sy * b.grey_row + sx];
-                    s_img[i] = v;
-                    canon[i] = v;
-                }
-            }
-            nunc += __popc(m);
+        __syncwarp();
+        const int n2 = min(nunc, DECODE_LIST);
+        for (int k = lane; k < n2; k += 32) {
+            const int i = (int)s_list[k];
+            const int y = i / S, x = i - y * S;
+            int sx, sy;
+            warp_src_coord(ax->Mi, x, y, bw, &sx, &sy);
+            uint8_t vv = 0;
+            if (sx >= 0 && sy >= 0 && sx < b.W && sy < b.H) vv = grey[(size_t)sy * b.grey_row + sx];
+            canon[i] = vv;
+            atomicAdd(&s_hist[vv], 1);
         }
     }
     __syncwarp();
-    const int n2 = min(nunc, DECODE_LIST);
-    for (int k = lane; k < n2; k += 32) {
-        const int i = (int)s_list[k];
-        const int y = i / S, x = i - y * S;
-        int sx, sy;
-        warp_src_coord(s_Mi, x, y, bw, &sx, &sy);
-        uint8_t v = 0;
-        if (sx >= 0 && sy >= 0 && sx < b.W && sy < b.H) v = grey[(size_t)sy * b.grey_row + sx];
-        s_img[i] = v;
-        canon[i] = v;
+    // histogram -> global as 256 x u16 (S <= 128: counts < 65536 unless the image is constant, which saturates harmlessly
+    // below: a constant image has one bin = S*S <= 16384)
+    uint32_t w4[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) w4[q] = (uint32_t)s_hist[8 * lane + 2 * q] | ((uint32_t)s_hist[8 * lane + 2 * q + 1] << 16);
+    reinterpret_cast<uint4*>(b.hist + slot * 256)[lane] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 3. k_otsu: one THREAD per candidate runs cv::threshold(BINARY|OTSU)'s sequential search (otsu_threshold, ab_math.cuh)
+//    on its histogram.  The (q1, mu1) recurrence -- an f64 division per bin whose rounding sequence must be
+//    reproduced -- was 40 % of the instructions of the warp-per-candidate kernel at 1/32 lane use (ncu r1k).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_otsu(Batch b) {
+    __shared__ int s_h[32 * 257];  // row stride 257: lane c walks bank (c + i) % 32
+    const int f = blockIdx.y, lane = threadIdx.x, c0 = blockIdx.x * 32;
+    const int nc = min((int)b.n_cands[f], b.cap_c);
+    if (c0 >= nc) return;
+    const int rows = min(32, nc - c0);
+    for (int r = 0; r < rows; r++) {
+        const uint4 u = reinterpret_cast<const uint4*>(b.hist + ((size_t)f * b.cap_c + c0 + r) * 256)[lane];
+        int* d = s_h + r * 257 + 8 * lane;
+        d[0] = (int)(u.x & 0xFFFFu);
+        d[1] = (int)(u.x >> 16);
+        d[2] = (int)(u.y & 0xFFFFu);
+        d[3] = (int)(u.y >> 16);
+        d[4] = (int)(u.z & 0xFFFFu);
+        d[5] = (int)(u.z >> 16);
+        d[6] = (int)(u.w & 0xFFFFu);
+        d[7] = (int)(u.w >> 16);
     }
     __syncwarp();
-    if (mode == 1) return;
-    // 256-bin histogram: lanes holding the same grey level are matched, one of them adds the group size
-    // (shared-memory atomics on a bimodal image serialise almost completely: 18 % of the stall samples in r1e)
-    for (int i0 = 0; i0 < S * S; i0 += 32) {
-        const int i = i0 + lane;
-        const unsigned v = i < S * S ? (unsigned)s_img[i] : 0x100u + (unsigned)lane;
-        const unsigned peers = __match_any_sync(0xFFFFFFFFu, v);
-        if (i < S * S && lane == __ffs((int)peers) - 1) s_hist[v] += __popc(peers);
+    if (lane < rows) b.aux[(size_t)f * b.cap_c + c0 + lane].thr = otsu_threshold(s_h + lane * 257, b.S * b.S);
+}
+
+inline size_t identify_smem_per_warp(int S) { return (((size_t)S * S + 15) & ~(size_t)15) + 112; }
+
+// ---------------------------------------------------------------------------------------------------
+// 4. k_identify: one WARP per candidate: majority vote per cell of the Otsu-binarised canonical image, then
+//    FiducidalMarkers::detect (src/arucofidmarkers.cpp:438-452) or HighlyReliableMarkers::detect
+//    (src/highlyreliablemarkers.cpp:332-383).  grid = (ceil(cap_c / DECODE_WARPS), B)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * DECODE_WARPS) k_identify(Batch b) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int f = blockIdx.y, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int ci = blockIdx.x * DECODE_WARPS + wib;
+    if (ci >= (int)b.n_cands[f] || ci >= b.cap_c) return;
+    const int S = b.S, SS = S * S;
+    const size_t img_bytes = ((size_t)SS + 15) & ~(size_t)15;
+    unsigned char* base = s_raw + (size_t)wib * (img_bytes + 112);
+    uint8_t* s_img = base;
+    uint8_t* s_cells = base + img_bytes;
+    const size_t slot = (size_t)f * b.cap_c + ci;
+    CandRec* cand = b.cands + slot;
+    const uint8_t* canon = b.canon + slot * (size_t)SS;
+    const int thr = b.aux[slot].thr;
+    if ((SS & 3) == 0) {
+        for (int i = lane; i < SS / 4; i += 32) reinterpret_cast<uint32_t*>(s_img)[i] = reinterpret_cast<const uint32_t*>(canon)[i];
+    } else {
+        for (int i = lane; i < SS; i += 32) s_img[i] = canon[i];
     }
     __syncwarp();
-    const int thr = otsu_threshold_warp(s_hist, S * S, reinterpret_cast<double*>(s_list), lane);
     const int ncell = (b.decoder == AB_DECODER_HRM) ? b.dict.n + 2 : 7;
     const int cell = S / ncell;
-    const int span = cell * ncell;
-    (void)span;
     for (int cidx = lane; cidx < ncell * ncell; cidx += 32) {  // one lane per cell: no atomics
         const int cy = cidx / ncell, cx = cidx - cy * ncell;
         int cnt = 0;
