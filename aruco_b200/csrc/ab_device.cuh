@@ -17,6 +17,8 @@ enum : unsigned {
 constexpr int MAX_QUADS = 1024;  // hard upper bound of quads per frame handled by the per-frame filter
 constexpr int MAX_CANDS = 1024;   // hard upper bound of candidates per frame
 
+// frame: bit 31 = border type (outer/hole), bit 30 = long contour (points written by k_emit_long, not k_emit)
+constexpr uint32_t CONTOUR_LONG = 0x40000000u, CONTOUR_FRAME_MASK = 0x3FFFFFFFu;
 struct ContourRec {
     uint32_t frame;
     uint32_t off;  // first point in the pool
@@ -31,6 +33,17 @@ struct LongRec {
     uint32_t sxy, fxy, bxy;  // start / forward walker / backward walker pixel (x | y << 16)
     uint32_t dirs;           // fw.b | bw.b << 4 | start.b << 8
     uint32_t nf, ng;
+};
+
+// a long contour closed by k_trace<true>: the walkers' checkpoints cut it into 6 segments with known end states, so
+// k_emit_long writes it with 12 walkers instead of 2 (states S0..S5 at indices 0, a[0..4]; S6 = S0 at index n)
+struct EmitRec {
+    uint32_t frame;   // bit 31 = border type
+    uint32_t off, n;  // slice of the point pool
+    uint32_t a[5];    // segment boundaries: p/2, p, nf, n-q, n-q/2
+    uint32_t xy[6];   // pixels of S0..S5 (x | y << 16)
+    uint32_t dirs;    // back-directions of S0..S5, 3 bits each
+    uint32_t pad;
 };
 
 struct QuadRec {
@@ -64,7 +77,8 @@ struct Counters {
     unsigned int err;
     unsigned int emit_work;
     unsigned int n_long, long_work;
-    unsigned int canny_changed, pad2;
+    unsigned int canny_changed, n_emit_long;
+    unsigned int emit_long_work, pad3;
     unsigned long long n_quads_total, n_cands_total, n_markers_total;
 };
 
@@ -97,6 +111,7 @@ struct Batch {
     unsigned long long cap_pool;
     LongRec* longq;
     unsigned int cap_long;
+    EmitRec* emitq;  // long contours (at most one per parked walk: capacity cap_long)
     QuadRec* quads;  // [B][cap_q]
     int cap_q;
     CandRec* cands;  // [B][cap_c]

@@ -53,6 +53,7 @@ struct ab_context {
     ContourRec* d_contours = nullptr;
     uint32_t* d_pool = nullptr;
     LongRec* d_longq = nullptr;
+    EmitRec* d_emitq = nullptr;
     unsigned capLongPF = 8192;
     QuadRec* d_quads = nullptr;
     CandRec* d_cands = nullptr;
@@ -121,6 +122,7 @@ static void free_buffers(ab_context* c) {
     F(c->d_contours);
     F(c->d_pool);
     F(c->d_longq);
+    F(c->d_emitq);
     F(c->d_quads);
     F(c->d_cands);
     F(c->d_canon);
@@ -394,6 +396,7 @@ int ab_reserve(ab_context* ctx, int width, int height, int max_batch, int max_qu
     CK(cudaMalloc(&ctx->d_contours, B * ctx->capContoursPF * sizeof(ContourRec)));
     CK(cudaMalloc(&ctx->d_pool, B * capP * 4));
     CK(cudaMalloc(&ctx->d_longq, B * ctx->capLongPF * sizeof(LongRec)));
+    CK(cudaMalloc(&ctx->d_emitq, B * ctx->capLongPF * sizeof(EmitRec)));
     CK(cudaMalloc(&ctx->d_quads, B * capQ * sizeof(QuadRec)));
     CK(cudaMalloc(&ctx->d_cands, B * capC * sizeof(CandRec)));
     CK(cudaMalloc(&ctx->d_canon, B * capC * (size_t)ctx->S_alloc * ctx->S_alloc));
@@ -543,6 +546,7 @@ static int fill_batch(ab_context* ctx, Batch& b, const uint8_t* dgrey, size_t ro
     b.cap_contours = ctx->capContoursPF * (unsigned)n;
     b.longq = ctx->d_longq;
     b.cap_long = ctx->capLongPF * (unsigned)n;
+    b.emitq = ctx->d_emitq;
     b.pool = ctx->d_pool;
     b.cap_pool = (unsigned long long)ctx->capPoolPF * n;
     b.quads = ctx->d_quads;
@@ -600,6 +604,7 @@ static Batch sub_view(ab_context* ctx, const Batch& w, int f0, int nf, int s) {
     v.cap_pool = (unsigned long long)ctx->capPoolPF * vt * nf;
     v.longq = w.longq + (size_t)ctx->capLongPF * vt * f0;
     v.cap_long = ctx->capLongPF * (unsigned)(vt * nf);
+    v.emitq = w.emitq + (size_t)ctx->capLongPF * vt * f0;
     v.quads = w.quads + (size_t)f0 * w.cap_q;
     v.cands = w.cands + (size_t)f0 * w.cap_c;
     v.canon = w.canon + (size_t)f0 * w.cap_c * (size_t)(w.S * w.S);
@@ -638,6 +643,7 @@ static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
     if (timing) cudaEventRecord(ctx->kev[2], st);
     k_trace<false><<<sms * 8, 128, 0, st>>>(bv);
     k_trace<true><<<sms * 4, 128, 0, st>>>(bv);
+    k_emit_long<<<sms * 8, 128, 0, st>>>(bv);
     k_emit<<<sms * 8, 128, 0, st>>>(bv);
     if (timing) cudaEventRecord(ctx->kev[3], st);
     k_polygon<<<sms * 8, 128, 0, st>>>(bv);
@@ -1075,6 +1081,7 @@ int ab_detect_rectangles(ab_context* ctx, const uint8_t* thres, int width, int h
     k_scan_starts<<<ctx->sm_count * 8, 256, 0, st>>>(b);
     k_trace<false><<<ctx->sm_count * 8, 128, 0, st>>>(b);
     k_trace<true><<<ctx->sm_count * 4, 128, 0, st>>>(b);
+    k_emit_long<<<ctx->sm_count * 8, 128, 0, st>>>(b);
     k_emit<<<ctx->sm_count * 8, 128, 0, st>>>(b);
     k_polygon<<<ctx->sm_count * 4, 128, 0, st>>>(b);
     k_frame_filter<<<1, 256, 0, st>>>(b);

@@ -107,6 +107,10 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
     WalkState fw{0, 0, 0}, bw{0, 0, 0};
     uint32_t nb_fw = 0, type_bit = 0;
     int nf = 0, ng = 0, frame = 0;
+    // LONG only: walker states at the last two power-of-two step counts (pixels, back-directions, step count);
+    // they cut the finished contour into segments that k_emit_long writes in parallel
+    uint32_t cpF1 = 0, cpF2 = 0, cpB1 = 0, cpB2 = 0, cpd = 0;
+    int pF = 0, qB = 0;
     for (;;) {
         unsigned idle = __ballot_sync(FULL, !active && !exhausted);
         if (idle) {
@@ -132,6 +136,8 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                     nf = (int)q.nf;
                     ng = (int)q.ng;
                     nb_fw = neighbours8(im, fw.x, fw.y);
+                    cpF1 = cpF2 = cpB1 = cpB2 = cpd = 0;
+                    pF = qB = 0;
                     active = true;
                 } else {
                     uint2 rec = b.starts[i];
@@ -165,6 +171,12 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                 WalkState bw1 = bw0;
                 const uint32_t nb_bw = walk_backward(im, bw1);
                 nf++;
+                if (LONG && (nf & (nf - 1)) == 0) {  // parked walks arrive with nf < 64: the first checkpoint is step 64
+                    cpF2 = cpF1;
+                    cpF1 = (uint32_t)fw.x | ((uint32_t)fw.y << 16);
+                    cpd = (cpd & ~0x3Fu) | ((cpd & 7u) << 3) | (uint32_t)fw.b;
+                    pF = nf;
+                }
                 if (same_state(fw, bw0)) {
                     closed = true;
                 } else if (is_smaller_trigger(im, fw, nb_fw, st.key)) {
@@ -172,6 +184,12 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                 } else {
                     bw = bw1;
                     ng++;
+                    if (LONG && (ng & (ng - 1)) == 0) {
+                        cpB2 = cpB1;
+                        cpB1 = (uint32_t)bw.x | ((uint32_t)bw.y << 16);
+                        cpd = (cpd & ~0xFC0u) | (((cpd >> 6) & 7u) << 9) | ((uint32_t)bw.b << 6);
+                        qB = ng;
+                    }
                     if (same_state(fw, bw)) closed = true;
                     else if (is_smaller_trigger(im, bw, nb_bw, st.key)) dead = true;
                     else if (nf + ng >= b.max_len) dead = true;  // too long: dropped by :517 anyway
@@ -186,8 +204,33 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                         } else if (off + (unsigned long long)len > b.cap_pool) {
                             atomicOr(&b.cnt->err, ERR_POOL_OVERFLOW);
                             b.contours[ci] = ContourRec{(uint32_t)frame | type_bit, 0u, 0u, (uint32_t)st.key};
-                        } else {
+                        } else if (!LONG) {
                             b.contours[ci] = ContourRec{(uint32_t)frame | type_bit, (uint32_t)off, (uint32_t)len, (uint32_t)st.key};
+                        } else {
+                            b.contours[ci] = ContourRec{(uint32_t)frame | type_bit | CONTOUR_LONG, (uint32_t)off, (uint32_t)len, (uint32_t)st.key};
+                            // boundaries 0 <= p/2 <= p <= nf <= n-q <= n-q/2 <= n; a missing checkpoint collapses its
+                            // segment onto the start state.  The second-last checkpoint exists iff the last one is >= 128.
+                            const uint32_t sxy = (uint32_t)st.x | ((uint32_t)st.y << 16), sb = (uint32_t)st.b;
+                            const bool f1 = pF > 0, f2 = pF >= 128, g1 = qB > 0, g2 = qB >= 128;
+                            EmitRec e;
+                            e.frame = (uint32_t)frame | type_bit;
+                            e.off = (uint32_t)off;
+                            e.n = (uint32_t)len;
+                            e.a[0] = f2 ? (uint32_t)(pF >> 1) : 0u;
+                            e.a[1] = f1 ? (uint32_t)pF : 0u;
+                            e.a[2] = (uint32_t)nf;
+                            e.a[3] = (uint32_t)(len - (g1 ? qB : 0));
+                            e.a[4] = (uint32_t)(len - (g2 ? (qB >> 1) : 0));
+                            e.xy[0] = sxy;
+                            e.xy[1] = f2 ? cpF2 : sxy;
+                            e.xy[2] = f1 ? cpF1 : sxy;
+                            e.xy[3] = (uint32_t)fw.x | ((uint32_t)fw.y << 16);
+                            e.xy[4] = g1 ? cpB1 : sxy;
+                            e.xy[5] = g2 ? cpB2 : sxy;
+                            e.dirs = sb | ((f2 ? ((cpd >> 3) & 7u) : sb) << 3) | ((f1 ? (cpd & 7u) : sb) << 6) | ((uint32_t)fw.b << 9) |
+                                     ((g1 ? ((cpd >> 6) & 7u) : sb) << 12) | ((g2 ? ((cpd >> 9) & 7u) : sb) << 15);
+                            e.pad = 0;
+                            b.emitq[atomicAdd(&b.cnt->n_emit_long, 1u)] = e;  // at most one per parked walk: fits cap_long
                         }
                     }
                     active = false;
@@ -253,8 +296,8 @@ __global__ void __launch_bounds__(128) k_emit(Batch b) {
                     // costs one dependent load round trip instead of two (forward lanes, then backward lanes)
                     const ContourRec rec = b.contours[i < ncont ? i : i - ncont];
                     const int n = (int)rec.n;
-                    if (n > 0) {
-                        im = b.bit_image((int)(rec.frame & 0x7FFFFFFFu));
+                    if (n > 0 && !(rec.frame & CONTOUR_LONG)) {  // long contours: k_emit_long
+                        im = b.bit_image((int)(rec.frame & CONTOUR_FRAME_MASK));
                         TraceStart st;
                         make_start(im, (int)(rec.frame >> 31), (int)(rec.key % (uint32_t)b.W), (int)(rec.key / (uint32_t)b.W), st);
                         w = WalkState{st.x, st.y, st.b};
@@ -270,6 +313,86 @@ __global__ void __launch_bounds__(128) k_emit(Batch b) {
                         }
                         active = remaining > 0;
                     }
+                }
+            }
+        }
+        if (__ballot_sync(FULL, active) == 0) {
+            if (__ballot_sync(FULL, !exhausted) == 0) break;
+            continue;
+        }
+        if (active) {
+            if (!backward) {
+                for (int r = 0; r < STEPS; r++) {
+                    *out++ = (uint32_t)w.x | ((uint32_t)w.y << 16);
+                    if (--remaining == 0) {
+                        active = false;
+                        break;
+                    }
+                    walk_forward(w, nb);
+                    nb = neighbours8(im, w.x, w.y);
+                }
+            } else {
+                for (int r = 0; r < STEPS; r++) {
+                    walk_backward(im, w);
+                    *out-- = (uint32_t)w.x | ((uint32_t)w.y << 16);
+                    if (--remaining == 0) {
+                        active = false;
+                        break;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Long contours: 12 work items per EmitRec -- every segment between two known walker states is filled from both
+// ends.  The longest dependent chain of the stage drops from n/2 to about n/8 neighbourhood loads (the walkers are
+// latency bound: one L2/DRAM round trip per step).  Items are ordered so that a warp holds one kind of walker.
+__global__ void __launch_bounds__(128) k_emit_long(Batch b) {
+    constexpr int STEPS = 16;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    unsigned int nrec = b.cnt->n_emit_long;
+    if (nrec > b.cap_long) nrec = b.cap_long;
+    const unsigned int n_items = 12u * nrec;
+    bool active = false, exhausted = false, backward = false;
+    BitImage im = b.bit_image(0);
+    WalkState w{0, 0, 0};
+    uint32_t nb = 0;
+    int remaining = 0;
+    uint32_t* out = nullptr;
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, !active && !exhausted);
+        if (idle) {
+            unsigned base = 0;
+            int leader = __ffs((int)idle) - 1;
+            if (lane == leader) base = atomicAdd(&b.cnt->emit_long_work, (unsigned)__popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (!active && !exhausted) {
+                unsigned i = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+                if (i >= n_items) {
+                    exhausted = true;
+                } else {
+                    backward = i >= 6u * nrec;
+                    const unsigned k = backward ? i - 6u * nrec : i;
+                    const unsigned seg = k / nrec;  // 0..5
+                    const EmitRec* e = b.emitq + (k - seg * nrec);
+                    const uint32_t n = e->n;
+                    const uint32_t a0 = seg == 0 ? 0u : e->a[seg - 1], a1 = seg == 5 ? n : e->a[seg];
+                    const int L = (int)(a1 - a0), h = (L + 1) >> 1;
+                    const unsigned s = backward ? (seg == 5 ? 0u : seg + 1u) : seg;  // state index (S6 = S0)
+                    const uint32_t xy = e->xy[s];
+                    im = b.bit_image((int)(e->frame & CONTOUR_FRAME_MASK));
+                    w = WalkState{(int)(xy & 0xFFFFu), (int)(xy >> 16), (int)((e->dirs >> (3 * s)) & 7u)};
+                    if (!backward) {
+                        out = b.pool + e->off + a0;  // positions a0 .. a0+h-1, ascending
+                        remaining = h;
+                        if (h > 0) nb = neighbours8(im, w.x, w.y);
+                    } else {
+                        out = b.pool + e->off + a1 - 1;  // positions a1-1 .. a0+h, descending
+                        remaining = L - h;
+                    }
+                    active = remaining > 0;
                 }
             }
         }

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(128) k_polygon(Batch b) {
     if (ncont > b.cap_contours) ncont = b.cap_contours;
     for (unsigned int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < ncont; ci += nwarps) {
         ContourRec rec = b.contours[ci];
-        rec.frame &= 0x7FFFFFFFu;  // bit 31 = border type (outer/hole), used by k_emit only
+        rec.frame &= CONTOUR_FRAME_MASK;  // bits 31/30 = border type / long contour, used by the emit kernels only
         const int n = (int)rec.n;
         if (n < 4) continue;
         const uint32_t* pts = b.pool + rec.off;

@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 W, H, N_MARKERS, BATCH, SIGMA = 3840, 2160, 100, 256, 2.0
 N_BASE = 8          # distinct rendered scenes; every frame of a batch gets its own noise realisation
 MARKER_SIZE = 0.05
-KERNELS_PER_BATCH = 13  # threshold, scan_starts, trace, trace_long, emit, polygon, frame_filter, homography, sample, otsu, identify, refine_lines, finalize
+KERNELS_PER_BATCH = 14  # threshold, scan_starts, trace, trace_long, emit_long, emit, polygon, frame_filter, homography, sample, otsu, identify, refine_lines, finalize
 
 
 def log(*a):
