@@ -48,9 +48,32 @@ AB_HD uint32_t row3(const uint32_t* row, int x) {
 #endif
 }
 
-// 8-neighbour mask of pixel (x,y): bit d set <=> neighbour in direction d is foreground
+// 8-neighbour mask of pixel (x,y): bit d set <=> neighbour in direction d is foreground.
+// The walkers are bound by L1 tag throughput (every lane reads its own cache line: one wavefront per lane and load
+// instruction), so the three rows are read with ONE word each; the second word is fetched only when the 3-pixel
+// window straddles a word boundary (2 of 32 positions).
 AB_HD uint32_t neighbours8(const BitImage& im, int x, int y) {
-    uint32_t t = row3(im.row(y - 1), x), m = row3(im.row(y), x), b = row3(im.row(y + 1), x);
+    const int p = x - 1 + 32 * BIT_PAD;  // pixel x lives at padded bit x + 32*BIT_PAD
+    const int sh = p & 31;
+    const uint32_t* r1 = im.row(y) + (p >> 5);
+    const uint32_t* r0 = r1 - im.wpr;
+    const uint32_t* r2 = r1 + im.wpr;
+    uint32_t t = r0[0], m = r1[0], b = r2[0];
+    uint32_t th = 0, mh = 0, bh = 0;
+    if (sh > 29) {
+        th = r0[1];
+        mh = r1[1];
+        bh = r2[1];
+    }
+#if defined(__CUDA_ARCH__)
+    t = __funnelshift_r(t, th, sh) & 7u;
+    m = __funnelshift_r(m, mh, sh) & 7u;
+    b = __funnelshift_r(b, bh, sh) & 7u;
+#else
+    t = (uint32_t)((((uint64_t)th << 32) | t) >> sh) & 7u;
+    m = (uint32_t)((((uint64_t)mh << 32) | m) >> sh) & 7u;
+    b = (uint32_t)((((uint64_t)bh << 32) | b) >> sh) & 7u;
+#endif
     return ((m >> 2) & 1u) | (((t >> 2) & 1u) << 1) | (((t >> 1) & 1u) << 2) | ((t & 1u) << 3) | ((m & 1u) << 4) |
            ((b & 1u) << 5) | (((b >> 1) & 1u) << 6) | (((b >> 2) & 1u) << 7);
 }
