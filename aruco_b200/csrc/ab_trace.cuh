@@ -24,46 +24,46 @@
 
 namespace ab {
 
-// Binary image packed 1 bit per pixel, LSB first, with one zero word left/right of every row and one zero
-// row above/below, so a 3x3 neighbourhood never needs a bounds test.
-struct BitImage {
-    const uint32_t* bits;  // points at the padded buffer
-    int wpr;               // words per padded row (bit_words_per_row)
-    int W, H;
-    AB_HD const uint32_t* row(int y) const { return bits + (size_t)(y + 1) * wpr; }
-};
-
-constexpr int BIT_PAD = 4;  // zero words left of every row (16 B: rows stay 128-bit aligned); >= 1 zero word on the right
-AB_HD int bit_words_per_row(int W) { return (((W + 31) >> 5) + BIT_PAD + 1 + 3) & ~3; }
-AB_HD size_t bit_image_words(int W, int H) { return (size_t)bit_words_per_row(W) * (H + 2); }
-
-// bits of pixels x-1, x, x+1 of one padded row (bit0 = x-1)
-AB_HD uint32_t row3(const uint32_t* row, int x) {
-    int p = x - 1 + 32 * BIT_PAD;  // pixel x lives at padded bit x + 32*BIT_PAD
-    uint32_t lo = row[p >> 5], hi = row[(p >> 5) + 1];
-#if defined(__CUDA_ARCH__)
-    return __funnelshift_r(lo, hi, p & 31) & 7u;
-#else
-    return (uint32_t)((((uint64_t)hi << 32) | lo) >> (p & 31)) & 7u;
-#endif
+// Binary image packed 1 bit per pixel, LSB first, stored in TILES: one 32-pixel word column x 32 rows = 32
+// consecutive words = 128 B = one L1 line.  With plain row-major rows a walker's 3x3 neighbourhood sat in three
+// lines; 1024 resident walkers per SM then need 3072 lines of an L1 that holds ~1800, and the hit rate of the
+// walker kernels was 17 % (ncu r1m) with L2 bandwidth as the bound.  Tiled, a neighbourhood is one line (two when
+// it straddles a tile edge) and stays there for ~32 steps.
+// One zero word column left and >= 1 right of every row, one zero row above and >= 1 below, so a 3x3 neighbourhood
+// never needs a bounds test.
+constexpr int BIT_PAD = 1;     // zero word columns left of the image
+constexpr int BIT_TILE = 32;   // rows (= words) per tile
+AB_HD int bit_words_per_row(int W) { return ((W + 31) >> 5) + BIT_PAD + 1; }  // word columns incl. padding
+AB_HD size_t bit_image_words(int W, int H) { return (size_t)bit_words_per_row(W) * BIT_TILE * (size_t)((H + 2 + BIT_TILE - 1) / BIT_TILE); }
+// index of the word in padded word column wc (image pixels 32*(wc-BIT_PAD) ..+31) of image row y (-1 <= y <= H)
+AB_HD size_t bit_word_index(int wpr, int wc, int y) {
+    const int yp = y + 1;
+    return ((size_t)(yp >> 5) * wpr + wc) * BIT_TILE + (yp & 31);
 }
 
+struct BitImage {
+    const uint32_t* bits;  // points at the padded buffer
+    int wpr;               // word columns per padded row (bit_words_per_row)
+    int W, H;
+    AB_HD const uint32_t* word(int wc, int y) const { return bits + bit_word_index(wpr, wc, y); }
+};
+
 // 8-neighbour mask of pixel (x,y): bit d set <=> neighbour in direction d is foreground.
-// The walkers are bound by L1 tag throughput (every lane reads its own cache line: one wavefront per lane and load
-// instruction), so the three rows are read with ONE word each; the second word is fetched only when the 3-pixel
-// window straddles a word boundary (2 of 32 positions).
+// The three rows are read with ONE word each; the word of the next column is fetched only when the 3-pixel window
+// straddles a word boundary (2 of 32 positions).
 AB_HD uint32_t neighbours8(const BitImage& im, int x, int y) {
     const int p = x - 1 + 32 * BIT_PAD;  // pixel x lives at padded bit x + 32*BIT_PAD
-    const int sh = p & 31;
-    const uint32_t* r1 = im.row(y) + (p >> 5);
-    const uint32_t* r0 = r1 - im.wpr;
-    const uint32_t* r2 = r1 + im.wpr;
+    const int sh = p & 31, yr = (y + 1) & 31;
+    const uint32_t* r1 = im.word(p >> 5, y);
+    const int jump = im.wpr * BIT_TILE - (BIT_TILE - 1);  // to the same column of the next tile row, minus 31
+    const uint32_t* r0 = r1 - (yr == 0 ? jump : 1);
+    const uint32_t* r2 = r1 + (yr == 31 ? jump : 1);
     uint32_t t = r0[0], m = r1[0], b = r2[0];
     uint32_t th = 0, mh = 0, bh = 0;
     if (sh > 29) {
-        th = r0[1];
-        mh = r1[1];
-        bh = r2[1];
+        th = r0[BIT_TILE];
+        mh = r1[BIT_TILE];
+        bh = r2[BIT_TILE];
     }
 #if defined(__CUDA_ARCH__)
     t = __funnelshift_r(t, th, sh) & 7u;

@@ -127,7 +127,7 @@ __global__ void k_canny_finish(uint8_t* thres, uint32_t* bits, size_t bits_words
             row[x] = on ? 255 : 0;
             if (on) word |= 1u << j;
         }
-        bits[fo * bits_words + (size_t)(y + 1) * wpr + BIT_PAD + w] = word;
+        bits[fo * bits_words + bit_word_index(wpr, BIT_PAD + w, y)] = word;
     }
 }
 

@@ -8,32 +8,46 @@
 
 namespace ab {
 
-// one thread per 128 pixels (four packed words, 128-bit loads); candidates are appended with one atomic per warp
+// one thread per word column x 4 rows of a bit tile (128-bit loads; a warp reads 4 whole tiles = 512 contiguous
+// bytes, plus the same rows of the west and east tiles); candidates are appended with one atomic per warp
 __global__ void __launch_bounds__(256) k_scan_starts(Batch b) {
     const int ww = (b.W + 31) >> 5;
-    const unsigned nq = (unsigned)(ww + 3) >> 2;  // quads per row
-    const unsigned long long total = (unsigned long long)nq * b.H * b.B;
+    const int trows = (b.H + 2 + BIT_TILE - 1) / BIT_TILE;
+    const unsigned long long total = (unsigned long long)ww * 8ull * trows * b.B;
     const int lane = threadIdx.x & 31;
     for (unsigned long long base = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; base < total;
          base += (unsigned long long)gridDim.x * blockDim.x) {
         unsigned long long i = base + lane;
         uint32_t outer[4] = {0, 0, 0, 0}, hole[4] = {0, 0, 0, 0};
-        int q = 0, y = 0, f = 0, cnt = 0;
+        int wcl = 0, y0 = 0, f = 0, cnt = 0;
         if (i < total) {
-            q = (int)(i % nq);
-            unsigned long long r = i / nq;
-            y = (int)(r % (unsigned)b.H);
-            f = (int)(r / (unsigned)b.H);
-            const uint32_t* row = b.bits + (size_t)f * b.bits_words + (size_t)(y + 1) * b.wpr + BIT_PAD + 4 * q;
-            const uint32_t* up = row - b.wpr;
-            const uint4 c4 = *reinterpret_cast<const uint4*>(row);
-            const uint4 u4 = *reinterpret_cast<const uint4*>(up);
-            const uint32_t c[6] = {row[-1], c4.x, c4.y, c4.z, c4.w, 0u};
-            const uint32_t u[6] = {up[-1], u4.x, u4.y, u4.z, u4.w, up[4]};
+            const int g = (int)(i & 7ull);
+            unsigned long long r = i >> 3;
+            wcl = (int)(r % (unsigned)ww);
+            r /= (unsigned)ww;
+            const int ty = (int)(r % (unsigned)trows);
+            f = (int)(r / (unsigned)trows);
+            y0 = ty * BIT_TILE + 4 * g - 1;  // image row of the first of the 4 rows (padded row - 1)
+            const uint32_t* tile = b.bits + (size_t)f * b.bits_words + ((size_t)ty * b.wpr + (wcl + BIT_PAD)) * BIT_TILE;
+            const uint4 c4 = *reinterpret_cast<const uint4*>(tile + 4 * g);
+            const uint4 w4 = *reinterpret_cast<const uint4*>(tile - BIT_TILE + 4 * g);
+            const uint4 e4 = *reinterpret_cast<const uint4*>(tile + BIT_TILE + 4 * g);
+            uint32_t cu = 0, wu = 0, eu = 0;  // the row above the first row
+            if (g > 0) {
+                cu = tile[4 * g - 1];
+                wu = tile[4 * g - 1 - BIT_TILE];
+                eu = tile[4 * g - 1 + BIT_TILE];
+            } else if (ty > 0) {
+                const uint32_t* up = tile - (size_t)b.wpr * BIT_TILE + (BIT_TILE - 1);
+                cu = up[0];
+                wu = up[-BIT_TILE];
+                eu = up[BIT_TILE];
+            }
+            const uint32_t c[5] = {cu, c4.x, c4.y, c4.z, c4.w}, w[5] = {wu, w4.x, w4.y, w4.z, w4.w}, e[5] = {eu, e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                uint32_t cur = c[k + 1], west = (cur << 1) | (c[k] >> 31);
-                uint32_t uu = u[k + 1], uw = (uu << 1) | (u[k] >> 31), ue = (uu >> 1) | (u[k + 2] << 31);
+                uint32_t cur = c[k + 1], west = (cur << 1) | (w[k + 1] >> 31);
+                uint32_t uu = c[k], uw = (uu << 1) | (w[k] >> 31), ue = (uu >> 1) | (e[k] << 31);
                 outer[k] = cur & ~west & ~uu & ~uw & ~ue;  // fg with W, N, NW, NE background
                 hole[k] = ~cur & west & uu;                // bg with W and N foreground
                 cnt += __popc(outer[k]) + __popc(hole[k]);
@@ -58,17 +72,17 @@ __global__ void __launch_bounds__(256) k_scan_starts(Batch b) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             uint32_t m = outer[k];
-            const uint32_t xb = (uint32_t)(128 * q + 32 * k);
+            const uint32_t xb = (uint32_t)(32 * wcl), y = (uint32_t)(y0 + k);
             while (m) {
                 int j = __ffs((int)m) - 1;
                 m &= m - 1;
-                b.starts[o++] = make_uint2((uint32_t)f, (xb + j) | ((uint32_t)y << 16));
+                b.starts[o++] = make_uint2((uint32_t)f, (xb + j) | (y << 16));
             }
             m = hole[k];
             while (m) {
                 int j = __ffs((int)m) - 1;
                 m &= m - 1;
-                b.starts[o++] = make_uint2((uint32_t)f | 0x80000000u, (xb + j) | ((uint32_t)y << 16));
+                b.starts[o++] = make_uint2((uint32_t)f | 0x80000000u, (xb + j) | (y << 16));
             }
         }
     }

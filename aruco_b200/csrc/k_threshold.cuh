@@ -102,7 +102,7 @@ __global__ void k_threshold_adaptive(ThrArgs a) {
                 uint32_t word = 0;
 #pragma unroll
                 for (int q = 0; q < 8; q++) word |= (uint32_t)nb[q] << (4 * q);
-                bits[(size_t)(yo + 1) * a.wpr + BIT_PAD + (X0 >> 5) + t] = word;
+                bits[bit_word_index(a.wpr, BIT_PAD + (X0 >> 5) + t, yo)] = word;
             }
             if (++cslot == k) cslot = 0;
         } else if (i >= r) {
@@ -135,7 +135,7 @@ __global__ void k_threshold_fixed(const uint8_t* grey, size_t grey_row, size_t g
             if (mode == 0) orow[x] = on ? 255 : 0;
             else if (orow + x != rowp + x) orow[x] = v;
         }
-        bits[fo * bits_words + (size_t)(y + 1) * wpr + BIT_PAD + w] = word;
+        bits[fo * bits_words + bit_word_index(wpr, BIT_PAD + w, y)] = word;
     }
 }
 
@@ -157,10 +157,10 @@ __global__ void k_erode(const uint32_t* in, uint32_t* out, uint8_t* thres, size_
             if (yy < 0 || yy >= H) {
                 cur = prv = nxt = 0xFFFFFFFFu;
             } else {
-                const uint32_t* row = base + (size_t)(yy + 1) * wpr + BIT_PAD + w;
-                cur = row[0] | ~vmask;                   // pixels beyond W count as 255
-                prv = (w == 0) ? 0xFFFFFFFFu : row[-1];  // pixels left of 0 count as 255
-                nxt = (w == ww - 1) ? 0xFFFFFFFFu : row[1];
+                const uint32_t* row = base + bit_word_index(wpr, BIT_PAD + w, yy);
+                cur = row[0] | ~vmask;                          // pixels beyond W count as 255
+                prv = (w == 0) ? 0xFFFFFFFFu : row[-BIT_TILE];  // pixels left of 0 count as 255
+                nxt = (w == ww - 1) ? 0xFFFFFFFFu : row[BIT_TILE];
                 if (w == ww - 2) {
                     int nv2 = W - 32 * (w + 1);
                     if (nv2 < 32) nxt |= ~((1u << nv2) - 1u);
@@ -170,7 +170,7 @@ __global__ void k_erode(const uint32_t* in, uint32_t* out, uint8_t* thres, size_
             acc &= cur & l & rr;
         }
         acc &= vmask;
-        out[(size_t)f * bits_words + (size_t)(y + 1) * wpr + BIT_PAD + w] = acc;
+        out[(size_t)f * bits_words + bit_word_index(wpr, BIT_PAD + w, y)] = acc;
         uint8_t* orow = thres + ((size_t)f * H + y) * W + 32 * w;
         for (int j = 0; j < nvalid; j++) orow[j] = (acc >> j) & 1u ? 255 : 0;
     }

@@ -62,7 +62,9 @@ __global__ void __launch_bounds__(160) k_threshold_fast(ThrArgs a) {
     const uint32_t vmask = c0 >= a.W ? 0u : (c0 + 3 < a.W ? 15u : ((1u << (a.W - c0)) - 1u));
     const size_t fo = (size_t)f * a.out_mul + a.out_off;
     uint8_t* orow = a.thres + fo * a.W * a.H + (size_t)y0 * a.W + c0;
-    uint32_t* brow = a.bits + fo * a.bits_words + (size_t)(y0 + 1) * a.wpr + BIT_PAD + (X0 >> 5) + (t >> 3);
+    uint32_t* brow = a.bits + fo * a.bits_words + bit_word_index(a.wpr, BIT_PAD + (X0 >> 5) + (t >> 3), y0);
+    int btr = (y0 + 1) & 31;  // row inside the bit tile
+    const int bjump = a.wpr * BIT_TILE - (BIT_TILE - 1);
     const int cst = K2 * a.idelta - (K2 - 1) / 2;  // S >= K2*src + cst  <=>  src - mean <= -idelta
     const uint32_t M = 0x00FF00FFu;
     uint32_t ring[K];
@@ -144,7 +146,8 @@ __global__ void __launch_bounds__(160) k_threshold_fast(ThrArgs a) {
                         word |= __shfl_xor_sync(0xFFFFFFFFu, word, 4);
                         if ((t & 7) == 0 && vmask) *brow = word;
                         orow += a.W;
-                        brow += a.wpr;
+                        brow += btr == 31 ? bjump : 1;
+                        btr = (btr + 1) & 31;
                     }
                     buf ^= 1;
                 }

@@ -84,7 +84,9 @@ __global__ void __launch_bounds__(TO + 32, AB_THP_MINB) k_threshold_pair(ThrArgs
     const bool ok_a = is_out && ca < a.W, ok_b = is_out && cb < a.W;
     const size_t fo = (size_t)f * a.out_mul + a.out_off;
     uint8_t* orow = a.thres + fo * a.W * a.H + (size_t)y0 * a.W + ca;
-    uint32_t* brow = a.bits + fo * a.bits_words + (size_t)(y0 + 1) * a.wpr + BIT_PAD + (X0 >> 5) + (t >> 3);
+    uint32_t* brow = a.bits + fo * a.bits_words + bit_word_index(a.wpr, BIT_PAD + (X0 >> 5) + (t >> 3), y0);
+    int btr = (y0 + 1) & 31;  // row inside the bit tile
+    const int bjump = a.wpr * BIT_TILE - (BIT_TILE - 1);
     const bool word_a = ok_a && (t & 7) == 0, word_b = ok_b && (t & 7) == 0;
     const int cst = K2 * a.idelta - (K2 - 1) / 2;  // S >= K2*src + cst  <=>  src - mean <= -idelta
     const uint32_t GC = (uint32_t)((0x8000 - cst) & 0xFFFF) * 0x00010001u;
@@ -174,9 +176,10 @@ __global__ void __launch_bounds__(TO + 32, AB_THP_MINB) k_threshold_pair(ThrArgs
                 x |= __shfl_xor_sync(0xFFFFFFFFu, x, 2);
                 const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, x, 4);
                 if (word_a && row_ok) brow[0] = prmt<0x5410>(x, y);
-                if (word_b && row_ok) brow[HO / 32] = prmt<0x7632>(x, y);
+                if (word_b && row_ok) brow[(HO / 32) * BIT_TILE] = prmt<0x7632>(x, y);
                 orow += a.W;
-                brow += a.wpr;
+                brow += btr == 31 ? bjump : 1;
+                btr = (btr + 1) & 31;
             }
             boff = BUF_BYTES - boff;
         }

@@ -17,7 +17,7 @@ void hc_pack_bits(const uint8_t* img, int W, int H, uint32_t* out) {
     memset(out, 0, sizeof(uint32_t) * ab::bit_image_words(W, H));
     for (int y = 0; y < H; y++)
         for (int x = 0; x < W; x++)
-            if (img[(size_t)y * W + x]) out[(size_t)(y + 1) * wpr + ((x + 32 * ab::BIT_PAD) >> 5)] |= 1u << ((x + 32 * ab::BIT_PAD) & 31);
+            if (img[(size_t)y * W + x]) out[ab::bit_word_index(wpr, (x + 32 * ab::BIT_PAD) >> 5, y)] |= 1u << ((x + 32 * ab::BIT_PAD) & 31);
 }
 
 // all contours with min_len < n < max_len in OpenCV order (reverse discovery). Returns number of contours;
