@@ -35,6 +35,7 @@ struct ab_context {
     cudaStream_t sub_stream[MAX_SUB] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
     int n_sub_streams = 1;  // measured on B200: no gain from 2-4 sub-batches (full grids leave no room to co-schedule)
+    int grid_trace = 8, grid_long = 8, grid_emit = 8;  // CTAs per SM of the persistent walker grids
     int last_nsub = 1;
     ab_params params;
     std::string err;
@@ -190,6 +191,10 @@ int ab_create(int device, ab_context** out) {
     }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     if (const char* e = getenv("ARUCO_B200_SUBBATCHES")) ctx->n_sub_streams = std::max(1, std::min(MAX_SUB, atoi(e)));
+    // walker grids in CTAs per SM (tuning knobs for variant studies)
+    if (const char* e = getenv("ARUCO_B200_GRID_TRACE")) ctx->grid_trace = std::max(1, atoi(e));
+    if (const char* e = getenv("ARUCO_B200_GRID_LONG")) ctx->grid_long = std::max(1, atoi(e));
+    if (const char* e = getenv("ARUCO_B200_GRID_EMIT")) ctx->grid_emit = std::max(1, atoi(e));
     for (int i = 0; i < 6; i++) cudaEventCreate(&ctx->ev[i]);
     for (int i = 0; i < 10; i++) cudaEventCreate(&ctx->kev[i]);
     for (int i = 0; i < 2; i++) {
@@ -641,9 +646,9 @@ static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
     if (timing) cudaEventRecord(ctx->ev[1], st);
     k_scan_starts<<<sms * 8, 256, 0, st>>>(bv);
     if (timing) cudaEventRecord(ctx->kev[2], st);
-    k_trace<false><<<sms * 8, 128, 0, st>>>(bv);
-    k_trace<true><<<sms * 4, 128, 0, st>>>(bv);
-    k_emit_long<<<sms * 8, 128, 0, st>>>(bv);
+    k_trace<false><<<sms * ctx->grid_trace, 128, 0, st>>>(bv);
+    k_trace<true><<<sms * ctx->grid_long, 128, 0, st>>>(bv);
+    k_emit_long<<<sms * ctx->grid_emit, 128, 0, st>>>(bv);
     k_emit<<<sms * 8, 128, 0, st>>>(bv);
     if (timing) cudaEventRecord(ctx->kev[3], st);
     k_polygon<<<sms * 8, 128, 0, st>>>(bv);
