@@ -9,15 +9,20 @@
 namespace ab {
 
 // one thread per word column x 4 rows of a bit tile (128-bit loads; a warp reads 4 whole tiles = 512 contiguous
-// bytes, plus the same rows of the west and east tiles); candidates are appended with one atomic per warp
+// bytes, plus the same rows of the west and east tiles); candidates are appended with ONE atomic per CTA and
+// iteration (one per warp put 520 k atomics on the same counter and the kernel waited on their round trips:
+// 76 % long-scoreboard stalls in ncu r1o)
 __global__ void __launch_bounds__(256) k_scan_starts(Batch b) {
+    __shared__ int s_tot[8];
+    __shared__ unsigned long long s_base;
     const int ww = (b.W + 31) >> 5;
     const int trows = (b.H + 2 + BIT_TILE - 1) / BIT_TILE;
     const unsigned long long total = (unsigned long long)ww * 8ull * trows * b.B;
     const int lane = threadIdx.x & 31;
-    for (unsigned long long base = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; base < total;
-         base += (unsigned long long)gridDim.x * blockDim.x) {
-        unsigned long long i = base + lane;
+    const int warp = threadIdx.x >> 5;
+    for (unsigned long long cbase = (unsigned long long)blockIdx.x * blockDim.x; cbase < total;
+         cbase += (unsigned long long)gridDim.x * blockDim.x) {  // CTA-uniform trip count: barriers inside
+        unsigned long long i = cbase + threadIdx.x;
         uint32_t outer[4] = {0, 0, 0, 0}, hole[4] = {0, 0, 0, 0};
         int wcl = 0, y0 = 0, f = 0, cnt = 0;
         if (i < total) {
@@ -53,22 +58,30 @@ __global__ void __launch_bounds__(256) k_scan_starts(Batch b) {
                 cnt += __popc(outer[k]) + __popc(hole[k]);
             }
         }
-        if (__ballot_sync(0xFFFFFFFFu, cnt != 0) == 0) continue;
         int incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
             if (lane >= d) incl += v;
         }
-        int tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        unsigned long long wbase = 0;
-        if (lane == 31) wbase = atomicAdd(&b.cnt->n_starts, (unsigned long long)tot);
-        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
-        if (wbase + (unsigned long long)tot > b.cap_starts) {
-            if (lane == 31) atomicOr(&b.cnt->err, ERR_STARTS_OVERFLOW);
+        if (lane == 31) s_tot[warp] = incl;
+        __syncthreads();
+        int before = 0, tot = 0;  // candidates of the warps before this one / of the whole CTA
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const int v = s_tot[w];
+            before += w < warp ? v : 0;
+            tot += v;
+        }
+        if (threadIdx.x == 0 && tot) s_base = atomicAdd(&b.cnt->n_starts, (unsigned long long)tot);
+        __syncthreads();
+        if (tot == 0) continue;
+        const unsigned long long cta_base = s_base;
+        if (cta_base + (unsigned long long)tot > b.cap_starts) {
+            if (threadIdx.x == 0) atomicOr(&b.cnt->err, ERR_STARTS_OVERFLOW);
             continue;
         }
-        unsigned long long o = wbase + (unsigned long long)(incl - cnt);
+        unsigned long long o = cta_base + (unsigned long long)(before + incl - cnt);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             uint32_t m = outer[k];

@@ -121,7 +121,30 @@ __global__ void __launch_bounds__(32 * DECODE_WARPS) k_sample(Batch b) {
         float Mf[9];
 #pragma unroll
         for (int q = 0; q < 9; q++) Mf[q] = (float)ax->Mi[q];
-        const float aM0 = fabsf(Mf[0]), aM1 = fabsf(Mf[1]), aM2 = fabsf(Mf[2]), aM3 = fabsf(Mf[3]), aM4 = fabsf(Mf[4]), aM5 = fabsf(Mf[5]);
+        // Forward error bound of the f32 evaluation, once per candidate: |error(fx)| <= u' * (|M0 x| + |M1 y| + |M2|) / |den|
+        // with u' covering ~12 roundings (unit roundoff 6e-8; 4e-6 leaves > 5x slack).  The bound is a ratio of affine
+        // functions with positive terms, so over the destination square it peaks at a corner -- unless den changes
+        // sign inside the square (horizon through the marker), in which case every pixel takes the exact path.
+        float gx, gy;  // a coordinate is trusted when it is more than (0.5 - g) away from a rounding boundary
+        {
+            const float aM0 = fabsf(Mf[0]), aM1 = fabsf(Mf[1]), aM2 = fabsf(Mf[2]), aM3 = fabsf(Mf[3]), aM4 = fabsf(Mf[4]), aM5 = fabsf(Mf[5]);
+            const float e = (float)(S - 1);
+            float mx = 0.f, my = 0.f;
+            int pos = 0, neg = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float cx = (c & 1) ? e : 0.f, cy = (c & 2) ? e : 0.f;
+                const float den = __fmaf_rn(Mf[6], cx, __fmaf_rn(Mf[7], cy, Mf[8]));
+                pos += den > 0.f;
+                neg += den < 0.f;
+                const float iad = 1.0f / fabsf(den);
+                mx = fmaxf(mx, __fmaf_rn(aM0, cx, __fmaf_rn(aM1, cy, aM2)) * iad);
+                my = fmaxf(my, __fmaf_rn(aM3, cx, __fmaf_rn(aM4, cy, aM5)) * iad);
+            }
+            const bool one_sign = pos == 4 || neg == 4;
+            gx = one_sign ? 0.5f - (4e-6f * mx + 2e-4f) : -1.f;
+            gy = one_sign ? 0.5f - (4e-6f * my + 2e-4f) : -1.f;
+        }
         const float invS = 1.0f / (float)S;
         const bool words = (SS & 3) == 0;
         int nunc = 0;
@@ -138,15 +161,12 @@ __global__ void __launch_bounds__(32 * DECODE_WARPS) k_sample(Batch b) {
                     const int y = (int)(((float)i + 0.5f) * invS), x = i - y * S;  // exact: the fraction is >= 0.5/S away from an integer
                     const float fxp = (float)x, fyp = (float)y;
                     const float den = __fmaf_rn(Mf[6], fxp, __fmaf_rn(Mf[7], fyp, Mf[8]));
-                    const float iden = __frcp_rn(den);
+                    float iden;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iden) : "f"(den));  // <= 1 ulp: inside the bound's slack
                     const float fx = __fmaf_rn(Mf[0], fxp, __fmaf_rn(Mf[1], fyp, Mf[2])) * iden;
                     const float fy = __fmaf_rn(Mf[3], fxp, __fmaf_rn(Mf[4], fyp, Mf[5])) * iden;
                     const float rx = rintf(fx), ry = rintf(fy);
-                    // forward error bound of the f32 evaluation (unit roundoff 6e-8; 1e-6 leaves > 3x slack), doubled
-                    const float iad = fabsf(iden);
-                    const float ex = __fmaf_rn(2e-6f, __fmaf_rn(__fmaf_rn(aM0, fxp, __fmaf_rn(aM1, fyp, aM2)), iad, fabsf(fx)), 2e-4f);
-                    const float ey = __fmaf_rn(2e-6f, __fmaf_rn(__fmaf_rn(aM3, fxp, __fmaf_rn(aM4, fyp, aM5)), iad, fabsf(fy)), 2e-4f);
-                    unc[u] = !(fabsf(fx) < 32768.f && fabsf(fy) < 32768.f) || !(0.5f - fabsf(fx - rx) > ex) || !(0.5f - fabsf(fy - ry) > ey);
+                    unc[u] = !(fabsf(fx) < 32768.f && fabsf(fy) < 32768.f) || !(fabsf(fx - rx) < gx) || !(fabsf(fy - ry) < gy);
                     if (!unc[u]) {
                         const int sx = (int)rx, sy = (int)ry;
                         if (sx >= 0 && sy >= 0 && sx < b.W && sy < b.H) v[u] = grey[(size_t)sy * b.grey_row + sx];
