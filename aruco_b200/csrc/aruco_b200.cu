@@ -85,7 +85,7 @@ struct ab_context {
     // timing
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t kev[10] = {};  // per-kernel boundaries: memset|threshold|scan|trace|polygon|filter|decode|refine|finalize
+    cudaEvent_t kev[12] = {};  // boundaries: threshold|scan|trace|trace_long|emit|polygon|filter|decode|refine|finalize
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 };
 
@@ -196,7 +196,7 @@ int ab_create(int device, ab_context** out) {
     if (const char* e = getenv("ARUCO_B200_GRID_LONG")) ctx->grid_long = std::max(1, atoi(e));
     if (const char* e = getenv("ARUCO_B200_GRID_EMIT")) ctx->grid_emit = std::max(1, atoi(e));
     for (int i = 0; i < 6; i++) cudaEventCreate(&ctx->ev[i]);
-    for (int i = 0; i < 10; i++) cudaEventCreate(&ctx->kev[i]);
+    for (int i = 0; i < 12; i++) cudaEventCreate(&ctx->kev[i]);
     for (int i = 0; i < 2; i++) {
         cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
@@ -220,7 +220,7 @@ void ab_destroy(ab_context* ctx) {
     F(ctx->d_dict_tree);
     for (int i = 0; i < 6; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-    for (int i = 0; i < 10; i++)
+    for (int i = 0; i < 12; i++)
         if (ctx->kev[i]) cudaEventDestroy(ctx->kev[i]);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
@@ -647,15 +647,17 @@ static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
     k_scan_starts<<<sms * 8, 256, 0, st>>>(bv);
     if (timing) cudaEventRecord(ctx->kev[2], st);
     k_trace<false><<<sms * ctx->grid_trace, 128, 0, st>>>(bv);
+    if (timing) cudaEventRecord(ctx->kev[3], st);
     k_trace<true><<<sms * ctx->grid_long, 128, 0, st>>>(bv);
+    if (timing) cudaEventRecord(ctx->kev[4], st);
     k_emit_long<<<sms * ctx->grid_emit, 128, 0, st>>>(bv);
     k_emit<<<sms * 8, 128, 0, st>>>(bv);
-    if (timing) cudaEventRecord(ctx->kev[3], st);
+    if (timing) cudaEventRecord(ctx->kev[5], st);
     k_polygon<<<sms * 8, 128, 0, st>>>(bv);
-    if (timing) cudaEventRecord(ctx->kev[4], st);
+    if (timing) cudaEventRecord(ctx->kev[6], st);
     k_frame_filter<<<n, 256, 0, st>>>(b);
     CK(cudaGetLastError());
-    if (timing) cudaEventRecord(ctx->kev[5], st);
+    if (timing) cudaEventRecord(ctx->kev[7], st);
     if (timing) cudaEventRecord(ctx->ev[2], st);
     dim3 gcand(b.cap_c, n);
     dim3 gdec((b.cap_c + DECODE_WARPS - 1) / DECODE_WARPS, n);
@@ -692,7 +694,7 @@ static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
         k_identify<<<gdec, 32 * DECODE_WARPS, dec_smem, st>>>(b);
         CK(cudaGetLastError());
     }
-    if (timing) cudaEventRecord(ctx->kev[6], st);
+    if (timing) cudaEventRecord(ctx->kev[8], st);
     if (timing) cudaEventRecord(ctx->ev[3], st);
     if (P.locked_corners && (P.corner_method == AB_CORNER_HARRIS || P.corner_method == AB_CORNER_SUBPIX)) {
         // findCornerMaxima before the refiner (src/markerdetector.cpp:397-398)
@@ -712,11 +714,11 @@ static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
         k_refine_subpix<<<dim3(b.cap_c, n), 128, smem, st>>>(b);
     }
     CK(cudaGetLastError());
-    if (timing) cudaEventRecord(ctx->kev[7], st);
+    if (timing) cudaEventRecord(ctx->kev[9], st);
     if (timing) cudaEventRecord(ctx->ev[4], st);
     k_finalize<<<n, 128, 0, st>>>(b);
     CK(cudaGetLastError());
-    if (timing) cudaEventRecord(ctx->kev[8], st);
+    if (timing) cudaEventRecord(ctx->kev[10], st);
     if (timing) cudaEventRecord(ctx->ev[5], st);
     return AB_OK;
 }
@@ -1042,7 +1044,7 @@ int ab_get_kernel_ms(ab_context* ctx, float* ms, int n) {
     if (!ctx || !ms || !ctx->timing || !ctx->have_last) return set_err(ctx, AB_E_STATE, "timing not enabled");
     cudaSetDevice(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < n && i < 8; i++) CK(cudaEventElapsedTime(&ms[i], ctx->kev[i], ctx->kev[i + 1]));
+    for (int i = 0; i < n && i < 10; i++) CK(cudaEventElapsedTime(&ms[i], ctx->kev[i], ctx->kev[i + 1]));
     return AB_OK;
 }
 

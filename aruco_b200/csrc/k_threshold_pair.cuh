@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(TO + 32, AB_THP_MINB) k_threshold_pair(ThrArgs
     constexpr int NT = TO + 2 * HT;              // working threads
     constexpr int DEPTH = AB_THP_DEPTH;                     // source rows in flight (cp.async groups)
     constexpr uint32_t STAGE_ROW = NT * 8;       // bytes of one staged row: 2 words per thread
-    constexpr int RH = (AB_THP_RH / K) * K;  // rows per CTA: whole turns of the ring, so the unrolled loop has no exits
-    __shared__ __align__(16) uint32_t cs[2][CSW];
+    constexpr int RH = (AB_THP_RH / (2 * K)) * (2 * K);  // rows per CTA: whole double turns of the ring, so the unrolled loop has no exits
+    __shared__ __align__(16) uint32_t cs[4][CSW];  // two buffers of two rows
     __shared__ __align__(16) uint2 stage[DEPTH][NT];  // ncu r1j: with loads held in registers two of the K unrolled steps
                                                       // waited ~1 row on the scoreboard; cp.async groups decouple them
     const int t = threadIdx.x;
@@ -143,45 +143,53 @@ __global__ void __launch_bounds__(TO + 32, AB_THP_MINB) k_threshold_pair(ThrArgs
     };
 #pragma unroll
     for (int j = 0; j < 2 * R; j++) accumulate(ring[j]);
-    for (int o = 0; o < nout; o += K) {
+    // horizontal window sums, comparison and stores of one output row whose column sums sit at shared offset `rd`
+    auto emit_row = [&](uint32_t rd, const uint32_t* c, bool row_ok) {
+        uint32_t w[NV];
 #pragma unroll
-        for (int jj = 0; jj < K; jj++) {
+        for (int q = 0; q < NV / 4; q++) lds128(rd + 16u * q, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        uint32_t S0 = GC;
+#pragma unroll
+        for (int d = R4 - R; d <= R4 + R; d++) S0 += w[d];
+        const uint32_t S1 = S0 - w[R4 - R] + w[R4 + R + 1];
+        const uint32_t S2 = S1 - w[R4 - R + 1] + w[R4 + R + 2];
+        const uint32_t S3 = S2 - w[R4 - R + 2] + w[R4 + R + 3];
+        const uint32_t D0 = S0 - (uint32_t)K2 * c[0], D1 = S1 - (uint32_t)K2 * c[1], D2 = S2 - (uint32_t)K2 * c[2],
+                       D3 = S3 - (uint32_t)K2 * c[3];
+        // sign bytes (bits 15 / 31) -> 0x00 / 0xFF output bytes of the two halves
+        const uint32_t L1 = prmt<0xFBD9>(D0, D1), L2 = prmt<0xFBD9>(D2, D3);
+        const uint32_t out_a = prmt<0x5410>(L1, L2), out_b = prmt<0x7632>(L1, L2);
+        if (ok_a && row_ok) *reinterpret_cast<uint32_t*>(orow) = out_a;
+        if (ok_b && row_ok) *reinterpret_cast<uint32_t*>(orow + HO) = out_b;
+        const uint32_t nib_a = ok_a ? ((out_a & 0x08040201u) * 0x01010101u) >> 24 : 0u;
+        const uint32_t nib_b = ok_b ? ((out_b & 0x08040201u) * 0x01010101u) >> 24 : 0u;
+        // 8 threads make one 32-bit word per half: two levels carry both halves in one register
+        uint32_t x = (nib_a | (nib_b << 16)) << nib_shift;
+        x |= __shfl_xor_sync(0xFFFFFFFFu, x, 1);
+        x |= __shfl_xor_sync(0xFFFFFFFFu, x, 2);
+        const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, x, 4);
+        if (word_a && row_ok) brow[0] = prmt<0x5410>(x, y);
+        if (word_b && row_ok) brow[(HO / 32) * BIT_TILE] = prmt<0x7632>(x, y);
+        orow += a.W;
+        brow += btr == 31 ? bjump : 1;
+        btr = (btr + 1) & 31;
+    };
+    // two rows per barrier (ncu r1p: 23 % of the stall samples sat on the per-row barrier, 24 % on the shared loads and
+    // shuffles behind it): the column sums of rows A and B are published together, then both rows are finished with
+    // twice the independent work in flight.  Row B's ring slot is never row A's centre slot (they differ by R mod K).
+    for (int o = 0; o < nout; o += 2 * K) {
+#pragma unroll
+        for (int jj = 0; jj < 2 * K; jj += 2) {
             accumulate(ring[(2 * R + jj) % K]);
             sts128(s_wr + boff, V0, V1, V2, V3);
+            accumulate(ring[(2 * R + jj + 1) % K]);
+            sts128(s_wr + boff + BUF_BYTES, V0, V1, V2, V3);
             __syncthreads();
             if (is_out) {
-                uint32_t w[NV];
-#pragma unroll
-                for (int q = 0; q < NV / 4; q++) lds128(s_rd + boff + 16u * q, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-                uint32_t S0 = GC;
-#pragma unroll
-                for (int d = R4 - R; d <= R4 + R; d++) S0 += w[d];
-                const uint32_t S1 = S0 - w[R4 - R] + w[R4 + R + 1];
-                const uint32_t S2 = S1 - w[R4 - R + 1] + w[R4 + R + 2];
-                const uint32_t S3 = S2 - w[R4 - R + 2] + w[R4 + R + 3];
-                const uint32_t* c = ring[(R + jj) % K];  // centre row: R steps older than the newest
-                const uint32_t D0 = S0 - (uint32_t)K2 * c[0], D1 = S1 - (uint32_t)K2 * c[1], D2 = S2 - (uint32_t)K2 * c[2],
-                               D3 = S3 - (uint32_t)K2 * c[3];
-                // sign bytes (bits 15 / 31) -> 0x00 / 0xFF output bytes of the two halves
-                const uint32_t L1 = prmt<0xFBD9>(D0, D1), L2 = prmt<0xFBD9>(D2, D3);
-                const uint32_t out_a = prmt<0x5410>(L1, L2), out_b = prmt<0x7632>(L1, L2);
-                const bool row_ok = o + jj < nout;
-                if (ok_a && row_ok) *reinterpret_cast<uint32_t*>(orow) = out_a;
-                if (ok_b && row_ok) *reinterpret_cast<uint32_t*>(orow + HO) = out_b;
-                const uint32_t nib_a = ok_a ? ((out_a & 0x08040201u) * 0x01010101u) >> 24 : 0u;
-                const uint32_t nib_b = ok_b ? ((out_b & 0x08040201u) * 0x01010101u) >> 24 : 0u;
-                // 8 threads make one 32-bit word per half: two levels carry both halves in one register
-                uint32_t x = (nib_a | (nib_b << 16)) << nib_shift;
-                x |= __shfl_xor_sync(0xFFFFFFFFu, x, 1);
-                x |= __shfl_xor_sync(0xFFFFFFFFu, x, 2);
-                const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, x, 4);
-                if (word_a && row_ok) brow[0] = prmt<0x5410>(x, y);
-                if (word_b && row_ok) brow[(HO / 32) * BIT_TILE] = prmt<0x7632>(x, y);
-                orow += a.W;
-                brow += btr == 31 ? bjump : 1;
-                btr = (btr + 1) & 31;
+                emit_row(s_rd + boff, ring[(R + jj) % K], o + jj < nout);
+                emit_row(s_rd + boff + BUF_BYTES, ring[(R + jj + 1) % K], o + jj + 1 < nout);
             }
-            boff = BUF_BYTES - boff;
+            boff = 2 * BUF_BYTES - boff;
         }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -200,7 +208,7 @@ inline bool launch_threshold_pair(const ThrArgs& a, int B, cudaStream_t st) {
         if (pad < best_pad) best_pad = pad, best_to = to;
     }
     const int tw = 8 * best_to;
-    const int rh = (AB_THP_RH / a.k) * a.k;
+    const int rh = (AB_THP_RH / (2 * a.k)) * (2 * a.k);
     dim3 grid((a.W + tw - 1) / tw, (a.H + rh - 1) / rh, B);
 #define AB_THP_TO(KK, TT)                                        \
     if (best_to == TT) {                                         \

@@ -316,9 +316,11 @@ def main():
     # ---- roofline of the dominant kernel ------------------------------------------------------------------
     peak, peak_src = measured_peaks()
     dom = max(kernel_ms, key=kernel_ms.get)
-    # algorithmic bytes per launch: threshold reads the grey frame and writes the u8
-    # binarised frame (+1/8 for the packed copy is not counted); trace/scan read the packed image once.
-    alg_bytes = {"threshold": 2.0 * W * H * B, "scan_starts": W * H / 8.0 * B, "trace": W * H / 8.0 * B}.get(dom, 2.0 * W * H * B)
+    # algorithmic bytes per launch: threshold reads the grey frame and
+    # writes the u8 binarised frame (the 1/8 B/px packed copy is not counted); the scan and the walkers read the packed
+    # image; the other kernels work per candidate (< 1 % of a frame) and are given the whole-path figure 3*W*H.
+    packed = W * H / 8.0 * B
+    alg_bytes = {"threshold": 2.0 * W * H * B, "scan_starts": packed, "trace": packed, "trace_long": packed, "emit": packed}.get(dom, 3.0 * W * H * B)
     achieved = alg_bytes / (kernel_ms[dom] / 1e3) / 1e9
     thr_gbs = 2.0 * W * H * B / (kernel_ms["threshold"] / 1e3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
