@@ -111,6 +111,7 @@ struct Batch {
     unsigned long long cap_pool;
     LongRec* longq;
     unsigned int cap_long;
+    const uint8_t* walk_lut;  // WALK_LUT_FW then WALK_LUT_BW (ab_trace.cuh)
     EmitRec* emitq;  // long contours (at most one per parked walk: capacity cap_long)
     QuadRec* quads;  // [B][cap_q]
     int cap_q;

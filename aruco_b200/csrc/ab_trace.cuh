@@ -48,10 +48,10 @@ struct BitImage {
     AB_HD const uint32_t* word(int wc, int y) const { return bits + bit_word_index(wpr, wc, y); }
 };
 
-// 8-neighbour mask of pixel (x,y): bit d set <=> neighbour in direction d is foreground.
+// 3x3 window of pixel (x,y) as 9 bits: bits 0-2 = row above (x-1, x, x+1), 3-5 = own row, 6-8 = row below.
 // The three rows are read with ONE word each; the word of the next column is fetched only when the 3-pixel window
 // straddles a word boundary (2 of 32 positions).
-AB_HD uint32_t neighbours8(const BitImage& im, int x, int y) {
+AB_HD uint32_t window9(const BitImage& im, int x, int y) {
     const int p = x - 1 + 32 * BIT_PAD;  // pixel x lives at padded bit x + 32*BIT_PAD
     const int sh = p & 31, yr = (y + 1) & 31;
     const uint32_t* r1 = im.word(p >> 5, y);
@@ -74,9 +74,17 @@ AB_HD uint32_t neighbours8(const BitImage& im, int x, int y) {
     m = (uint32_t)((((uint64_t)mh << 32) | m) >> sh) & 7u;
     b = (uint32_t)((((uint64_t)bh << 32) | b) >> sh) & 7u;
 #endif
+    return t + m * 8u + b * 64u;
+}
+
+// 8-neighbour mask from the window: bit d set <=> neighbour in direction d is foreground
+AB_HD uint32_t nb_from_window(uint32_t w) {
+    const uint32_t t = w & 7u, m = (w >> 3) & 7u, b = (w >> 6) & 7u;
     return ((m >> 2) & 1u) | (((t >> 2) & 1u) << 1) | (((t >> 1) & 1u) << 2) | ((t & 1u) << 3) | ((m & 1u) << 4) |
            ((b & 1u) << 5) | (((b >> 1) & 1u) << 6) | (((b >> 2) & 1u) << 7);
 }
+
+AB_HD uint32_t neighbours8(const BitImage& im, int x, int y) { return nb_from_window(window9(im, x, y)); }
 
 AB_HD int dir_dx(int d) { return (d == 0 || d == 1 || d == 7) ? 1 : ((d >= 3 && d <= 5) ? -1 : 0); }
 AB_HD int dir_dy(int d) { return (d >= 1 && d <= 3) ? -1 : ((d >= 5) ? 1 : 0); }
@@ -167,6 +175,35 @@ AB_HD uint32_t walk_backward(const BitImage& im, WalkState& s) {
     s.y = qy;
     return nbq;
 }
+
+// ---- table-driven step (k_trace): all of the combinational logic of a step is a function of the 9-bit window and
+// a 3-bit direction, so the kernel looks it up instead of computing it (the walkers are issue bound).
+//   WALK_LUT_FW[w | b << 9]: state (pixel with window w, back-direction b) -> bits 0-2 direction of the successor,
+//                            bit 3 / bit 4: the state is the start state of an outer / hole start candidate
+//   WALK_LUT_BW[w | d << 9]: w = window of the predecessor pixel q, d = direction from q to the current pixel
+//                            -> bits 0-2 back-direction b' of the predecessor state, bits 3/4 as above for (q, b')
+constexpr int WALK_LUT_SIZE = 4096;
+constexpr uint32_t WALK_TRIG_OUTER = 8u, WALK_TRIG_HOLE = 16u;
+AB_HD uint8_t walk_lut_flags(uint32_t nb, int b) {
+    uint32_t f = 0;
+    if (is_outer_candidate(nb) && b == first_clockwise(nb, 4)) f |= WALK_TRIG_OUTER;
+    if (is_hole_candidate_east(nb) && b == first_clockwise(nb, 0)) f |= WALK_TRIG_HOLE;
+    return (uint8_t)f;
+}
+AB_HD uint8_t walk_lut_fw_entry(uint32_t idx) {
+    const uint32_t nb = nb_from_window(idx & 511u);
+    const int b = (int)(idx >> 9);
+    return (uint8_t)((uint32_t)(next_dir(nb, b) & 7) | walk_lut_flags(nb, b));
+}
+AB_HD uint8_t walk_lut_bw_entry(uint32_t idx) {
+    const uint32_t nb = nb_from_window(idx & 511u);
+    int b = first_clockwise(nb, (int)(idx >> 9));
+    if (b < 0) b = 0;  // isolated pixel: never reached by a walk
+    return (uint8_t)((uint32_t)b | walk_lut_flags(nb, b));
+}
+// dx / dy of direction d, two bits per direction biased by 1
+AB_HD int step_dx(int d) { return (int)((0x901Au >> (2 * d)) & 3u) - 1; }
+AB_HD int step_dy(int d) { return (int)((0xA901u >> (2 * d)) & 3u) - 1; }
 
 // Bidirectional search: is `st` the Suzuki start of its border?  Walks forwards and backwards alternately
 // and stops as soon as either walker stands on the start state of a candidate with a smaller scan position

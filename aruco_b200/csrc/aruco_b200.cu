@@ -55,6 +55,7 @@ struct ab_context {
     uint32_t* d_pool = nullptr;
     LongRec* d_longq = nullptr;
     EmitRec* d_emitq = nullptr;
+    uint8_t* d_walk_lut = nullptr;
     unsigned capLongPF = 8192;
     QuadRec* d_quads = nullptr;
     CandRec* d_cands = nullptr;
@@ -190,6 +191,18 @@ int ab_create(int device, ab_context** out) {
         cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    {  // step tables of the border walkers (ab_trace.cuh)
+        std::vector<uint8_t> lut(2 * WALK_LUT_SIZE);
+        for (uint32_t i = 0; i < (uint32_t)WALK_LUT_SIZE; i++) {
+            lut[i] = walk_lut_fw_entry(i);
+            lut[WALK_LUT_SIZE + i] = walk_lut_bw_entry(i);
+        }
+        if (cudaMalloc(&ctx->d_walk_lut, lut.size()) != cudaSuccess ||
+            cudaMemcpy(ctx->d_walk_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->d_walk_lut = nullptr;
+        }
+    }
     if (const char* e = getenv("ARUCO_B200_SUBBATCHES")) ctx->n_sub_streams = std::max(1, std::min(MAX_SUB, atoi(e)));
     // walker grids in CTAs per SM (tuning knobs for variant studies)
     if (const char* e = getenv("ARUCO_B200_GRID_TRACE")) ctx->grid_trace = std::max(1, atoi(e));
@@ -210,6 +223,7 @@ void ab_destroy(ab_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     free_buffers(ctx);
+    if (ctx->d_walk_lut) cudaFree(ctx->d_walk_lut);
     auto F = [](auto*& p) {
         if (p) cudaFree(p);
         p = nullptr;
@@ -552,6 +566,7 @@ static int fill_batch(ab_context* ctx, Batch& b, const uint8_t* dgrey, size_t ro
     b.longq = ctx->d_longq;
     b.cap_long = ctx->capLongPF * (unsigned)n;
     b.emitq = ctx->d_emitq;
+    b.walk_lut = ctx->d_walk_lut;
     b.pool = ctx->d_pool;
     b.cap_pool = (unsigned long long)ctx->capPoolPF * n;
     b.quads = ctx->d_quads;

@@ -114,6 +114,12 @@ __global__ void __launch_bounds__(256) k_scan_starts(Batch b) {
 // most of its time issuing instructions for ~9 of 32 lanes (ncu r1e).
 constexpr int TRACE_LONG_T = 48;
 
+// `s` is the start state of a start candidate (table flags e): does its trigger scan before key0?
+__device__ __forceinline__ bool smaller_trigger(uint32_t e, const WalkState& s, int W, int64_t key0) {
+    const int64_t k = (int64_t)s.y * W + s.x;
+    return ((e & WALK_TRIG_OUTER) && k < key0) || ((e & WALK_TRIG_HOLE) && k + 1 < key0);
+}
+
 template <bool LONG>
 __global__ void __launch_bounds__(128) k_trace(Batch b) {
     constexpr int STEPS = 8;
@@ -132,7 +138,9 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
     BitImage im = b.bit_image(0);
     TraceStart st{0, 0, 0, 0};
     WalkState fw{0, 0, 0}, bw{0, 0, 0};
-    uint32_t nb_fw = 0, type_bit = 0;
+    uint32_t e_fw = 0, type_bit = 0;  // e_fw: forward table entry of the current forward state
+    const uint8_t* __restrict__ lut_fw = b.walk_lut;
+    const uint8_t* __restrict__ lut_bw = b.walk_lut + WALK_LUT_SIZE;
     int nf = 0, ng = 0, frame = 0;
     // LONG only: walker states at the last two power-of-two step counts (pixels, back-directions, step count);
     // they cut the finished contour into segments that k_emit_long writes in parallel
@@ -162,7 +170,7 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                     bw = WalkState{(int)(q.bxy & 0xFFFFu), (int)(q.bxy >> 16), (int)((q.dirs >> 4) & 7u)};
                     nf = (int)q.nf;
                     ng = (int)q.ng;
-                    nb_fw = neighbours8(im, fw.x, fw.y);
+                    e_fw = lut_fw[window9(im, fw.x, fw.y) | ((uint32_t)fw.b << 9)];
                     cpF1 = cpF2 = cpB1 = cpB2 = cpd = 0;
                     pF = qB = 0;
                     active = true;
@@ -174,7 +182,7 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                     if (make_start(im, (int)(rec.x >> 31), (int)(rec.y & 0xFFFFu), (int)(rec.y >> 16), st)) {
                         fw = WalkState{st.x, st.y, st.b};
                         bw = fw;
-                        nb_fw = neighbours8(im, fw.x, fw.y);
+                        e_fw = lut_fw[window9(im, fw.x, fw.y) | ((uint32_t)fw.b << 9)];
                         nf = ng = 0;
                         nodefer = false;
                         active = true;
@@ -193,10 +201,18 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                 // dependent load rounds per iteration were the latency floor of long walks); the backward step
                 // is only COMMITTED if the forward step neither closed the cycle nor hit a smaller start
                 const WalkState bw0 = bw;
-                walk_forward(fw, nb_fw);
-                nb_fw = neighbours8(im, fw.x, fw.y);
-                WalkState bw1 = bw0;
-                const uint32_t nb_bw = walk_backward(im, bw1);
+                {
+                    const int d = (int)(e_fw & 7u);
+                    fw.x += step_dx(d);
+                    fw.y += step_dy(d);
+                    fw.b = (d + 4) & 7;
+                }
+                const uint32_t w_f = window9(im, fw.x, fw.y);
+                WalkState bw1{bw0.x + step_dx(bw0.b), bw0.y + step_dy(bw0.b), 0};
+                const uint32_t w_q = window9(im, bw1.x, bw1.y);
+                e_fw = lut_fw[w_f | ((uint32_t)fw.b << 9)];
+                const uint32_t e_bw = lut_bw[w_q | ((uint32_t)((bw0.b + 4) & 7) << 9)];
+                bw1.b = (int)(e_bw & 7u);
                 nf++;
                 if (LONG && (nf & (nf - 1)) == 0) {  // parked walks arrive with nf < 64: the first checkpoint is step 64
                     cpF2 = cpF1;
@@ -206,7 +222,7 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                 }
                 if (same_state(fw, bw0)) {
                     closed = true;
-                } else if (is_smaller_trigger(im, fw, nb_fw, st.key)) {
+                } else if ((e_fw & (WALK_TRIG_OUTER | WALK_TRIG_HOLE)) && smaller_trigger(e_fw, fw, im.W, st.key)) {
                     dead = true;
                 } else {
                     bw = bw1;
@@ -218,7 +234,7 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                         qB = ng;
                     }
                     if (same_state(fw, bw)) closed = true;
-                    else if (is_smaller_trigger(im, bw, nb_bw, st.key)) dead = true;
+                    else if ((e_bw & (WALK_TRIG_OUTER | WALK_TRIG_HOLE)) && smaller_trigger(e_bw, bw, im.W, st.key)) dead = true;
                     else if (nf + ng >= b.max_len) dead = true;  // too long: dropped by :517 anyway
                 }
                 if (closed) {
