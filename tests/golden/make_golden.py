@@ -90,6 +90,17 @@ def main():
     exp["boards"]["chessboard_meters"] = read_board_cfg(os.path.join(REF, "chessboard/chessboardinfo_meters.yml"))
     with open(os.path.join(OUT, "expected.json"), "w") as f:
         json.dump(exp, f, indent=1)
+    # raw YAML wire-format fixtures for the C++ reader/writer (tests/test_yaml.py): test DATA, byte for byte
+    ydir = os.path.join(OUT, "yaml")
+    os.makedirs(ydir, exist_ok=True)
+    for rel in ("single/intrinsics.yml", "single/expected.yml", "hrm/expected.yml", "hrm/intrinsics.yml", "board/expected.yml",
+                "board/board_pix.yml", "board/board_meters.yml", "board/intrinsics.yml", "chessboard/expected.yml",
+                "chessboard/chessboardinfo_pix.yml", "chessboard/intrinsics.yml", "hrm/dictionaries/d4x4_100.yml",
+                "hrm/dictionaries/d6x6_100.yml", "mask/dictionary.yml"):
+        with open(os.path.join(REF, rel), "rb") as f:
+            data = f.read()
+        with open(os.path.join(ydir, rel.replace("/", "__")), "wb") as f:
+            f.write(data)
     print("wrote", os.listdir(OUT))
 
 

@@ -114,6 +114,36 @@ def test_cpp_facade_aruco_simple(built, frames, expected, tmp_path):
         assert np.abs(np.array([float(v) for v in r[13:16]]) - np.array(g["tvec"])).max() < 1e-4
 
 
+@pytest.mark.parametrize("name,cfgfile", [("board", "board__board_pix.yml"), ("chessboard", "chessboard__chessboardinfo_pix.yml")])
+def test_cpp_facade_aruco_simple_board_from_yaml(built, frames, expected, name, cfgfile, tmp_path):
+    """Headless utils/aruco_simple_board.cpp on the C++ facade, configured only by the reference's YAML files
+    (board configuration + intrinsics read by include/aruco/serialization.hpp); the Board it saves, read back by
+    cv::FileStorage, must be the reference's golden board (Aruco.Board / Aruco.Multi)."""
+    import os
+    import subprocess
+    import cv2
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "tests", "_build", "aruco_simple_board")
+    ydir = os.path.join(ROOT, "tests", "golden", "yaml")
+    raw, out_yml = tmp_path / "frame.raw", tmp_path / "board.yml"
+    frames[name].tofile(str(raw))
+    H, W = frames[name].shape
+    r = subprocess.run([exe, str(raw), str(W), str(H), os.path.join(ydir, cfgfile), os.path.join(ydir, name + "__intrinsics.yml"), "1.0",
+                        str(out_yml)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    fs = cv2.FileStorage(str(out_yml), cv2.FILE_STORAGE_READ)
+    b = fs.getNode("Board")
+    g = expected["goldens"][name]
+    assert np.abs(np.array([b.getNode("Rvec").at(k).real() for k in range(3)]) - np.array(g["rvec"])).max() < 1e-4
+    assert np.abs(np.array([b.getNode("Tvec").at(k).real() for k in range(3)]) - np.array(g["tvec"])).max() < 1e-4
+    ms = b.getNode("Markers")
+    assert [int(ms.at(i).getNode("id").real()) for i in range(ms.size())] == [m["id"] for m in g["markers"]]
+    for i, m in enumerate(g["markers"]):
+        c = ms.at(i).getNode("corners")
+        got = np.array([[c.at(k).at(0).real(), c.at(k).at(1).real()] for k in range(4)])
+        assert np.abs(got - np.array(m["corners"])).max() < 0.01
+
+
 @pytest.mark.parametrize("name,cfgname", [("board", "board_pix"), ("chessboard", "chessboard_pix")])
 def test_board_detector_goldens(built, frames, expected, name, cfgname):
     """Aruco.Board / Aruco.Multi (test/core_tests.cpp:164-228) through the device: detect without camera, then
