@@ -23,9 +23,9 @@ tests/_build/libhostcheck.so: tests/hostcheck/hostcheck.cpp $(wildcard aruco_b20
 	@mkdir -p tests/_build
 	$(CXX) -O2 -ffp-contract=off -shared -fPIC -o $@ tests/hostcheck/hostcheck.cpp
 
-FACADE_HDR := include/aruco/markerdetector.hpp include/aruco/serialization.hpp
+FACADE_HDR := include/aruco/markerdetector.hpp include/aruco/serialization.hpp include/aruco/arucofidmarkers.hpp
 FACADE_LD  := -Laruco_b200/lib -laruco_b200 -Wl,-rpath,'$$ORIGIN/../../aruco_b200/lib'
-facade: tests/_build/aruco_simple tests/_build/aruco_simple_board tests/_build/yaml_tool
+facade: tests/_build/aruco_simple tests/_build/aruco_simple_board tests/_build/aruco_create_board tests/_build/yaml_tool
 tests/_build/%: tests/cpp/%.cpp $(FACADE_HDR) $(LIB)
 	@mkdir -p tests/_build
 	$(CXX) -std=c++14 -O1 -Wall -o $@ $< $(FACADE_LD)

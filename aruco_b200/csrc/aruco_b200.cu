@@ -17,6 +17,7 @@
 #include "k_contours.cuh"
 #include "k_polygon.cuh"
 #include "k_decode.cuh"
+#include "k_render.cuh"
 #include "k_refine.cuh"
 #include "k_finalize.cuh"
 
@@ -1137,6 +1138,117 @@ int ab_warp(ab_context* ctx, const uint8_t* grey, int width, int height, size_t 
     cudaFree(d_img);
     cudaFree(d_out);
     cudaFree(d_quad);
+    return AB_OK;
+}
+
+// ---- marker / board rendering (k_render.cuh) -----------------------------------------------------------------
+static int render_canvas(ab_context* ctx, int W, int H, uint8_t background, const std::vector<RenderRect>& rects, int n_black,
+                         uint8_t* out, size_t out_stride) {
+    cudaSetDevice(ctx->device);
+    uint8_t* d_img = nullptr;
+    RenderRect* d_rects = nullptr;
+    CK(cudaMalloc(&d_img, (size_t)W * H));
+    k_fill_u8<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_img, (size_t)W * H, background);
+    if (!rects.empty()) {
+        CK(cudaMalloc(&d_rects, rects.size() * sizeof(RenderRect)));
+        CK(cudaMemcpyAsync(d_rects, rects.data(), rects.size() * sizeof(RenderRect), cudaMemcpyHostToDevice, ctx->stream));
+        int maxs = 1;
+        for (const auto& r : rects) maxs = std::max(maxs, r.size);
+        dim3 grid((unsigned)std::min(1024, (maxs * maxs + 255) / 256), (unsigned)rects.size());
+        k_render_fiducidal<<<grid, 256, 0, ctx->stream>>>(d_img, W, H, d_rects, n_black);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpy2DAsync(out, out_stride, d_img, W, W, H, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_img);
+    if (d_rects) cudaFree(d_rects);
+    return AB_OK;
+}
+
+int ab_create_marker_image(ab_context* ctx, int id, int size, int locked, uint8_t* out, size_t out_stride, int* out_side) {
+    if (!ctx) return AB_E_INVALID;
+    if (id < 0 || id >= 1024) return set_err(ctx, AB_E_INVALID, "createMarkerImage: 0 <= id < 1024");  // CV_Assert, cpp:214
+    if (size < 1 || size > 16384) return set_err(ctx, AB_E_INVALID, "createMarkerImage: bad size");
+    const int sq = locked ? (int)((float)size * 0.25f) : 0;  // cpp:241
+    const int side = size + 2 * sq;
+    if (out_side) *out_side = side;
+    if (!out) return AB_OK;
+    if (out_stride < (size_t)side) return set_err(ctx, AB_E_INVALID, "createMarkerImage: stride too small");
+    std::vector<RenderRect> rects;
+    if (locked) {  // four black squares in the corners of a white canvas (cpp:243-254)
+        rects.push_back(RenderRect{0, 0, sq, 0});
+        rects.push_back(RenderRect{0, side - sq, sq, 0});
+        rects.push_back(RenderRect{side - sq, side - sq, sq, 0});
+        rects.push_back(RenderRect{side - sq, 0, sq, 0});
+    }
+    const int n_black = (int)rects.size();
+    rects.push_back(RenderRect{sq, sq, size, id});
+    return render_canvas(ctx, side, side, locked ? 255 : 0, rects, n_black, out, out_stride);
+}
+
+int ab_create_board_image(ab_context* ctx, int kind, int grid_w, int grid_h, int marker_size, int marker_distance, int center_data,
+                          const int32_t* ids, int n_ids, uint8_t* out, size_t out_stride, int* out_w, int* out_h, int32_t* ids_out,
+                          float* corners_out, int cap, int* n_out) {
+    if (!ctx) return AB_E_INVALID;
+    if (kind < 0 || kind > 2 || grid_w < 1 || grid_h < 1 || marker_size < 7 || marker_distance < 0 || (long long)grid_w * grid_h > 65536)
+        return set_err(ctx, AB_E_INVALID, "createBoardImage: bad arguments");
+    const int dist = kind == 1 ? 0 : marker_distance;  // the chessboard has no gaps
+    const int step = marker_size + dist;
+    const int sizeY = grid_h * marker_size + (grid_h - 1) * dist, sizeX = grid_w * marker_size + (grid_w - 1) * dist;
+    const int centerX = sizeX / 2, centerY = sizeY / 2;
+    if ((long long)sizeX * sizeY > (1ll << 30)) return set_err(ctx, AB_E_INVALID, "createBoardImage: image too large");
+    std::vector<RenderRect> rects;
+    for (int y = 0; y < grid_h; y++) {
+        bool toWrite = (y % 2) != 0;  // chessboard: alternate, starting with a marker on even rows (cpp:355-361)
+        for (int x = 0; x < grid_w; x++) {
+            toWrite = !toWrite;
+            const bool use = kind == 0 ? true : (kind == 1 ? toWrite : (y == 0 || y == grid_h - 1 || x == 0 || x == grid_w - 1));
+            if (use) rects.push_back(RenderRect{x * step, y * step, marker_size, 0});
+        }
+    }
+    const int n = (int)rects.size();
+    if (out_w) *out_w = sizeX;
+    if (out_h) *out_h = sizeY;
+    if (n_out) *n_out = n;
+    if (!out) return AB_OK;
+    if (!ids || n_ids < n) return set_err(ctx, AB_E_INVALID, "createBoardImage: %d marker ids needed", n);
+    if (cap < n || !ids_out || !corners_out) return set_err(ctx, AB_E_CAPACITY, "createBoardImage: room for %d markers needed", n);
+    if (out_stride < (size_t)sizeX) return set_err(ctx, AB_E_INVALID, "createBoardImage: stride too small");
+    const bool center = kind == 0 ? true : center_data != 0;
+    for (int i = 0; i < n; i++) {
+        if (ids[i] < 0 || ids[i] >= 1024) return set_err(ctx, AB_E_INVALID, "createBoardImage: 0 <= id < 1024");
+        rects[i].id = ids[i];
+        ids_out[i] = ids[i];
+        const float x0 = (float)rects[i].x0, y0 = (float)rects[i].y0, s = (float)marker_size;
+        const float c[12] = {x0, y0, 0, x0 + s, y0, 0, x0 + s, y0 + s, 0, x0, y0 + s, 0};
+        for (int k = 0; k < 4; k++) {
+            corners_out[12 * i + 3 * k] = c[3 * k] - (center ? (float)centerX : 0.f);
+            corners_out[12 * i + 3 * k + 1] = c[3 * k + 1] - (center ? (float)centerY : 0.f);
+            corners_out[12 * i + 3 * k + 2] = 0.f;
+        }
+    }
+    return render_canvas(ctx, sizeX, sizeY, 255, rects, 0, out, out_stride);
+}
+
+int ab_create_hrm_marker_image(ab_context* ctx, int n, const uint8_t* bits, int pix_size, uint8_t* out, size_t out_stride, int* out_side) {
+    if (!ctx) return AB_E_INVALID;
+    if (n < 1 || n > 8 || pix_size < 1 || pix_size > 16384) return set_err(ctx, AB_E_INVALID, "getImg: bad arguments");
+    const int nrows = n + 2;
+    if (pix_size % nrows != 0) pix_size = pix_size + nrows - pix_size % nrows;  // hrm.cpp:237-238
+    if (out_side) *out_side = pix_size;
+    if (!out) return AB_OK;
+    if (!bits || out_stride < (size_t)pix_size) return set_err(ctx, AB_E_INVALID, "getImg: bad arguments");
+    cudaSetDevice(ctx->device);
+    uint8_t *d_img = nullptr, *d_bits = nullptr;
+    CK(cudaMalloc(&d_img, (size_t)pix_size * pix_size));
+    CK(cudaMalloc(&d_bits, (size_t)n * n));
+    CK(cudaMemcpyAsync(d_bits, bits, (size_t)n * n, cudaMemcpyHostToDevice, ctx->stream));
+    k_render_hrm<<<std::min(1024, (pix_size * pix_size + 255) / 256), 256, 0, ctx->stream>>>(d_img, pix_size, n, d_bits);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy2DAsync(out, out_stride, d_img, pix_size, pix_size, pix_size, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_img);
+    cudaFree(d_bits);
     return AB_OK;
 }
 

@@ -53,6 +53,32 @@ class FiducidalMarkers:
     def detect(canonical, n_rotations=None):
         raise RuntimeError("FiducidalMarkers.detect runs on the device inside MarkerDetector.detect")
 
+    # generators (src/arucofidmarkers.h:49-88): drawn on the device, see aruco_b200/render.py
+    @staticmethod
+    def createMarkerImage(id, size, addWaterMark=False, locked=False):
+        from . import render
+        return render.createMarkerImage(id, size, addWaterMark, locked)
+
+    @staticmethod
+    def getMarkerMat(id):
+        from . import render
+        return render.getMarkerMat(id)
+
+    @staticmethod
+    def createBoardImage(gridSize, MarkerSize, MarkerDistance, ids):
+        from . import render
+        return render.createBoardImage(gridSize, MarkerSize, MarkerDistance, ids)
+
+    @staticmethod
+    def createBoardImage_ChessBoard(gridSize, MarkerSize, ids, centerData=True):
+        from . import render
+        return render.createBoardImage_ChessBoard(gridSize, MarkerSize, ids, centerData)
+
+    @staticmethod
+    def createBoardImage_Frame(gridSize, MarkerSize, MarkerDistance, ids, centerData=True):
+        from . import render
+        return render.createBoardImage_Frame(gridSize, MarkerSize, MarkerDistance, ids, centerData)
+
 
 class HighlyReliableMarkers:
     """Built-in decoder #2 (src/highlyreliablemarkers.h:190-262). State is process-global like the reference's

@@ -171,6 +171,23 @@ AB_API int ab_detect_board(ab_context* ctx, const ab_marker* markers, int n, con
                            const float* D, float marker_size, float repj_err_thres, int set_y_perpendicular,
                            ab_marker* board_markers, ab_board* out);
 
+/* ---- next row: marker / board rendering on the device ----------------------------------------------------- */
+/* FiducidalMarkers::createMarkerImage (src/arucofidmarkers.cpp:213-263) without the text watermark (cv::putText
+ * glyphs are OpenCV font data: not reproduced, addWaterMark must be false).  The image is square with side
+ * size + 2*int(size*0.25f) when locked, else size; *out_side receives it; out == NULL only queries the side.   */
+AB_API int ab_create_marker_image(ab_context* ctx, int id, int size, int locked, uint8_t* out, size_t out_stride, int* out_side);
+/* createBoardImage (kind 0, :283-329), createBoardImage_ChessBoard (kind 1, :337-389), createBoardImage_Frame (kind 2,
+ * :397-436) for a caller-supplied id list (the reference draws the ids with rand()).  Returns the image
+ * (*out_w x *out_h; out == NULL only queries the size and the marker count) and the BoardConfiguration in pixels:
+ * ids_out[i], corners_out[12*i..] (4 x (x,y,0)), *n_out markers.  kind 0 always centres the coordinates.          */
+AB_API int ab_create_board_image(ab_context* ctx, int kind, int grid_w, int grid_h, int marker_size, int marker_distance,
+                                 int center_data, const int32_t* ids, int n_ids, uint8_t* out, size_t out_stride, int* out_w,
+                                 int* out_h, int32_t* ids_out, float* corners_out, int cap, int* n_out);
+/* MarkerCode::getImg (src/highlyreliablemarkers.cpp:234-256): bits = n*n bytes (row-major, non-zero = white); pix_size
+ * is rounded up to a multiple of n+2; *out_side receives the side; out == NULL only queries it.                   */
+AB_API int ab_create_hrm_marker_image(ab_context* ctx, int n, const uint8_t* bits, int pix_size, uint8_t* out, size_t out_stride,
+                                      int* out_side);
+
 /* pinned host memory for frame staging */
 AB_API int ab_host_alloc(void** ptr, size_t bytes);
 AB_API int ab_host_free(void* ptr);

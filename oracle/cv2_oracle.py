@@ -614,3 +614,72 @@ def board_detect(markers, board_cfg: dict, K=None, D=None, marker_size: float = 
         rvec = rotate_x_axis(rvec)
     out.update(prob=len(sel) / len(ids), rvec=rvec, tvec=tvec.reshape(3).astype(np.float64))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Marker / board generators: numpy restatement, pinned by the reference's own PNGs
+# (testdata/board/{marker,locked-marker}-expected.png, board.png, chessboard/chessboard.png; tests/golden/render.npz)
+# ---------------------------------------------------------------------------------------------------------
+def create_marker_image(marker_id, size, locked=False):
+    """FiducidalMarkers::createMarkerImage without the watermark (src/arucofidmarkers.cpp:213-263)."""
+    assert 0 <= marker_id < 1024
+    m = np.zeros((size, size), np.uint8)
+    sw = size // 7
+    words = [0x10, 0x17, 0x09, 0x0E]
+    for y in range(5):
+        val = words[(marker_id >> (2 * (4 - y))) & 3]
+        for x in range(5):
+            if (val >> (4 - x)) & 1:
+                m[(y + 1) * sw:(y + 2) * sw, (x + 1) * sw:(x + 2) * sw] = 255
+    if locked:
+        sq = int(np.float32(size) * np.float32(0.25))
+        big = np.full((size + 2 * sq, size + 2 * sq), 255, np.uint8)
+        big[:sq, :sq] = 0
+        big[big.shape[0] - sq:, :sq] = 0
+        big[big.shape[0] - sq:, big.shape[1] - sq:] = 0
+        big[:sq, big.shape[1] - sq:] = 0
+        big[sq:sq + size, sq:sq + size] = m
+        m = big
+    return m
+
+
+def create_board_image(kind, grid_w, grid_h, marker_size, marker_distance, ids, center=True):
+    """kind 0: createBoardImage (:283-329, always centred), 1: _ChessBoard (:337-389), 2: _Frame (:397-436).
+    Returns (image, ids used, corners [n,4,3] f32)."""
+    dist = 0 if kind == 1 else marker_distance
+    step = marker_size + dist
+    size_y = grid_h * marker_size + (grid_h - 1) * dist
+    size_x = grid_w * marker_size + (grid_w - 1) * dist
+    cx, cy = size_x // 2, size_y // 2
+    img = np.full((size_y, size_x), 255, np.uint8)
+    used, corners, k = [], [], 0
+    for y in range(grid_h):
+        to_write = (y % 2) != 0
+        for x in range(grid_w):
+            to_write = not to_write
+            use = True if kind == 0 else (to_write if kind == 1 else (y in (0, grid_h - 1) or x in (0, grid_w - 1)))
+            if not use:
+                continue
+            img[y * step:y * step + marker_size, x * step:x * step + marker_size] = create_marker_image(ids[k], marker_size)
+            x0, y0, s = float(x * step), float(y * step), float(marker_size)
+            c = np.array([[x0, y0, 0], [x0 + s, y0, 0], [x0 + s, y0 + s, 0], [x0, y0 + s, 0]], np.float32)
+            if kind == 0 or center:
+                c -= np.array([cx, cy, 0], np.float32)
+            used.append(int(ids[k]))
+            corners.append(c)
+            k += 1
+    return img, used, np.array(corners, np.float32).reshape(-1, 4, 3)
+
+
+def hrm_marker_image(bits, n, pix_size):
+    """MarkerCode::getImg (src/highlyreliablemarkers.cpp:234-256); bits: n*n 0/1 row-major."""
+    nrows = n + 2
+    if pix_size % nrows != 0:
+        pix_size = pix_size + nrows - pix_size % nrows
+    cell = pix_size // nrows
+    img = np.zeros((pix_size, pix_size), np.uint8)
+    for i in range(n):
+        for j in range(n):
+            if bits[i * n + j]:
+                img[(i + 1) * cell:(i + 2) * cell, (j + 1) * cell:(j + 2) * cell] = 255
+    return img

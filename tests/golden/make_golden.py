@@ -90,6 +90,13 @@ def main():
     exp["boards"]["chessboard_meters"] = read_board_cfg(os.path.join(REF, "chessboard/chessboardinfo_meters.yml"))
     with open(os.path.join(OUT, "expected.json"), "w") as f:
         json.dump(exp, f, indent=1)
+    # the reference's generator goldens (Aruco.CreateMarker, test/core_tests.cpp:32-75, and the printed boards)
+    render = {}
+    for key, rel in [("marker_471_500", "board/marker-expected.png"), ("locked_marker_471_500", "board/locked-marker-expected.png"),
+                     ("board_4x6_150_30", "board/board.png"), ("chessboard_5x7_300", "chessboard/chessboard.png"),
+                     ("hrm_board4x4", "hrm/boards/board4x4.png")]:
+        render[key] = cv2.imread(os.path.join(REF, rel), cv2.IMREAD_GRAYSCALE)
+    np.savez_compressed(os.path.join(OUT, "render.npz"), **render)
     # raw YAML wire-format fixtures for the C++ reader/writer (tests/test_yaml.py): test DATA, byte for byte
     ydir = os.path.join(OUT, "yaml")
     os.makedirs(ydir, exist_ok=True)

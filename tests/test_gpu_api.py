@@ -144,6 +144,31 @@ def test_cpp_facade_aruco_simple_board_from_yaml(built, frames, expected, name, 
         assert np.abs(got - np.array(m["corners"])).max() < 0.01
 
 
+def test_cpp_facade_aruco_create_board(built, expected, tmp_path):
+    """Headless utils/aruco_create_board.cpp on the C++ facade: the image equals the reference's printed board
+    (testdata/board/board.png), the YAML it writes is read back by cv::FileStorage with board_pix.yml's layout scaled to
+    150-pixel markers, and the board is detected in its own picture."""
+    import os
+    import subprocess
+    import cv2
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "tests", "_build", "aruco_create_board")
+    ids = [m["id"] for m in expected["boards"]["board_pix"]["markers"]]
+    raw, yml = tmp_path / "board.raw", tmp_path / "board.yml"
+    r = subprocess.run([exe, "4", "6", "150", "0", "30", str(raw), str(yml)] + [str(i) for i in ids], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    w, h, n, found, prob = r.stdout.split()
+    assert (int(w), int(h), int(n), int(found), float(prob)) == (690, 1050, 24, 24, 1.0)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "render.npz"))["board_4x6_150_30"]
+    assert np.array_equal(np.fromfile(str(raw), np.uint8).reshape(1050, 690), gold)
+    fs = cv2.FileStorage(str(yml), cv2.FILE_STORAGE_READ)
+    ms = fs.getNode("aruco_bc_markers")
+    assert int(fs.getNode("aruco_bc_mInfoType").real()) == 0 and [int(ms.at(i).getNode("id").real()) for i in range(ms.size())] == ids
+    c0 = ms.at(0).getNode("corners")
+    want0 = np.array(expected["boards"]["board_pix"]["markers"][0]["corners"]) * 1.5  # same layout, 150 instead of 100 pixels
+    assert np.array_equal(np.array([[c0.at(k).at(d).real() for d in range(3)] for k in range(4)]), want0)
+
+
 @pytest.mark.parametrize("name,cfgname", [("board", "board_pix"), ("chessboard", "chessboard_pix")])
 def test_board_detector_goldens(built, frames, expected, name, cfgname):
     """Aruco.Board / Aruco.Multi (test/core_tests.cpp:164-228) through the device: detect without camera, then
