@@ -323,8 +323,13 @@ def main():
     alg_bytes = {"threshold": 2.0 * W * H * B, "scan_starts": packed, "trace": packed, "trace_long": packed, "emit": packed}.get(dom, 3.0 * W * H * B)
     achieved = alg_bytes / (kernel_ms[dom] / 1e3) / 1e9
     thr_gbs = 2.0 * W * H * B / (kernel_ms["threshold"] / 1e3) / 1e9
+    # DRAM bytes per launch of the threshold kernel from the committed ncu --set full capture of this command
+    # (profiles/r1p_ncu_threshold_pair_raw.csv: dram__bytes_read.sum 2.238 GB + dram__bytes_write.sum 2.361 GB at 256 x 4K);
+    # only quoted for the workload it was captured on
+    traffic = 4.599e9 if (dom == "threshold" and B == BATCH) else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": kernel_ms,
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/r1p_ncu_threshold_pair_raw.csv)",
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "kernel_ms": kernel_ms,
                 "threshold_kernel": {"achieved": thr_gbs, "frac": thr_gbs / peak},
                 "whole_path": {"algorithmic_bytes_per_frame": 3 * W * H, "achieved": fps / world * 3 * W * H / 1e9,
                                "frac": fps / world * 3 * W * H / 1e9 / peak}}

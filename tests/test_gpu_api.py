@@ -41,13 +41,16 @@ def test_defaults_and_setters_mirror_the_reference(built):
         d.warp(np.zeros((20, 20), np.uint8), 56, [[0, 0], [1, 0], [1, 1]])
 
 
-@pytest.mark.parametrize("method,p1,p2", [(1, 7, 7), (1, -1, -1), (1, 2, 7), (1, 8, 6.5), (1, 21, 7), (1, 35, 3), (1, 61, 0), (0, 100, 0), (0, 127.5, 0), (2, 0, 0)])
+@pytest.mark.parametrize("method,p1,p2", [(1, 7, 7), (1, -1, -1), (1, 2, 7), (1, 8, 6.5), (1, 21, 7), (1, 35, 3), (1, 61, 0), (0, 100, 0), (0, 127.5, 0), (2, 0, 0),
+                                          # lane-paired kernel (K <= 11 while K^2*255 + |K^2*delta| < 2^15) and its fallbacks
+                                          (1, 3, 7), (1, 5, 0), (1, 9, 7), (1, 11, 7), (1, 11, 20), (1, 7, -7), (1, 7, 300), (1, 7, -300), (1, 13, 7)])
 def test_threshold_worker_bit_exact(det, frames, method, p1, p2):
     from oracle import native
     import ctypes as C
     lib = native.load()
     rng = np.random.default_rng(1)
-    for img in (frames["hrm"], rng.integers(0, 256, (97, 131), dtype=np.uint8), rng.integers(0, 256, (480, 1000), dtype=np.uint8)):
+    for img in (frames["hrm"], rng.integers(0, 256, (97, 131), dtype=np.uint8), rng.integers(0, 256, (480, 1000), dtype=np.uint8),
+                rng.integers(0, 256, (131, 1536), dtype=np.uint8), rng.integers(100, 140, (300, 16), dtype=np.uint8)):
         img = np.ascontiguousarray(img)
         got = det.thresHold(method, img, p1, p2)
         q1, q2 = (7.0 if p1 == -1 else p1), (7.0 if p2 == -1 else p2)
