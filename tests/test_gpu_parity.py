@@ -107,6 +107,8 @@ GOLDEN_CASES = [
     ("single", dict(p1_range=1, thres_method=0, p1=100), True), ("board", dict(p1_range=1, erosion=True), False),
     # ThresholdMethods::CANNY (cv::Canny(10, 220), markerdetector.cpp:664-675)
     ("single", dict(thres_method=2), True), ("board", dict(thres_method=2), True), ("chessboard", dict(thres_method=2, corner_method=2), True),
+    # warp sizes whose S*S is not a multiple of 4 / of 7 (byte path of the canonical-image writer, ragged cells)
+    ("single", dict(warp_size=57), True), ("board", dict(warp_size=35, corner_method=0), False), ("chessboard", dict(warp_size=99), True),
 ]
 
 
