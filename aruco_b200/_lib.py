@@ -76,6 +76,8 @@ SYMBOLS = {
     "ab_create_board_image": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _sz, C.POINTER(C.c_int), C.POINTER(C.c_int), _vp, _vp, _i,
                                    C.POINTER(C.c_int)]),
     "ab_create_hrm_marker_image": (_i, [_vp, _i, _vp, _i, _vp, _sz, C.POINTER(C.c_int)]),
+    "ab_create_hrm_board_image": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _sz, C.POINTER(C.c_int), C.POINTER(C.c_int), _vp, _vp, _i,
+                                       C.POINTER(C.c_int)]),
     "ab_host_alloc": (_i, [C.POINTER(_vp), _sz]),
     "ab_host_free": (_i, [_vp]),
 }

@@ -1252,6 +1252,56 @@ int ab_create_hrm_marker_image(ab_context* ctx, int n, const uint8_t* bits, int 
     return AB_OK;
 }
 
+int ab_create_hrm_board_image(ab_context* ctx, int grid_w, int grid_h, int n, const uint8_t* bits, int count, uint8_t* out,
+                              size_t out_stride, int* out_w, int* out_h, int32_t* ids_out, float* corners_out, int cap, int* n_out) {
+    if (!ctx) return AB_E_INVALID;
+    if (grid_w < 1 || grid_h < 1 || n < 1 || n > 8 || (long long)grid_w * grid_h > 65536) return set_err(ctx, AB_E_INVALID, "createBoardImage: bad arguments");
+    const int ms = (n + 2) * 20, md = ms / 5;  // hrm.cpp:500-501
+    const int sizeY = grid_h * ms + (grid_h - 1) * md, sizeX = grid_w * ms + (grid_w - 1) * md;
+    const float centerX = (float)(sizeX / 2.), centerY = (float)(sizeY / 2.);
+    const int nm = grid_w * grid_h;
+    if (out_w) *out_w = sizeX;
+    if (out_h) *out_h = sizeY;
+    if (n_out) *n_out = nm;
+    if (!out) return AB_OK;
+    if (!bits || count < nm) return set_err(ctx, AB_E_INVALID, "createBoardImage: the dictionary has %d markers, %d needed", count, nm);
+    if (cap < nm || !ids_out || !corners_out) return set_err(ctx, AB_E_CAPACITY, "createBoardImage: room for %d markers needed", nm);
+    if (out_stride < (size_t)sizeX) return set_err(ctx, AB_E_INVALID, "createBoardImage: stride too small");
+    std::vector<RenderRect> rects;
+    int idp = 0;
+    for (int y = 0; y < grid_h; y++)
+        for (int x = 0; x < grid_w; x++, idp++) {
+            rects.push_back(RenderRect{x * (md + ms), y * (md + ms), ms, idp});
+            uint8_t code[64];
+            for (int i = 0; i < n * n; i++) code[i] = bits[(size_t)idp * n * n + i] != 0;
+            uint64_t rb[4];
+            uint32_t rid[4];
+            hrm_rotations(code, n, rb, rid);
+            ids_out[idp] = (int32_t)rid[0];  // MarkerCode::getId()
+            const float x0 = (float)(x * (md + ms)) - centerX, y0 = (float)(y * (md + ms)) - centerY, s = (float)ms;
+            // y negated so that the z axis points up (hrm.cpp:536-540)
+            const float c[12] = {x0, -y0, 0, x0 + s, -y0, 0, x0 + s, -(y0 + s), 0, x0, -(y0 + s), 0};
+            for (int k = 0; k < 12; k++) corners_out[12 * idp + k] = c[k];
+        }
+    cudaSetDevice(ctx->device);
+    uint8_t *d_img = nullptr, *d_bits = nullptr;
+    RenderRect* d_rects = nullptr;
+    CK(cudaMalloc(&d_img, (size_t)sizeX * sizeY));
+    CK(cudaMalloc(&d_bits, (size_t)nm * n * n));
+    CK(cudaMalloc(&d_rects, rects.size() * sizeof(RenderRect)));
+    CK(cudaMemcpyAsync(d_bits, bits, (size_t)nm * n * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_rects, rects.data(), rects.size() * sizeof(RenderRect), cudaMemcpyHostToDevice, ctx->stream));
+    k_fill_u8<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_img, (size_t)sizeX * sizeY, 255);
+    k_render_hrm_board<<<dim3((unsigned)((ms * ms + 255) / 256), (unsigned)nm), 256, 0, ctx->stream>>>(d_img, sizeX, sizeY, d_rects, n, d_bits);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy2DAsync(out, out_stride, d_img, sizeX, sizeX, sizeY, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_img);
+    cudaFree(d_bits);
+    cudaFree(d_rects);
+    return AB_OK;
+}
+
 int ab_calculate_extrinsics(ab_context* ctx, ab_marker* markers, int n, const float* K, const float* D, float marker_size,
                             int set_y_perp) {
     if (!ctx || !markers || n < 0 || !K || !(marker_size > 0)) return set_err(ctx, AB_E_INVALID, "calculateExtrinsics: invalid arguments");

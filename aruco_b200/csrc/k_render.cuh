@@ -50,4 +50,18 @@ __global__ void k_render_hrm(uint8_t* img, int pix, int n, const uint8_t* bits) 
     }
 }
 
+// HighlyReliableMarkers::createBoardImage (src/highlyreliablemarkers.cpp:498-545): rect.id indexes the dictionary;
+// every marker is MarkerCode::getImg at side rect.size (a multiple of n+2 by construction)
+__global__ void k_render_hrm_board(uint8_t* img, int W, int H, const RenderRect* rects, int n, const uint8_t* bits) {
+    const RenderRect r = rects[blockIdx.y];
+    const int cell = r.size / (n + 2);
+    const uint8_t* code = bits + (size_t)r.id * n * n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < r.size * r.size; i += gridDim.x * blockDim.x) {
+        const int py = i / r.size, px = i - py * r.size;
+        const int cy = py / cell - 1, cx = px / cell - 1;
+        const int X = r.x0 + px, Y = r.y0 + py;
+        if (X < W && Y < H) img[(size_t)Y * W + X] = (cy >= 0 && cy < n && cx >= 0 && cx < n && code[cy * n + cx]) ? 255 : 0;
+    }
+}
+
 }  // namespace ab

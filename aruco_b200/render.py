@@ -89,3 +89,23 @@ def hrmMarkerImage(code, pixSize: int, device: int = 0) -> np.ndarray:
     d._check(d._lib.ab_create_hrm_marker_image(d._h, n, bits.ctypes.data_as(C.c_void_p), int(pixSize), out.ctypes.data_as(C.c_void_p),
                                                side.value, C.byref(side)))
     return out
+
+
+def hrmCreateBoardImage(gridSize, codes: Sequence[str], device: int = 0):
+    """HighlyReliableMarkers::createBoardImage (highlyreliablemarkers.cpp:498-545), non-chromatic.  codes: the dictionary's
+    n*n strings of '0'/'1' (the first gridSize.width * gridSize.height are drawn).  Returns (image, BoardConfiguration in
+    pixels, ids = MarkerCode::getId())."""
+    gw, gh = int(gridSize[0]), int(gridSize[1])
+    bits = np.array([[c == "1" for c in code] for code in codes], np.uint8)
+    n = int(round(np.sqrt(bits.shape[1])))
+    d = _det(device)
+    w, h, nm = C.c_int(0), C.c_int(0), C.c_int(0)
+    d._check(d._lib.ab_create_hrm_board_image(d._h, gw, gh, n, None, 0, None, 0, C.byref(w), C.byref(h), None, None, 0, C.byref(nm)))
+    img = np.empty((h.value, w.value), np.uint8)
+    ids = np.zeros(nm.value, np.int32)
+    corners = np.zeros((nm.value, 4, 3), np.float32)
+    bits = np.ascontiguousarray(bits)
+    d._check(d._lib.ab_create_hrm_board_image(d._h, gw, gh, n, bits.ctypes.data_as(C.c_void_p), int(bits.shape[0]), img.ctypes.data_as(C.c_void_p),
+                                              w.value, C.byref(w), C.byref(h), ids.ctypes.data_as(C.c_void_p), corners.ctypes.data_as(C.c_void_p),
+                                              nm.value, C.byref(nm)))
+    return img, BoardConfiguration(ids.tolist(), corners, BoardConfiguration.PIX)

@@ -188,6 +188,14 @@ AB_API int ab_create_board_image(ab_context* ctx, int kind, int grid_w, int grid
 AB_API int ab_create_hrm_marker_image(ab_context* ctx, int n, const uint8_t* bits, int pix_size, uint8_t* out, size_t out_stride,
                                       int* out_side);
 
+/* HighlyReliableMarkers::createBoardImage (src/highlyreliablemarkers.cpp:498-545) without the chromatic variant: a
+ * grid_w x grid_h grid of the first grid_w*grid_h dictionary markers (bits: count*n*n bytes, row-major), marker side
+ * (n+2)*20, gap side/5; ids_out = MarkerCode::getId() (the folded id of rotation 0), corners centred with y negated.
+ * out == NULL only queries the size and the marker count.                                                        */
+AB_API int ab_create_hrm_board_image(ab_context* ctx, int grid_w, int grid_h, int n, const uint8_t* bits, int count, uint8_t* out,
+                                     size_t out_stride, int* out_w, int* out_h, int32_t* ids_out, float* corners_out, int cap,
+                                     int* n_out);
+
 /* pinned host memory for frame staging */
 AB_API int ab_host_alloc(void** ptr, size_t bytes);
 AB_API int ab_host_free(void* ptr);

@@ -683,3 +683,24 @@ def hrm_marker_image(bits, n, pix_size):
             if bits[i * n + j]:
                 img[(i + 1) * cell:(i + 2) * cell, (j + 1) * cell:(j + 2) * cell] = 255
     return img
+
+
+def hrm_create_board_image(grid_w, grid_h, codes, n):
+    """HighlyReliableMarkers::createBoardImage, non-chromatic (src/highlyreliablemarkers.cpp:498-545).
+    codes: list of n*n '0'/'1' strings.  Returns (image, ids = MarkerCode::getId(), corners [m,4,3] f32)."""
+    ms = (n + 2) * 20
+    md = ms // 5
+    size_y = grid_h * ms + (grid_h - 1) * md
+    size_x = grid_w * ms + (grid_w - 1) * md
+    cx, cy = np.float32(size_x / 2.), np.float32(size_y / 2.)
+    img = np.full((size_y, size_x), 255, np.uint8)
+    ids, corners, k = [], [], 0
+    for y in range(grid_h):
+        for x in range(grid_w):
+            bits = [c == "1" for c in codes[k]]
+            img[y * (ms + md):y * (ms + md) + ms, x * (ms + md):x * (ms + md) + ms] = hrm_marker_image(bits, n, ms)
+            ids.append(int(code_rotations(np.array(bits, np.uint8).reshape(n, n))[1][0]))  # MarkerCode::getId(): `2 << pos` fold
+            x0, y0, s = np.float32(x * (ms + md)) - cx, np.float32(y * (ms + md)) - cy, np.float32(ms)
+            corners.append([[x0, -y0, 0], [x0 + s, -y0, 0], [x0 + s, -(y0 + s), 0], [x0, -(y0 + s), 0]])
+            k += 1
+    return img, ids, np.array(corners, np.float32)

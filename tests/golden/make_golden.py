@@ -103,7 +103,7 @@ def main():
     for rel in ("single/intrinsics.yml", "single/expected.yml", "hrm/expected.yml", "hrm/intrinsics.yml", "board/expected.yml",
                 "board/board_pix.yml", "board/board_meters.yml", "board/intrinsics.yml", "chessboard/expected.yml",
                 "chessboard/chessboardinfo_pix.yml", "chessboard/intrinsics.yml", "hrm/dictionaries/d4x4_100.yml",
-                "hrm/dictionaries/d6x6_100.yml", "mask/dictionary.yml"):
+                "hrm/dictionaries/d6x6_100.yml", "mask/dictionary.yml", "hrm/boards/board4x4.yml"):
         with open(os.path.join(REF, rel), "rb") as f:
             data = f.read()
         with open(os.path.join(ydir, rel.replace("/", "__")), "wb") as f:

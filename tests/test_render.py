@@ -28,6 +28,30 @@ def test_oracle_generators_reproduce_the_reference_pngs(render_goldens, expected
     assert np.array_equal(img, render_goldens["chessboard_5x7_300"]) and used == board_ids(expected, "chessboard_pix")
 
 
+def hrm_codes(expected, name="d4x4_100"):
+    return [l.split('"')[1] for l in expected["dictionaries"][name].splitlines() if l.startswith("marker_")]
+
+
+def read_board_yaml(name):
+    import cv2
+    fs = cv2.FileStorage(os.path.join(ROOT, "tests", "golden", "yaml", name), cv2.FILE_STORAGE_READ)
+    ms = fs.getNode("aruco_bc_markers")
+    ids = [int(ms.at(i).getNode("id").real()) for i in range(ms.size())]
+    corners = np.array([[[ms.at(i).getNode("corners").at(k).at(d).real() for d in range(3)] for k in range(4)] for i in range(ms.size())], np.float32)
+    return ids, corners
+
+
+def test_oracle_hrm_board_reproduces_the_reference_png_and_yaml(render_goldens, expected):
+    """testdata/hrm/boards/board4x4.{png,yml} = HighlyReliableMarkers::createBoardImage(4x4, d4x4_100).  The shipped YAML was
+    written when MarkerCode folded ids with 1 << pos; the current source folds with 2 << pos (highlyreliablemarkers.cpp:176,
+    SURVEY B.4), so today's getId() is exactly twice the stored id."""
+    from oracle import cv2_oracle as o
+    img, ids, corners = o.hrm_create_board_image(4, 4, hrm_codes(expected), 4)
+    want_ids, want_c = read_board_yaml("hrm__boards__board4x4.yml")
+    assert np.array_equal(img, render_goldens["hrm_board4x4"]) and np.array_equal(corners, want_c)
+    assert ids == [2 * i for i in want_ids]
+
+
 def test_oracle_board_configuration_matches_the_reference_yaml(expected):
     """board_pix.yml was written by createBoardImage(4x6, 100, 20): same ids -> same corner coordinates."""
     from oracle import cv2_oracle as o
@@ -102,6 +126,21 @@ def test_device_hrm_marker_image_and_round_trip(built, expected):
         assert [mk.id for mk in det.detect(page)] == [42]
     finally:
         HighlyReliableMarkers._dict = saved
+
+
+@pytest.mark.gpu
+def test_device_hrm_board_image(built, render_goldens, expected):
+    from aruco_b200 import render
+    from oracle import cv2_oracle as o
+    img, cfg = render.hrmCreateBoardImage((4, 4), hrm_codes(expected))
+    want_ids, want_c = read_board_yaml("hrm__boards__board4x4.yml")
+    assert np.array_equal(img, render_goldens["hrm_board4x4"]) and np.array_equal(cfg.objPoints, want_c)
+    assert cfg.ids == [2 * i for i in want_ids]
+    codes6 = hrm_codes(expected, "d6x6_100")
+    img, cfg = render.hrmCreateBoardImage((5, 3), codes6)
+    want_img, want_ids6, want_c6 = o.hrm_create_board_image(5, 3, codes6, 6)
+    # BoardConfiguration::ids is vector<int>: getId() (unsigned) above 2^31 wraps negative, compare modulo 2^32
+    assert np.array_equal(img, want_img) and [i & 0xFFFFFFFF for i in cfg.ids] == want_ids6 and np.array_equal(cfg.objPoints, want_c6)
 
 
 @pytest.mark.gpu
