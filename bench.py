@@ -126,7 +126,7 @@ def run_reference(args):
     from oracle import native
     native.load()
     threads = host_threads()
-    sample = max(threads, 16)
+    sample = max(2 * threads, 32)  # frames per step: ~2-3 CPU-seconds per step on every thread
     rng = np.random.default_rng(7)
     scenes = base_scenes(min(N_BASE, 4), 0)
     frames = np.stack([np.clip(np.rint(scenes[i % len(scenes)] + rng.normal(0, SIGMA, (H, W)).astype(np.float32)), 0, 255).astype(np.uint8)
@@ -362,7 +362,7 @@ def main():
     if not args.skip_cpu:
         from oracle import native
         threads = host_threads()
-        sample = max(2 * threads, 32)
+        sample = min(B, 256)  # the whole batch: ~20 CPU-seconds of work spread over the host threads
         hostf = frames[:sample].cpu().numpy()
         native.detect_batch(hostf[:threads], oracle_params(), K, D, MARKER_SIZE, threads=threads)
         t0 = time.perf_counter()
