@@ -206,6 +206,8 @@ int ab_create(int device, ab_context** out) {
     }
     if (const char* e = getenv("ARUCO_B200_SUBBATCHES")) ctx->n_sub_streams = std::max(1, std::min(MAX_SUB, atoi(e)));
     // walker grids in CTAs per SM (tuning knobs for variant studies)
+    // capacity of the parked-walk queue per frame (tests shrink it to exercise the finish-in-place path)
+    if (const char* e = getenv("ARUCO_B200_CAP_LONG")) ctx->capLongPF = (unsigned)std::max(1, atoi(e));
     if (const char* e = getenv("ARUCO_B200_GRID_TRACE")) ctx->grid_trace = std::max(1, atoi(e));
     if (const char* e = getenv("ARUCO_B200_GRID_LONG")) ctx->grid_long = std::max(1, atoi(e));
     if (const char* e = getenv("ARUCO_B200_GRID_EMIT")) ctx->grid_emit = std::max(1, atoi(e));

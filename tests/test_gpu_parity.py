@@ -180,6 +180,24 @@ def test_synthetic_configs_all_stages(det, W, H, n, seed, sigma, kw):
         assert len(ms) >= 0.9 * n and set(m.id for m in ms) <= set(truth["ids"])
 
 
+def test_parked_walk_queue_overflow_finishes_in_place(built, monkeypatch):
+    """When the queue of parked long walks is full, k_trace<false> finishes the walk itself and k_emit (two walkers per
+    contour) writes it: same markers, same contours as with the default capacity (12-walker k_emit_long path)."""
+    from aruco_b200 import MarkerDetector, synth
+    g, _ = synth.render_frame(1920, 1080, 50, 21, 2.0)
+    K, D = synth.camera_for(1920, 1080)
+    ref_det = MarkerDetector()
+    ref = ref_det.detect(g, K, D, 0.05)
+    ref_contours = [ref_det.getContour(0, i) for i in range(len(ref_det.getAllCandidates(0)[0]))]
+    monkeypatch.setenv("ARUCO_B200_CAP_LONG", "3")
+    small = MarkerDetector()
+    got = small.detect(g, K, D, 0.05)
+    assert len(ref) >= 45 and [m.id for m in got] == [m.id for m in ref]
+    assert all((a.corners == b.corners).all() and (a.Rvec == b.Rvec).all() for a, b in zip(got, ref))
+    got_contours = [small.getContour(0, i) for i in range(len(small.getAllCandidates(0)[0]))]
+    assert len(got_contours) == len(ref_contours) and all((a == b).all() for a, b in zip(got_contours, ref_contours))
+
+
 @pytest.mark.parametrize("n,flips", [(4, 0), (5, 1), (6, 2), (8, 4)])
 def test_hrm_synthetic_4k_with_bit_flips(det, expected, n, flips):
     """C5: HRM dictionaries on synthetic 4K frames; bit flips exercise the correction radius."""
