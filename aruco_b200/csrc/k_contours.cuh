@@ -1,8 +1,10 @@
 // Stage 2a: border extraction (replaces cv::findContours(RETR_LIST, CHAIN_APPROX_NONE),
 // src/markerdetector.cpp:510-511, and the length filter at :517).  See ab_trace.cuh for the algorithm.
-//   k_scan_starts: bitwise scan of the packed image for start candidates (one thread per 32-pixel word)
-//   k_trace:       one thread per candidate walks its border cycle; the Suzuki start of every border with
-//                  min_len < n < max_len re-walks it and writes the ordered points into the pool.
+//   k_scan_starts:  bitwise scan of the tiled packed image for start candidates (one thread per word column x 4 rows)
+//   k_trace<false>: one lane per candidate walks its border cycle in both directions; walks alive after 48 iterations
+//                   are parked.  k_trace<true> finishes the parked walks.  The Suzuki start of every border with
+//                   min_len < n < max_len reserves its slice of the point pool and leaves a contour record.
+//   k_emit_long / k_emit: re-walk the kept contours and write their ordered points (12 / 2 walkers per contour).
 #pragma once
 #include "ab_device.cuh"
 
