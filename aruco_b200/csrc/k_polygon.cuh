@@ -87,19 +87,41 @@ __global__ void __launch_bounds__(128) k_polygon(Batch b) {
             bool le = true;
             int split = 0;
             if (m > 0) {
-                unsigned long long bd = 0;  // bit pattern of a non-negative double orders like the value
-                int bi = 0x7FFFFFFF;
+                // seg_dist2 (ab_math.cuh) on integers.  Coordinates are < 2^14, so t, dd, the cross product c and the
+                // end-point distances are exact in int32.  Points that project inside the segment have distance c*c/dd:
+                // for one segment that is ordered exactly like |c| (distinct |c| differ by >= 2^-28 relative, far above
+                // the rounding of the f64 quotient; equal |c| give equal quotients), so only the lane's best inside
+                // point pays for the f64 division (it was 13 % of the kernel's instructions, ncu r1o).
+                const int dxi = ex - sx, dyi = ey - sy, ddi = dxi * dxi + dyi * dyi;
+                int best_c = 0, best_ci = 0x7FFFFFFF, best_o = 0, best_oi = 0x7FFFFFFF;
                 for (int i = lane; i < m; i += 32) {
                     int q = s + 1 + i;
                     if (q >= n) q -= n;
-                    uint32_t pp = pts[q];
-                    double d = seg_dist2((int)(pp & 0xFFFFu), (int)(pp >> 16), sx, sy, ex, ey);
-                    unsigned long long db = (unsigned long long)__double_as_longlong(d);
-                    if (d > 0 && db > bd) {
-                        bd = db;
-                        bi = i;
+                    const uint32_t pp = pts[q];
+                    const int px = (int)(pp & 0xFFFFu), py = (int)(pp >> 16);
+                    const int qx = px - sx, qy = py - sy;
+                    const int tt = qx * dxi + qy * dyi;
+                    if (tt < 0 || tt > ddi) {
+                        const int fx = tt < 0 ? qx : px - ex, fy = tt < 0 ? qy : py - ey;
+                        const int v = fx * fx + fy * fy;
+                        if (v > best_o) {
+                            best_o = v;
+                            best_oi = i;
+                        }
+                    } else {
+                        const int c = abs(qx * dyi - qy * dxi);
+                        if (c > best_c) {
+                            best_c = c;
+                            best_ci = i;
+                        }
                     }
                 }
+                // the lane's first strict maximum over both kinds of points
+                const double d_in = best_c ? ((double)best_c * (double)best_c) / (double)ddi : 0.0, d_out = (double)best_o;
+                const bool take_in = d_in > d_out || (d_in == d_out && best_ci < best_oi);
+                const double dbest = take_in ? d_in : d_out;
+                unsigned long long bd = dbest > 0 ? (unsigned long long)__double_as_longlong(dbest) : 0ull;  // bit pattern of a non-negative double orders like the value
+                int bi = dbest > 0 ? (take_in ? best_ci : best_oi) : 0x7FFFFFFF;
 #pragma unroll
                 for (int dlt = 16; dlt > 0; dlt >>= 1) {
                     unsigned long long od = __shfl_xor_sync(0xFFFFFFFFu, bd, dlt);
