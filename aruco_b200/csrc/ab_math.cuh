@@ -313,6 +313,8 @@ struct Camera {
     double k1, k2, p1, p2, k3;
     float fxf, fyf, cxf, cyf;
     int has_K, has_D;
+    int zero_D;  // all distortion coefficients are 0: cv::undistortPoints is then the identity on pixel coordinates
+                 // after its f32 rounding ((u - cx) / fx * fx + cx is within 1e-12 of u, f32 spacing is >= 6e-5)
 };
 
 // cv::undistortPoints(src, K, D, R=I, P=K): 5 fixed-point iterations, result rounded to f32

@@ -458,6 +458,7 @@ static Camera make_camera(const float* K, const float* D) {
         c.p1 = D[2];
         c.p2 = D[3];
         c.k3 = D[4];
+        c.zero_D = D[0] == 0.f && D[1] == 0.f && D[2] == 0.f && D[3] == 0.f && D[4] == 0.f;
     }
     return c;
 }

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) k_refine_lines(Batch b) {
             if (j < 0) j += n;
             uint32_t p = rev ? pts[n - 1 - j] : pts[j];
             float x = (float)(p & 0xFFFFu), y = (float)(p >> 16);
-            if (undist) undistort_point_px(b.cam, x, y, &x, &y);
+            if (undist && !b.cam.zero_D) undistort_point_px(b.cam, x, y, &x, &y);  // contour points are integer pixels
             mnx = fminf(mnx, x);
             mxx = fmaxf(mxx, x);
             mny = fminf(mny, y);
