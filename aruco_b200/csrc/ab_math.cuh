@@ -337,7 +337,7 @@ AB_HD void undistort_point_px(const Camera& c, float u, float v, float* ou, floa
 AB_HD void undistort_point_norm(const Camera& c, double u, double v, double* ox, double* oy) {
     double x0 = (u - c.cx) / c.fx, y0 = (v - c.cy) / c.fy;
     double x = x0, y = y0;
-    for (int j = 0; j < 20; j++) {
+    for (int j = 0; j < (c.zero_D ? 0 : 20); j++) {  // zero coefficients: every iteration returns (x0, y0) exactly
         double r2 = x * x + y * y;
         double icdist = 1. / (1 + ((c.k3 * r2 + c.k2) * r2 + c.k1) * r2);
         double deltaX = 2 * c.p1 * x * y + c.p2 * (r2 + 2 * x * x);

@@ -173,6 +173,7 @@ static ab::Camera make_cam(const float* K, const float* D) {
     c.has_D = D != nullptr;
     if (K) { c.fxf = K[0]; c.cxf = K[2]; c.fyf = K[4]; c.cyf = K[5]; c.fx = K[0]; c.cx = K[2]; c.fy = K[4]; c.cy = K[5]; }
     if (D) { c.k1 = D[0]; c.k2 = D[1]; c.p1 = D[2]; c.p2 = D[3]; c.k3 = D[4]; }
+    c.zero_D = D && D[0] == 0.f && D[1] == 0.f && D[2] == 0.f && D[3] == 0.f && D[4] == 0.f;
     return c;
 }
 
