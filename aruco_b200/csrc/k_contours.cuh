@@ -117,9 +117,10 @@ __global__ void __launch_bounds__(256) k_scan_starts(Batch b) {
 constexpr int TRACE_LONG_T = 48;
 
 // `s` is the start state of a start candidate (table flags e): does its trigger scan before key0?
+// (raster positions fit 32 bits: W, H <= 16384)
 __device__ __forceinline__ bool smaller_trigger(uint32_t e, const WalkState& s, int W, int64_t key0) {
-    const int64_t k = (int64_t)s.y * W + s.x;
-    return ((e & WALK_TRIG_OUTER) && k < key0) || ((e & WALK_TRIG_HOLE) && k + 1 < key0);
+    const uint32_t k = (uint32_t)(s.y * W + s.x), k0 = (uint32_t)key0;
+    return ((e & WALK_TRIG_OUTER) && k < k0) || ((e & WALK_TRIG_HOLE) && k + 1u < k0);
 }
 
 template <bool LONG>
