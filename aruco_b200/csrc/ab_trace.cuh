@@ -36,9 +36,10 @@ constexpr int BIT_TILE = 32;   // rows (= words) per tile
 AB_HD int bit_words_per_row(int W) { return ((W + 31) >> 5) + BIT_PAD + 1; }  // word columns incl. padding
 AB_HD size_t bit_image_words(int W, int H) { return (size_t)bit_words_per_row(W) * BIT_TILE * (size_t)((H + 2 + BIT_TILE - 1) / BIT_TILE); }
 // index of the word in padded word column wc (image pixels 32*(wc-BIT_PAD) ..+31) of image row y (-1 <= y <= H)
-AB_HD size_t bit_word_index(int wpr, int wc, int y) {
+// (a frame's packed image has < 2^28 words for W, H <= 16384: 32-bit index arithmetic)
+AB_HD uint32_t bit_word_index(int wpr, int wc, int y) {
     const int yp = y + 1;
-    return ((size_t)(yp >> 5) * wpr + wc) * BIT_TILE + (yp & 31);
+    return (uint32_t)(((yp >> 5) * wpr + wc) * BIT_TILE + (yp & 31));
 }
 
 struct BitImage {
