@@ -87,7 +87,7 @@ struct ab_context {
     // timing
     bool timing = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t kev[12] = {};  // boundaries: threshold|scan|trace|trace_long|emit|polygon|filter|decode|refine|finalize
+    cudaEvent_t kev[12] = {};  // boundaries: threshold|scan|trace|trace_long|emit|polygon|filter|sample|identify|refine|finalize
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 };
 
@@ -684,6 +684,7 @@ static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
     if (dec_smem > 48 * 1024) cudaFuncSetAttribute(k_identify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
     k_homography<<<dim3((b.cap_c + 63) / 64, n), 64, 0, st>>>(b);
     k_sample<<<gdec, 32 * DECODE_WARPS, 0, st>>>(b);
+    if (timing) cudaEventRecord(ctx->kev[8], st);
     if (P.decoder == AB_DECODER_HOST_CALLBACK) {
         CK(cudaGetLastError());
         // MarkerdetectorFunc plugin hook (markerdetector.h:78,243): canonical images go to the host, the
@@ -713,7 +714,7 @@ static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
         k_identify<<<gdec, 32 * DECODE_WARPS, dec_smem, st>>>(b);
         CK(cudaGetLastError());
     }
-    if (timing) cudaEventRecord(ctx->kev[8], st);
+    if (timing) cudaEventRecord(ctx->kev[9], st);
     if (timing) cudaEventRecord(ctx->ev[3], st);
     if (P.locked_corners && (P.corner_method == AB_CORNER_HARRIS || P.corner_method == AB_CORNER_SUBPIX)) {
         // findCornerMaxima before the refiner (src/markerdetector.cpp:397-398)
@@ -733,11 +734,11 @@ static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
         k_refine_subpix<<<dim3(b.cap_c, n), 128, smem, st>>>(b);
     }
     CK(cudaGetLastError());
-    if (timing) cudaEventRecord(ctx->kev[9], st);
+    if (timing) cudaEventRecord(ctx->kev[10], st);
     if (timing) cudaEventRecord(ctx->ev[4], st);
     k_finalize<<<n, 128, 0, st>>>(b);
     CK(cudaGetLastError());
-    if (timing) cudaEventRecord(ctx->kev[10], st);
+    if (timing) cudaEventRecord(ctx->kev[11], st);
     if (timing) cudaEventRecord(ctx->ev[5], st);
     return AB_OK;
 }
@@ -1063,7 +1064,7 @@ int ab_get_kernel_ms(ab_context* ctx, float* ms, int n) {
     if (!ctx || !ms || !ctx->timing || !ctx->have_last) return set_err(ctx, AB_E_STATE, "timing not enabled");
     cudaSetDevice(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < n && i < 10; i++) CK(cudaEventElapsedTime(&ms[i], ctx->kev[i], ctx->kev[i + 1]));
+    for (int i = 0; i < n && i < 11; i++) CK(cudaEventElapsedTime(&ms[i], ctx->kev[i], ctx->kev[i + 1]));
     return AB_OK;
 }
 

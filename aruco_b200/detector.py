@@ -376,11 +376,11 @@ class MarkerDetector:
         self._check(self._lib.ab_get_stage_ms(self._h, _ptr(ms), 5))
         return dict(zip(("threshold", "rectangles", "identify", "refine", "filter_pose"), ms.tolist()))
 
-    KERNELS = ("threshold", "scan_starts", "trace", "trace_long", "emit", "polygon", "frame_filter", "decode", "refine", "finalize")
+    KERNELS = ("threshold", "scan_starts", "trace", "trace_long", "emit", "polygon", "frame_filter", "sample", "identify", "refine", "finalize")
 
     def kernel_ms(self):
-        ms = np.zeros(10, np.float32)
-        self._check(self._lib.ab_get_kernel_ms(self._h, _ptr(ms), 10))
+        ms = np.zeros(11, np.float32)
+        self._check(self._lib.ab_get_kernel_ms(self._h, _ptr(ms), 11))
         return dict(zip(self.KERNELS, ms.tolist()))
 
     # ---- public workers (markerdetector.h:255-280) -----------------------------------------------------------

@@ -345,6 +345,8 @@ def main():
     packed = W * H / 8.0 * B
     alg_bytes = {"threshold": 2.0 * W * H * B, "scan_starts": packed, "trace": packed, "trace_long": packed, "emit": packed}.get(dom, 3.0 * W * H * B)
     achieved = alg_bytes / (kernel_ms[dom] / 1e3) / 1e9
+    n_cands_batch = int(det.counters()["candidates"])
+    warp_gbs = n_cands_batch * 2.0 * 56 * 56 / (kernel_ms["sample"] / 1e3) / 1e9
     thr_gbs = 2.0 * W * H * B / (kernel_ms["threshold"] / 1e3) / 1e9
     # DRAM bytes per launch of the threshold kernel from the committed ncu --set full capture of this command
     # (profiles/r1p_ncu_threshold_pair_raw.csv: dram__bytes_read.sum 2.238 GB + dram__bytes_write.sum 2.361 GB at 256 x 4K);
@@ -354,6 +356,8 @@ def main():
                 "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/r1p_ncu_threshold_pair_raw.csv)",
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "kernel_ms": kernel_ms,
                 "threshold_kernel": {"achieved": thr_gbs, "frac": thr_gbs / peak},
+                # the warp stage (k_homography + k_sample): N_cand * (S^2 gathered + S^2 written) algorithmic bytes
+                "warp_kernel": {"achieved": warp_gbs, "frac": warp_gbs / peak, "candidates_per_batch": n_cands_batch},
                 "whole_path": {"algorithmic_bytes_per_frame": 3 * W * H, "achieved": fps / world * 3 * W * H / 1e9,
                                "frac": fps / world * 3 * W * H / 1e9 / peak}}
 

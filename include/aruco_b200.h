@@ -130,8 +130,8 @@ AB_API int ab_get_counters(ab_context* ctx, int64_t* counters, int n);
 AB_API int ab_enable_timing(ab_context* ctx, int enable);
 AB_API int ab_get_stage_ms(ab_context* ctx, float* ms, int n);
 /* per-kernel device milliseconds of the last batch: [0]=threshold(+erosion) [1]=scan_starts [2]=trace (short walks)
- * [3]=trace (parked long walks) [4]=emit [5]=polygon [6]=frame_filter [7]=decode (homography, sample, otsu, identify)
- * [8]=refine [9]=finalize(+pose)                                                                              */
+ * [3]=trace (parked long walks) [4]=emit [5]=polygon [6]=frame_filter [7]=homography + sample (the warp stage)
+ * [8]=otsu + identify [9]=refine [10]=finalize(+pose)                                                         */
 AB_API int ab_get_kernel_ms(ab_context* ctx, float* ms, int n);
 
 /* ---- public workers of MarkerDetector ---------------------------------------------------------------- */
