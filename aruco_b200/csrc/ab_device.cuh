@@ -12,6 +12,7 @@ enum : unsigned {
     ERR_POOL_OVERFLOW = 4u,
     ERR_QUADS_OVERFLOW = 8u,
     ERR_CANDS_OVERFLOW = 16u,
+    ERR_LINE_FIT = 32u,  // LINES: the Jacobi SVD of a side needed more sweeps than the kernel replays
 };
 
 constexpr int MAX_QUADS = 1024;  // hard upper bound of quads per frame handled by the per-frame filter

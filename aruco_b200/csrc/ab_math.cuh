@@ -361,6 +361,88 @@ AB_HD void distort_norm_to_px(const Camera& c, double x, double y, double* u, do
 }
 
 // ---------------------------------------------------------------------------------------------------
+// cv::solve(A, B, X, DECOMP_SVD) in CV_32F as the LINES refinement uses it (src/markerdetector.cpp:112,124,138):
+// OpenCV's one-sided Jacobi SVD on the two columns of A (f32 rotations, f64 dot products, eps = 2*FLT_EPSILON)
+// followed by its back substitution (f32 products accumulated in f64).  The pieces below are shared by the scalar
+// 2x2 solve of getCrossPoint and by the warp-parallel m x 2 fit in k_refine_lines.
+
+// Jacobi rotation (c, s) that orthogonalises two columns with squared norms a, b and dot product p
+AB_HD void jacobi_rotation_f32(double a, double b, double p, float* c, float* s) {
+    p *= 2;
+    double beta = a - b, gamma = hypot(p, beta);
+    if (beta < 0) {
+        double delta = (gamma - beta) * 0.5;
+        *s = (float)sqrt(delta / gamma);
+        *c = (float)(p / (gamma * (double)*s * 2));
+    } else {
+        *c = (float)sqrt((gamma + beta) / (gamma * 2));
+        *s = (float)(p / (gamma * (double)*c * 2));
+    }
+}
+
+// X = V * diag(1/w) * U^T b from the two singular triplets (SVBkSb): W2 = squared column norms after the last sweep,
+// ub[i] = sum_j (u_i[j] * b[j]) with u_i = column i scaled by sc[i] (see jacobi_scales_f32), Vt rows = right vectors
+// returns the index of the larger singular value (they are used in descending order)
+AB_HD int jacobi_scales_f32(const double W2[2], float w[2], float sc[2]) {
+    double sd[2];
+    for (int i = 0; i < 2; i++) {
+        sd[i] = sqrt(W2[i]);
+        w[i] = (float)sd[i];
+        sc[i] = (float)(sd[i] > (double)FLT_MIN ? 1 / sd[i] : 0.);
+    }
+    return sd[0] < sd[1] ? 1 : 0;
+}
+AB_HD void jacobi_backsubst_f32(int o0, const float w[2], const double ub[2], const float Vt[2][2], float X[2]) {
+    const int ord[2] = {o0, 1 - o0};
+    const double threshold = ((double)w[0] + (double)w[1]) * (double)(float)(DBL_EPSILON * 2);
+    X[0] = X[1] = 0.f;
+    for (int k = 0; k < 2; k++) {
+        const int i = ord[k];
+        double wi = w[i];
+        if (fabs(wi) <= threshold) continue;
+        double sv = ub[i] * (1 / wi);
+        for (int j = 0; j < 2; j++) X[j] = (float)((double)X[j] + sv * (double)Vt[i][j]);
+    }
+}
+
+// getCrossPoint (src/markerdetector.cpp:132-139): Matx22f(l1.x, l1.y; l2.x, l2.y).solve(Vec2f(-l1.z, -l2.z), DECOMP_SVD)
+AB_HD void cross_point_f32(const float* l1, const float* l2, float* x, float* y) {
+    float A0[2] = {l1[0], l2[0]}, A1[2] = {l1[1], l2[1]};
+    const float rhs[2] = {-l1[2], -l2[2]};
+    float Vt[2][2] = {{1.f, 0.f}, {0.f, 1.f}};
+    double W2[2] = {(double)A0[0] * A0[0] + (double)A0[1] * A0[1], (double)A1[0] * A1[0] + (double)A1[1] * A1[1]};
+    for (int iter = 0; iter < 30; iter++) {
+        double p = (double)A0[0] * A1[0] + (double)A0[1] * A1[1];
+        if (fabs(p) <= (double)(FLT_EPSILON * 2) * sqrt(W2[0] * W2[1])) break;
+        float c, s;
+        jacobi_rotation_f32(W2[0], W2[1], p, &c, &s);
+        double a = 0, b = 0;
+        for (int k = 0; k < 2; k++) {
+            float t0 = c * A0[k] + s * A1[k], t1 = -s * A0[k] + c * A1[k];
+            A0[k] = t0;
+            A1[k] = t1;
+            a += (double)t0 * t0;
+            b += (double)t1 * t1;
+            float v0 = c * Vt[0][k] + s * Vt[1][k], v1 = -s * Vt[0][k] + c * Vt[1][k];
+            Vt[0][k] = v0;
+            Vt[1][k] = v1;
+        }
+        W2[0] = a;
+        W2[1] = b;
+    }
+    float w[2], sc[2], X[2];
+    const int o0 = jacobi_scales_f32(W2, w, sc);
+    double ub[2] = {0, 0};
+    for (int k = 0; k < 2; k++) {
+        ub[0] += (double)((A0[k] * sc[0]) * rhs[k]);
+        ub[1] += (double)((A1[k] * sc[1]) * rhs[k]);
+    }
+    jacobi_backsubst_f32(o0, w, ub, Vt, X);
+    *x = X[0];
+    *y = X[1];
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Pose: cv::solvePnP(SOLVEPNP_ITERATIVE) for 4 coplanar points (src/markerdetector.cpp:458, marker.cpp:118)
 // planar homography initialisation + Levenberg-Marquardt on the pixel reprojection error
 // ---------------------------------------------------------------------------------------------------

@@ -642,6 +642,15 @@ static Batch sub_view(ab_context* ctx, const Batch& w, int f0, int nf, int s) {
     return v;
 }
 
+// LINES refinement: with a distorted camera the undistorted contour of a candidate is cached in shared memory
+constexpr int LINES_CACHE_POINTS = 4096;
+static void launch_refine_lines(const Batch& b, dim3 grid, cudaStream_t st) {
+    if (b.cam.has_K && b.cam.has_D && !b.cam.zero_D)
+        k_refine_lines<true><<<grid, 128, LINES_CACHE_POINTS * sizeof(float2), st>>>(b, LINES_CACHE_POINTS);
+    else
+        k_refine_lines<false><<<grid, 128, 0, st>>>(b, 0);
+}
+
 // one sub-batch (a view of the batch buffers) on one stream: every stage of the path
 static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
     const ab_params& P = ctx->params;
@@ -724,7 +733,7 @@ static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
         k_corner_maxima<<<dim3(4 * b.cap_c, n), 64, smem, st>>>(b);
     }
     if (P.corner_method == AB_CORNER_LINES) {
-        k_refine_lines<<<gcand, 128, 0, st>>>(b);
+        launch_refine_lines(b, gcand, st);
     } else if (P.corner_method == AB_CORNER_HARRIS) {
         k_refine_harris<<<dim3(b.cap_c, n), 128, 0, st>>>(b);
     } else if (P.corner_method == AB_CORNER_SUBPIX) {
@@ -807,6 +816,7 @@ static int check_device_errors(ab_context* ctx, const Counters* c) {
     if (c->err & ERR_POOL_OVERFLOW) what += " contour-points(max_contour_points_per_frame)";
     if (c->err & ERR_QUADS_OVERFLOW) what += " quads(max_quads_per_frame)";
     if (c->err & ERR_CANDS_OVERFLOW) what += " candidates(max_candidates_per_frame)";
+    if (c->err & ERR_LINE_FIT) what += " line-fit-sweeps(LINES_MAX_SWEEPS)";
     return set_err(ctx, AB_E_CAPACITY, "device buffer overflow:%s -- results are incomplete; call ab_reserve with larger capacities",
                    what.c_str());
 }

@@ -26,27 +26,37 @@ __device__ __forceinline__ float warp_max_f(float v) {
     return v;
 }
 
-__global__ void __launch_bounds__(128) k_refine_lines(Batch b) {
-    __shared__ int s_ci[4];
-    __shared__ float s_line[4][3];
-    const int f = blockIdx.y, ci = blockIdx.x, t = threadIdx.x, lane = t & 31, l = t >> 5;
-    if (ci >= (int)b.n_cands[f]) return;
-    CandRec* cand = b.cands + (size_t)f * b.cap_c + ci;
-    if (cand->id < 0) return;
-    const ContourRec rec = b.contours[cand->contour];
-    const int n = (int)rec.n;
-    const uint32_t* pts = b.pool + rec.off;
-    const bool rev = cand->swapped != 0;  // the reference reverses the contour of swapped candidates (:622-625)
+constexpr int LINES_MAX_SWEEPS = 8;  // Jacobi sweeps kept for replay (two columns converge in 1-3)
+
+// refineCandidateLines for one candidate by one CTA of 128 threads (warp l = side l).  `pts` = the contour in the
+// order the reference holds it (`rev`: read it backwards, :622-625), `c` = the 4 corners (integer valued).
+// Every side is fitted exactly as interpolate2Dline does (:83-130): cv::solve(DECOMP_SVD) on the m x 2 CV_32F system
+// = OpenCV's one-sided Jacobi SVD of the columns (coordinate, 1).  The rotated columns are not stored: a sweep
+// re-derives them from the points by replaying the earlier rotations (1-3 of them), so one pass over the side yields
+// the squared norms and dot product the next sweep needs.  f64 sums are tree-reduced (the reference adds
+// sequentially; they only enter through values rounded to f32).  UNDIST: cv::undistortPoints of the contour first
+// (:957-959), cached in shared memory when the contour fits `cache_cap` points.
+template <bool UNDIST>
+__device__ __forceinline__ void refine_lines_cta(const uint32_t* pts, int n, bool rev, const float* c, const Camera& cam,
+                                                 float2* s_pts, int cache_cap, int* s_ci, float (*s_line)[3], float* refined,
+                                                 unsigned int* err) {
+    const int t = threadIdx.x, lane = t & 31, l = t >> 5;
     if (t < 4) s_ci[t] = -1;
     __syncthreads();
     uint32_t ck[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) ck[k] = (uint32_t)(int)cand->c[2 * k] | ((uint32_t)(int)cand->c[2 * k + 1] << 16);
+    for (int k = 0; k < 4; k++) ck[k] = (uint32_t)(int)c[2 * k] | ((uint32_t)(int)c[2 * k + 1] << 16);
+    const bool cached = UNDIST && n <= cache_cap;
     for (int j = t; j < n; j += blockDim.x) {
         uint32_t p = rev ? pts[n - 1 - j] : pts[j];
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (p == ck[k]) atomicMax(&s_ci[k], j);  // last match wins (:935-941)
+        if (cached) {
+            float x, y;
+            undistort_point_px(cam, (float)(p & 0xFFFFu), (float)(p >> 16), &x, &y);  // contour points are integer pixels
+            s_pts[j] = make_float2(x, y);
+        }
     }
     __syncthreads();
     const int c0 = s_ci[0], c1 = s_ci[1], c2 = s_ci[2], c3 = s_ci[3];
@@ -56,79 +66,162 @@ __global__ void __launch_bounds__(128) k_refine_lines(Batch b) {
     else if (c2 > c1 && c2 < c0) inverse = false;
     else inverse = true;
     const int inc = inverse ? -1 : 1;
-    const bool undist = b.cam.has_K && b.cam.has_D;
     {
         const int start = s_ci[l], end = s_ci[(l + 1) & 3];
         int m = inverse ? (start - end) : (end - start);
         if (m < 0) m += n;
-        int m2 = (m == 1) ? 2 : m;  // 1-point side: add the next corner (:972-976)
-        float mnx = 3.0e38f, mxx = -3.0e38f, mny = 3.0e38f, mxy = -3.0e38f;
-        double Sx = 0, Sy = 0, Sxx = 0, Syy = 0, Sxy = 0;
-        for (int i = lane; i < m2; i += 32) {
+        const int m2 = (m == 1) ? 2 : m;  // 1-point side: add the next corner (:972-976)
+        auto point = [&](int i, float& x, float& y) {
             int j = start + inc * i;
             if (m == 1 && i == 1) j = end;
             j %= n;
             if (j < 0) j += n;
-            uint32_t p = rev ? pts[n - 1 - j] : pts[j];
-            float x = (float)(p & 0xFFFFu), y = (float)(p >> 16);
-            if (undist && !b.cam.zero_D) undistort_point_px(b.cam, x, y, &x, &y);  // contour points are integer pixels
+            if (cached) {
+                float2 q = s_pts[j];
+                x = q.x;
+                y = q.y;
+            } else {
+                uint32_t p = rev ? pts[n - 1 - j] : pts[j];
+                x = (float)(p & 0xFFFFu);
+                y = (float)(p >> 16);
+                if (UNDIST) undistort_point_px(cam, x, y, &x, &y);
+            }
+        };
+        // pass 0: bounding box decides the parametrisation; column sums of both candidates
+        float mnx = 3.0e38f, mxx = -3.0e38f, mny = 3.0e38f, mxy = -3.0e38f;
+        double Sx = 0, Sy = 0, Sxx = 0, Syy = 0;
+        for (int i = lane; i < m2; i += 32) {
+            float x, y;
+            point(i, x, y);
             mnx = fminf(mnx, x);
             mxx = fmaxf(mxx, x);
             mny = fminf(mny, y);
             mxy = fmaxf(mxy, y);
-            double dx = x, dy = y;
-            Sx += dx;
-            Sy += dy;
-            Sxx += dx * dx;
-            Syy += dy * dy;
-            Sxy += dx * dy;
+            Sx += (double)x;
+            Sy += (double)y;
+            Sxx += (double)x * x;
+            Syy += (double)y * y;
         }
         mnx = warp_min_f(mnx);
         mxx = warp_max_f(mxx);
         mny = warp_min_f(mny);
         mxy = warp_max_f(mxy);
-        Sx = warp_sum_d(Sx);
-        Sy = warp_sum_d(Sy);
-        Sxx = warp_sum_d(Sxx);
-        Syy = warp_sum_d(Syy);
-        Sxy = warp_sum_d(Sxy);
-        if (lane == 0) {
-            double N = (double)m2;
-            if (mxx - mnx > mxy - mny) {  // y = a x + c  (interpolate2Dline, :103-115)
-                double a = (N * Sxy - Sx * Sy) / (N * Sxx - Sx * Sx);
-                double c = (Sy - a * Sx) / N;
-                s_line[l][0] = (float)a;
-                s_line[l][1] = -1.f;
-                s_line[l][2] = (float)c;
-            } else {  // x = b y + c
-                double bb = (N * Sxy - Sx * Sy) / (N * Syy - Sy * Sy);
-                double c = (Sx - bb * Sy) / N;
-                s_line[l][0] = -1.f;
-                s_line[l][1] = (float)bb;
-                s_line[l][2] = (float)c;
+        const bool along_x = mxx - mnx > mxy - mny;  // y = a x + c (:103-115), else x = b y + c (:116-128)
+        double W2[2] = {warp_sum_d(along_x ? Sxx : Syy), (double)m2};
+        double p = warp_sum_d(along_x ? Sx : Sy);
+        float rc[LINES_MAX_SWEEPS], rs[LINES_MAX_SWEEPS];
+        float Vt[2][2] = {{1.f, 0.f}, {0.f, 1.f}};
+        int ns = 0;
+        const int max_iter = max(m2, 30);
+        for (int iter = 0; iter < max_iter; iter++) {
+            if (fabs(p) <= (double)(FLT_EPSILON * 2) * sqrt(W2[0] * W2[1])) break;
+            if (ns == LINES_MAX_SWEEPS) {
+                if (lane == 0) atomicOr(err, ERR_LINE_FIT);
+                break;
             }
+            float cc, ss;
+            jacobi_rotation_f32(W2[0], W2[1], p, &cc, &ss);
+#pragma unroll
+            for (int k = 0; k < LINES_MAX_SWEEPS; k++)
+                if (k == ns) {
+                    rc[k] = cc;
+                    rs[k] = ss;
+                }
+            ns++;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                float v0 = cc * Vt[0][k] + ss * Vt[1][k], v1 = -ss * Vt[0][k] + cc * Vt[1][k];
+                Vt[0][k] = v0;
+                Vt[1][k] = v1;
+            }
+            double a = 0, bb = 0, pn = 0;
+            for (int i = lane; i < m2; i += 32) {
+                float x, y;
+                point(i, x, y);
+                float t0 = along_x ? x : y, t1 = 1.f;
+#pragma unroll
+                for (int k = 0; k < LINES_MAX_SWEEPS; k++)
+                    if (k < ns) {
+                        float n0 = rc[k] * t0 + rs[k] * t1, n1 = -rs[k] * t0 + rc[k] * t1;
+                        t0 = n0;
+                        t1 = n1;
+                    }
+                a += (double)t0 * t0;
+                bb += (double)t1 * t1;
+                pn += (double)t0 * t1;
+            }
+            W2[0] = warp_sum_d(a);
+            W2[1] = warp_sum_d(bb);
+            p = warp_sum_d(pn);
+        }
+        float w[2], sc[2], X[2];
+        const int o0 = jacobi_scales_f32(W2, w, sc);
+        double ub[2] = {0, 0};
+        for (int i = lane; i < m2; i += 32) {
+            float x, y;
+            point(i, x, y);
+            float t0 = along_x ? x : y, t1 = 1.f;
+            const float rhs = along_x ? y : x;
+#pragma unroll
+            for (int k = 0; k < LINES_MAX_SWEEPS; k++)
+                if (k < ns) {
+                    float n0 = rc[k] * t0 + rs[k] * t1, n1 = -rs[k] * t0 + rc[k] * t1;
+                    t0 = n0;
+                    t1 = n1;
+                }
+            ub[0] += (double)((t0 * sc[0]) * rhs);
+            ub[1] += (double)((t1 * sc[1]) * rhs);
+        }
+        ub[0] = warp_sum_d(ub[0]);
+        ub[1] = warp_sum_d(ub[1]);
+        jacobi_backsubst_f32(o0, w, ub, Vt, X);
+        if (lane == 0) {
+            s_line[l][0] = along_x ? X[0] : -1.f;
+            s_line[l][1] = along_x ? -1.f : X[0];
+            s_line[l][2] = X[1];
         }
     }
     __syncthreads();
     if (t < 4) {
         // getCrossPoint(lines[i], lines[i-1]) (:132-139, :985-987)
-        const float* l1 = s_line[t];
-        const float* l2 = s_line[(t + 3) & 3];
-        double a11 = l1[0], a12 = l1[1], a21 = l2[0], a22 = l2[1], b1 = -(double)l1[2], b2 = -(double)l2[2];
-        double det = a11 * a22 - a12 * a21;
-        float x = (float)((b1 * a22 - a12 * b2) / det);
-        float y = (float)((a11 * b2 - b1 * a21) / det);
-        if (undist) {
+        float x, y;
+        cross_point_f32(s_line[t], s_line[(t + 3) & 3], &x, &y);
+        if (cam.has_K && cam.has_D) {
             // distortPoints (:141-153): normalise in f32, project with R=t=0 in f64
-            float xn = (x - b.cam.cxf) / b.cam.fxf, yn = (y - b.cam.cyf) / b.cam.fyf;
+            float xn = (x - cam.cxf) / cam.fxf, yn = (y - cam.cyf) / cam.fyf;
             double u, v;
-            distort_norm_to_px(b.cam, (double)xn, (double)yn, &u, &v);
+            distort_norm_to_px(cam, (double)xn, (double)yn, &u, &v);
             x = (float)u;
             y = (float)v;
         }
-        cand->refined[2 * t] = x;
-        cand->refined[2 * t + 1] = y;
+        refined[2 * t] = x;
+        refined[2 * t + 1] = y;
     }
+}
+
+template <bool UNDIST>
+__global__ void __launch_bounds__(128) k_refine_lines(Batch b, int cache_cap) {
+    extern __shared__ float2 s_lines_pts[];
+    __shared__ int s_ci[4];
+    __shared__ float s_line[4][3];
+    const int f = blockIdx.y, ci = blockIdx.x;
+    if (ci >= (int)b.n_cands[f]) return;
+    CandRec* cand = b.cands + (size_t)f * b.cap_c + ci;
+    if (cand->id < 0) return;
+    const ContourRec rec = b.contours[cand->contour];
+    // the reference reverses the contour of swapped candidates (:622-625)
+    refine_lines_cta<UNDIST>(b.pool + rec.off, (int)rec.n, cand->swapped != 0, cand->c, b.cam, s_lines_pts, cache_cap, s_ci,
+                             s_line, cand->refined, &b.cnt->err);
+}
+
+// public worker MarkerDetector::refineCandidateLines (h:280): one candidate, contour given by the caller
+template <bool UNDIST>
+__global__ void __launch_bounds__(128) k_refine_lines_single(const uint32_t* pts, int n, const float* corners, Camera cam,
+                                                             int cache_cap, float* out, unsigned int* err) {
+    extern __shared__ float2 s_lines_pts[];
+    __shared__ int s_ci[4];
+    __shared__ float s_line[4][3];
+    refine_lines_cta<UNDIST>(pts, n, false, corners, cam, s_lines_pts, cache_cap, s_ci, s_line, out, err);
 }
 
 // bilinear getRectSubPix sample with replicated border, f32 arithmetic in OpenCV's order

@@ -707,7 +707,117 @@ void project_norm(const Cam& c, double x, double y, double* u, double* v) {
     *v = (y * cd + c.p1 * a3 + c.p2 * a1) * c.fy + c.cy;
 }
 
-// refineCandidateLines (src/markerdetector.cpp:931-997); least squares in f64 (OpenCV: f32 SVD, ~1e-4 px)
+// cv::solve(A, B, X, DECOMP_SVD) for an m x 2 CV_32F system, as interpolate2Dline / getCrossPoint call it
+// (src/markerdetector.cpp:112,124,138).  OpenCV (un-vendored dependency; modules/core/src/lapack.cpp, 4.x)
+// transposes A, runs its one-sided Jacobi SVD in f32 with f64 dot products (JacobiSVDImpl_<float>:
+// eps = 2*FLT_EPSILON, at most max(m,30) sweeps, singular values sorted descending, rows scaled by 1/w)
+// and back-substitutes with SVBkSb (f32 products accumulated in f64, threshold (float)(2*DBL_EPSILON)*sum(w)).
+// cv2 4.13 is bit-identical to this for m < 25 (tests/test_oracle_cross.py); wheels built with a LAPACK HAL
+// switch to sgesdd at m >= 25, whose rounding depends on the BLAS kernels of the host CPU.
+void svd_solve_f32_m2(const float* c0, const float* c1, int m, const float* b, float X[2]) {
+    std::vector<float> a0(c0, c0 + m), a1(c1, c1 + m);
+    float* At[2] = {a0.data(), a1.data()};
+    double W[2];
+    float Vt[2][2] = {{1.f, 0.f}, {0.f, 1.f}};
+    for (int i = 0; i < 2; i++) {
+        double sd = 0;
+        for (int k = 0; k < m; k++) { float t = At[i][k]; sd += (double)t * t; }
+        W[i] = sd;
+    }
+    const float eps = FLT_EPSILON * 2;
+    const int max_iter = std::max(m, 30);
+    for (int iter = 0; iter < max_iter; iter++) {
+        float* Ai = At[0];
+        float* Aj = At[1];
+        double a = W[0], p = 0, bb = W[1];
+        for (int k = 0; k < m; k++) p += (double)Ai[k] * Aj[k];
+        if (fabs(p) <= eps * sqrt(a * bb)) break;
+        p *= 2;
+        double beta = a - bb, gamma = hypot(p, beta);
+        float c, s;
+        if (beta < 0) {
+            double delta = (gamma - beta) * 0.5;
+            s = (float)sqrt(delta / gamma);
+            c = (float)(p / (gamma * s * 2));
+        } else {
+            c = (float)sqrt((gamma + beta) / (gamma * 2));
+            s = (float)(p / (gamma * c * 2));
+        }
+        a = bb = 0;
+        for (int k = 0; k < m; k++) {
+            float t0 = c * Ai[k] + s * Aj[k];
+            float t1 = -s * Ai[k] + c * Aj[k];
+            Ai[k] = t0; Aj[k] = t1;
+            a += (double)t0 * t0; bb += (double)t1 * t1;
+        }
+        W[0] = a; W[1] = bb;
+        for (int k = 0; k < 2; k++) {
+            float t0 = c * Vt[0][k] + s * Vt[1][k];
+            float t1 = -s * Vt[0][k] + c * Vt[1][k];
+            Vt[0][k] = t0; Vt[1][k] = t1;
+        }
+    }
+    for (int i = 0; i < 2; i++) {
+        double sd = 0;
+        for (int k = 0; k < m; k++) { float t = At[i][k]; sd += (double)t * t; }
+        W[i] = sqrt(sd);
+    }
+    int o0 = 0, o1 = 1;
+    if (W[0] < W[1]) { std::swap(W[0], W[1]); o0 = 1; o1 = 0; }
+    const int ord[2] = {o0, o1};
+    float w[2] = {(float)W[0], (float)W[1]};
+    for (int i = 0; i < 2; i++) {
+        float sc = (float)(W[i] > (double)FLT_MIN ? 1 / W[i] : 0.);
+        float* r = At[ord[i]];
+        for (int k = 0; k < m; k++) r[k] *= sc;
+    }
+    double threshold = ((double)w[0] + (double)w[1]) * (double)(float)(DBL_EPSILON * 2);
+    X[0] = X[1] = 0.f;
+    for (int i = 0; i < 2; i++) {
+        double wi = w[i];
+        if (fabs(wi) <= threshold) continue;
+        wi = 1 / wi;
+        const float* u = At[ord[i]];
+        double sacc = 0;
+        for (int j = 0; j < m; j++) sacc += u[j] * b[j];  // f32 product, f64 accumulator (SVBkSbImpl_)
+        sacc *= wi;
+        for (int j = 0; j < 2; j++) X[j] = (float)(X[j] + sacc * Vt[ord[i]][j]);
+    }
+}
+
+// interpolate2Dline (src/markerdetector.cpp:83-130)
+void interpolate_2d_line(const std::vector<Pt2f>& pts, float line[3]) {
+    float minX, maxX, minY, maxY;
+    minX = maxX = pts[0].x;
+    minY = maxY = pts[0].y;
+    for (size_t i = 1; i < pts.size(); i++) {
+        minX = std::min(minX, pts[i].x); maxX = std::max(maxX, pts[i].x);
+        minY = std::min(minY, pts[i].y); maxY = std::max(maxY, pts[i].y);
+    }
+    const int m = (int)pts.size();
+    std::vector<float> a(m), one(m, 1.f), rhs(m);
+    float X[2];
+    if (maxX - minX > maxY - minY) {  // Ax + C = y
+        for (int i = 0; i < m; i++) { a[i] = pts[i].x; rhs[i] = pts[i].y; }
+        svd_solve_f32_m2(a.data(), one.data(), m, rhs.data(), X);
+        line[0] = X[0]; line[1] = -1.f; line[2] = X[1];
+    } else {  // By + C = x
+        for (int i = 0; i < m; i++) { a[i] = pts[i].y; rhs[i] = pts[i].x; }
+        svd_solve_f32_m2(a.data(), one.data(), m, rhs.data(), X);
+        line[0] = -1.f; line[1] = X[0]; line[2] = X[1];
+    }
+}
+
+// getCrossPoint (src/markerdetector.cpp:132-139): Matx22f::solve(Vec2f, DECOMP_SVD)
+void cross_point(const float* l1, const float* l2, float* x, float* y) {
+    const float c0[2] = {l1[0], l2[0]}, c1[2] = {l1[1], l2[1]}, rhs[2] = {-l1[2], -l2[2]};
+    float X[2];
+    svd_solve_f32_m2(c0, c1, 2, rhs, X);
+    *x = X[0];
+    *y = X[1];
+}
+
+// refineCandidateLines (src/markerdetector.cpp:931-997)
 void refine_lines(Candidate& cd, const Cam& cam) {
     const std::vector<Pt>& ct = cd.contour;
     const int n = (int)ct.size();
@@ -735,27 +845,13 @@ void refine_lines(Candidate& cd, const Cam& cam) {
             j = ((j + inc) % n + n) % n;
         }
         if (pts.size() == 1) pts.push_back(c2f[ci[(l + 1) % 4]]);
-        float minX = 3e38f, maxX = -3e38f, minY = 3e38f, maxY = -3e38f;
-        double Sx = 0, Sy = 0, Sxx = 0, Syy = 0, Sxy = 0, N = (double)pts.size();
-        for (auto& p : pts) {
-            minX = std::min(minX, p.x); maxX = std::max(maxX, p.x);
-            minY = std::min(minY, p.y); maxY = std::max(maxY, p.y);
-            Sx += p.x; Sy += p.y; Sxx += (double)p.x * p.x; Syy += (double)p.y * p.y; Sxy += (double)p.x * p.y;
-        }
-        if (maxX - minX > maxY - minY) {
-            double a = (N * Sxy - Sx * Sy) / (N * Sxx - Sx * Sx), c = (Sy - a * Sx) / N;
-            lines[l][0] = (float)a; lines[l][1] = -1.f; lines[l][2] = (float)c;
-        } else {
-            double b = (N * Sxy - Sx * Sy) / (N * Syy - Sy * Sy), c = (Sx - b * Sy) / N;
-            lines[l][0] = -1.f; lines[l][1] = (float)b; lines[l][2] = (float)c;
-        }
+        interpolate_2d_line(pts, lines[l]);
     }
     for (int i = 0; i < 4; i++) {
         const float* l1 = lines[i];
         const float* l2 = lines[(i + 3) % 4];
-        double det = (double)l1[0] * l2[1] - (double)l1[1] * l2[0];
-        float x = (float)((-(double)l1[2] * l2[1] + (double)l1[1] * l2[2]) / det);
-        float y = (float)((-(double)l1[0] * l2[2] + (double)l1[2] * l2[0]) / det);
+        float x, y;
+        cross_point(l1, l2, &x, &y);
         if (und) {
             float xn = (x - cam.Kf[2]) / cam.Kf[0], yn = (y - cam.Kf[5]) / cam.Kf[4];
             double u, v;
@@ -1242,6 +1338,13 @@ int orc_warp(const uint8_t* grey, int W, int H, const float* quad, int S, uint8_
 }
 
 int orc_otsu(const uint8_t* img, int N) { return otsu(img, N); }
+
+// cv::solve(A[m x 2], B, X, DECOMP_SVD) in CV_32F (test hook for the restated Jacobi SVD)
+void orc_svd_solve_f32(const float* A, int m, const float* B, float* X) {
+    std::vector<float> c0(m), c1(m);
+    for (int i = 0; i < m; i++) { c0[i] = A[2 * i]; c1[i] = A[2 * i + 1]; }
+    svd_solve_f32_m2(c0.data(), c1.data(), m, B, X);
+}
 
 int orc_solve_pnp(const float* K, const float* D, const float* corners, float size, double* rvec, double* tvec) {
     Cam c;

@@ -18,6 +18,7 @@ Deterministic resolutions of the reference's undefined behaviour (SURVEY.md Appe
 from __future__ import annotations
 
 import dataclasses
+import math
 from typing import List, Optional
 
 import numpy as np
@@ -324,6 +325,74 @@ def hrm_detect(canon: np.ndarray, D: HrmDictionary):
     return -1, 0, bw, code
 
 
+# cv::solve(DECOMP_SVD) in CV_32F is OpenCV's own one-sided Jacobi SVD (modules/core/src/lapack.cpp) -- unless the
+# build carries a LAPACK HAL, which takes over at >= 25 rows (hal_internal.cpp: HAL_SVD_SMALL_MATRIX_THRESH) with
+# sgesdd, whose f32 rounding depends on the BLAS kernels picked for the host CPU.  This wheel has one (OpenBLAS).
+#   "jacobi": cv2.solve below 25 rows (= OpenCV's Jacobi, the real thing), the restated Jacobi from 25 rows on
+#             -- the arithmetic OpenCV's source defines, identical on every machine; tests/test_oracle_cross.py
+#             checks the restatement bit for bit against cv2.solve for every row count below 25.
+#   "cv2":    cv2.solve for every size (this wheel: LAPACK from 25 rows on).
+LINES_SOLVER = "jacobi"
+_HAL_SVD_ROWS = 25
+
+
+def _seq_sum(v) -> float:
+    return float(np.cumsum(np.asarray(v, np.float64))[-1])  # sequential f64 accumulation
+
+
+def jacobi_svd_solve_f32(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """cv::solve(A[m x 2], B[m], DECOMP_SVD) for CV_32F without a LAPACK HAL: JacobiSVDImpl_<float> on A^T
+    (eps = 2*FLT_EPSILON, f64 dot products, f32 rotations) + SVBkSb (f32 products summed in f64)."""
+    f32 = np.float32
+    m = A.shape[0]
+    At = [A[:, 0].astype(f32).copy(), A[:, 1].astype(f32).copy()]
+    Vt = np.eye(2, dtype=f32)
+    W = [_seq_sum(At[0].astype(np.float64) ** 2), _seq_sum(At[1].astype(np.float64) ** 2)]
+    eps = float(np.finfo(f32).eps) * 2
+    for _ in range(max(m, 30)):
+        p = _seq_sum(At[0].astype(np.float64) * At[1].astype(np.float64))
+        if abs(p) <= eps * math.sqrt(W[0] * W[1]):
+            break
+        p *= 2
+        beta = W[0] - W[1]
+        gamma = math.hypot(p, beta)
+        if beta < 0:
+            sn = f32(math.sqrt((gamma - beta) * 0.5 / gamma))
+            cs = f32(p / (gamma * float(sn) * 2))
+        else:
+            cs = f32(math.sqrt((gamma + beta) / (gamma * 2)))
+            sn = f32(p / (gamma * float(cs) * 2))
+        t0 = (cs * At[0]).astype(f32) + (sn * At[1]).astype(f32)
+        t1 = ((-sn) * At[0]).astype(f32) + (cs * At[1]).astype(f32)
+        At = [t0.astype(f32), t1.astype(f32)]
+        W = [_seq_sum(t0.astype(np.float64) ** 2), _seq_sum(t1.astype(np.float64) ** 2)]
+        v0 = (cs * Vt[0]).astype(f32) + (sn * Vt[1]).astype(f32)
+        v1 = ((-sn) * Vt[0]).astype(f32) + (cs * Vt[1]).astype(f32)
+        Vt = np.stack([v0, v1]).astype(f32)
+    Wd = [math.sqrt(_seq_sum(At[0].astype(np.float64) ** 2)), math.sqrt(_seq_sum(At[1].astype(np.float64) ** 2))]
+    order = [1, 0] if Wd[0] < Wd[1] else [0, 1]
+    w = [f32(Wd[0]), f32(Wd[1])]
+    tiny = float(np.finfo(f32).tiny)
+    U = [(At[i] * f32(1 / Wd[i] if Wd[i] > tiny else 0.0)).astype(f32) for i in range(2)]
+    thr = (float(w[0]) + float(w[1])) * float(f32(2 * np.finfo(np.float64).eps))
+    X = np.zeros(2, f32)
+    Bf = B.reshape(-1).astype(f32)
+    for i in order:
+        wi = float(w[i])
+        if abs(wi) <= thr:
+            continue
+        sv = _seq_sum((U[i] * Bf).astype(f32)) * (1 / wi)
+        for j in range(2):
+            X[j] = f32(float(X[j]) + sv * float(Vt[i, j]))
+    return X
+
+
+def _solve_svd_f32(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    if LINES_SOLVER == "jacobi" and A.shape[0] >= _HAL_SVD_ROWS:
+        return jacobi_svd_solve_f32(A, B)
+    return cv2.solve(A, B, flags=cv2.DECOMP_SVD)[1].reshape(2)
+
+
 def _interpolate2dline(pts: np.ndarray):
     """src/markerdetector.cpp:83-130 (f32 SVD least squares)."""
     pts = pts.astype(np.float32)
@@ -333,13 +402,11 @@ def _interpolate2dline(pts: np.ndarray):
     A[:, 1] = 1
     if np.float32(maxx - minx) > np.float32(maxy - miny):
         A[:, 0] = pts[:, 0]
-        B = pts[:, 1:2].copy()
-        _, X = cv2.solve(A, B, flags=cv2.DECOMP_SVD)
-        return np.array([X[0, 0], -1.0, X[1, 0]], np.float32)
+        X = _solve_svd_f32(A, pts[:, 1:2].copy())
+        return np.array([X[0], -1.0, X[1]], np.float32)
     A[:, 0] = pts[:, 1]
-    B = pts[:, 0:1].copy()
-    _, X = cv2.solve(A, B, flags=cv2.DECOMP_SVD)
-    return np.array([-1.0, X[0, 0], X[1, 0]], np.float32)
+    X = _solve_svd_f32(A, pts[:, 0:1].copy())
+    return np.array([-1.0, X[0], X[1]], np.float32)
 
 
 def _cross_point(l1, l2):

@@ -188,6 +188,9 @@ void hc_undistort_px(const float* K, const float* D, const float* in, int n, flo
 }
 
 void hc_rotate_x_axis(double* rvec) { ab::rotate_x_axis(rvec); }
+
+// getCrossPoint as k_refine_lines computes it
+void hc_cross_point(const float* l1, const float* l2, float* xy) { ab::cross_point_f32(l1, l2, &xy[0], &xy[1]); }
 }
 
 extern "C" {

@@ -44,8 +44,22 @@ def oracle_pose(corners, K, D, size):
     return r, t
 
 
-def check_frame(det, grey, P, K=None, D=None, size=-1.0, hrm_text=None, frame=0, markers=None, min_direct_pose=0.85):
-    """Full per-stage comparison of one frame against the C++ oracle (and the cv2 oracle when available)."""
+def cv2_pose(corners, K, D, size):
+    """cv2.solvePnP (real OpenCV) for GIVEN corners, as markerdetector.cpp:458 / marker.cpp:118 call it."""
+    import cv2
+    from oracle import cv2_oracle as o
+    ok, rv, tv = cv2.solvePnP(o.object_points(size), np.asarray(corners, np.float32).reshape(4, 1, 2), np.asarray(K, np.float32),
+                              np.asarray(D, np.float32).reshape(1, -1) if D is not None else None)
+    return rv.ravel(), tv.ravel()
+
+
+def check_frame(det, grey, P, K=None, D=None, size=-1.0, hrm_text=None, frame=0, markers=None, min_direct_pose=0.99,
+                stats=None):
+    """Full per-stage comparison of one frame against the C++ oracle and the cv2 oracle (real OpenCV).
+    Pose gate (north star: Rvec/Tvec within 1e-4 relative): the GPU pipeline's pose against each oracle PIPELINE's pose,
+    for at least `min_direct_pose` of the frame's markers (`stats` accumulates the counts for multi-frame gates), and
+    for EVERY marker against the oracle's and OpenCV's own solvePnP on the GPU's corners (so a marker that misses the
+    direct gate is one whose pose is ill-conditioned in its corners, not one the pose kernel got wrong)."""
     from oracle import native
     hn = native.dict_from_yaml_text(hrm_text) if hrm_text else None
     ref = native.detect(grey, P, K, D, size, hn, cap=2048)
@@ -59,10 +73,11 @@ def check_frame(det, grey, P, K=None, D=None, size=-1.0, hrm_text=None, frame=0,
     for i in range(len(ids)):
         assert (det.getCanonical(frame, i) == ref["canon"][i]).all(), "canonical image %d differs" % i
     assert [m.id for m in markers] == [m["id"] for m in ref["markers"]]
+    posed = size > 0 and K is not None
     direct = 0
     for m, r in zip(markers, ref["markers"]):
         assert np.abs(m.corners - r["corners"]).max() < CORNER_TOL
-        if size > 0 and K is not None:
+        if posed:
             assert m.Rvec is not None and abs(m.ssize - size) < 1e-7
             if not P.set_y_perpendicular:  # (rotateXAxis is applied after the solve; covered by the direct check)
                 rr, tt = oracle_pose(m.corners, K, D, size)
@@ -70,9 +85,11 @@ def check_frame(det, grey, P, K=None, D=None, size=-1.0, hrm_text=None, frame=0,
             direct += rel_err(m.Rvec, r["rvec"]) < POSE_RTOL and rel_err(m.Tvec, r["tvec"]) < POSE_RTOL
         else:
             assert m.Rvec is None and m.ssize == -1.0
-    if size > 0 and K is not None and markers:
-        # near-frontal markers have two pose minima; a <=0.01 px corner difference may flip the one reached
-        assert direct >= min_direct_pose * len(markers), "only %d/%d poses agree directly" % (direct, len(markers))
+    if posed and markers:
+        assert direct >= min_direct_pose * len(markers), "only %d/%d poses agree with the C++ oracle" % (direct, len(markers))
+    if stats is not None:
+        stats["markers"] = stats.get("markers", 0) + len(markers)
+        stats["direct_port"] = stats.get("direct_port", 0) + direct
     if have_cv2():
         from oracle import cv2_oracle as o
         hc = o.HrmDictionary.from_yaml_text(hrm_text) if hrm_text else None
@@ -84,8 +101,20 @@ def check_frame(det, grey, P, K=None, D=None, size=-1.0, hrm_text=None, frame=0,
         for i, c in enumerate(b["candidates"]):
             assert (det.getContour(frame, i) == c["contour"]).all()
         assert [m.id for m in markers] == [m["id"] for m in b["markers"]]
+        direct_cv = 0
         for m, r in zip(markers, b["markers"]):
             assert np.abs(m.corners - r["corners"]).max() < CORNER_TOL
+            if posed:
+                if not P.set_y_perpendicular:
+                    rr, tt = cv2_pose(m.corners, K, D, size)
+                    assert rel_err(m.Rvec, rr) < POSE_RTOL and rel_err(m.Tvec, tt) < POSE_RTOL
+                direct_cv += rel_err(m.Rvec, r["rvec"]) < POSE_RTOL and rel_err(m.Tvec, r["tvec"]) < POSE_RTOL
+        if posed and markers:
+            assert direct_cv >= min_direct_pose * len(markers), "only %d/%d poses agree with the cv2 oracle" % (direct_cv, len(markers))
+        if stats is not None:
+            stats["direct_cv2"] = stats.get("direct_cv2", 0) + direct_cv
+            stats["corner_max_cv2"] = max(stats.get("corner_max_cv2", 0.0),
+                                          max([float(np.abs(m.corners - r["corners"]).max()) for m, r in zip(markers, b["markers"])] or [0.0]))
     return markers, ref
 
 
@@ -178,6 +207,63 @@ def test_synthetic_configs_all_stages(det, W, H, n, seed, sigma, kw):
     ms, _ = check_frame(det, g, P, K, D, 0.05)
     if not kw.get("erosion"):
         assert len(ms) >= 0.9 * n and set(m.id for m in ms) <= set(truth["ids"])
+
+
+@pytest.mark.parametrize("W,H,n,frames_n,kw", [
+    (1920, 1080, 50, 22, dict(corner_method=2)),  # C3: SUBPIX + PnP, >= 1000 markers
+    (1920, 1080, 50, 22, dict()),                 # 1080p LINES (the frames with near-frontal, bistable markers)
+    (3840, 2160, 100, 11, dict()),                # C4: LINES + PnP, >= 1000 markers
+])
+def test_pose_gate_c3_c4_against_both_oracles(det, W, H, n, frames_n, kw):
+    """North-star pose gate at >= 1000 markers per config: Rvec/Tvec of the GPU pipeline within 1e-4 relative of the
+    C++ oracle pipeline AND of the cv2 oracle pipeline (real OpenCV primitives; LINES fit = OpenCV's Jacobi SVD), for
+    >= 99.9 % of the markers, every stage before it bit-exact (check_frame)."""
+    from aruco_b200 import synth
+    K, D = synth.camera_for(W, H)
+    P = P_(**kw)
+    configure(det, P)
+    stats = {}
+    for i in range(frames_n):
+        g, _ = synth.render_frame(W, H, n, seed=700 + i, sigma=2.0)
+        check_frame(det, g, P, K, D, 0.05, stats=stats)
+    assert stats["markers"] >= 1000
+    assert stats["direct_port"] >= 0.999 * stats["markers"], stats
+    if have_cv2():
+        assert stats["direct_cv2"] >= 0.999 * stats["markers"], stats
+        if P.corner_method == 3:
+            assert stats["corner_max_cv2"] < 1e-4, stats  # same f32 arithmetic as OpenCV's Jacobi: far below the 0.01 px bar
+
+
+def test_pose_sensitivity_to_the_lapack_line_fit(det):
+    """This wheel's cv2.solve switches to LAPACK sgesdd from 25 rows on (OpenBLAS HAL); its f32 rounding differs from
+    OpenCV's own Jacobi SVD by ~1e-3 px in the LINES corners.  Against THAT oracle the corners still meet the 0.01 px bar
+    and the poses agree directly for >= 98 %; every remaining marker is explained by its corners alone: OpenCV's own
+    solvePnP on the GPU's corners returns the GPU's pose (checked for every marker inside check_frame)."""
+    if not have_cv2():
+        pytest.skip("cv2 needed")
+    from aruco_b200 import synth
+    from oracle import cv2_oracle as o
+    W, H = 1920, 1080
+    K, D = synth.camera_for(W, H)
+    P = P_()
+    configure(det, P)
+    tot = agree = 0
+    o.LINES_SOLVER = "cv2"
+    try:
+        for i in range(10):
+            g, _ = synth.render_frame(W, H, 50, seed=i, sigma=2.0)
+            ms = det.detect(g, K, D, 0.05)
+            b = o.detect(g, P, K, D, 0.05)
+            assert [m.id for m in ms] == [m["id"] for m in b["markers"]]
+            for m, r in zip(ms, b["markers"]):
+                assert np.abs(m.corners - r["corners"]).max() < CORNER_TOL
+                rr, tt = cv2_pose(m.corners, K, D, 0.05)
+                assert rel_err(m.Rvec, rr) < POSE_RTOL and rel_err(m.Tvec, tt) < POSE_RTOL
+                tot += 1
+                agree += rel_err(m.Rvec, r["rvec"]) < POSE_RTOL and rel_err(m.Tvec, r["tvec"]) < POSE_RTOL
+    finally:
+        o.LINES_SOLVER = "jacobi"
+    assert tot >= 450 and agree >= 0.98 * tot, (agree, tot)
 
 
 def test_parked_walk_queue_overflow_finishes_in_place(built, monkeypatch):
@@ -413,5 +499,5 @@ def test_c4_full_batch_every_frame_against_oracle(det):
             n_markers += 1
             direct += rel_err(a.Rvec, b["rvec"]) < POSE_RTOL and rel_err(a.Tvec, b["tvec"]) < POSE_RTOL
     assert n_markers > 0.9 * 100 * B
-    # GPU and oracle run the same f64 line fit here, so the poses agree directly (no bistability flips)
+    # GPU and oracle both run OpenCV's f32 Jacobi line fit (interpolate2Dline), so the poses agree directly
     assert direct >= 0.999 * n_markers, "%d/%d poses agree" % (direct, n_markers)

@@ -175,6 +175,28 @@ def test_undistort_points_bit_identical(hc, expected):
     assert (out == ref).all()
 
 
+def test_cross_point_bit_identical_to_cv2_solve(hc):
+    """getCrossPoint (markerdetector.cpp:132-139) = Matx22f::solve(DECOMP_SVD): the device function against cv2.solve."""
+    import cv2
+    rng = np.random.default_rng(3)
+    for _ in range(500):
+        k = rng.integers(0, 4)
+        l1 = np.array([rng.uniform(-1, 1), -1.0, rng.uniform(-4000, 4000)], np.float32)
+        l2 = np.array([-1.0, rng.uniform(-1, 1), rng.uniform(-4000, 4000)], np.float32)
+        if k == 1:
+            l1, l2 = l2, l1
+        elif k == 2:
+            l2 = np.array([rng.uniform(-1, 1), -1.0, rng.uniform(-4000, 4000)], np.float32)
+        elif k == 3:
+            l1 = np.array([-1.0, rng.uniform(-1, 1), rng.uniform(-4000, 4000)], np.float32)
+        A = np.array([[l1[0], l1[1]], [l2[0], l2[1]]], np.float32)
+        B = np.array([[-l1[2]], [-l2[2]]], np.float32)
+        ref = cv2.solve(A, B, flags=cv2.DECOMP_SVD)[1].ravel()
+        out = np.zeros(2, np.float32)
+        hc.hc_cross_point(P(l1), P(l2), P(out))
+        assert (out == ref).all(), (l1, l2, out, ref)
+
+
 def test_rotate_x_axis(hc):
     from oracle import cv2_oracle as o
     rng = np.random.default_rng(4)

@@ -101,28 +101,86 @@ def test_native_oracle_equals_cv2_oracle(built, frames, expected, name, prm, cam
             assert rel_err(x["rvec"], y["rvec"]) < POSE_RTOL and rel_err(x["tvec"], y["tvec"]) < POSE_RTOL
 
 
+def test_jacobi_svd_restatement_is_cv2_solve(built):
+    """interpolate2Dline / getCrossPoint call cv::solve(DECOMP_SVD) on CV_32F systems (markerdetector.cpp:112,124,138).
+    Below 25 rows cv2.solve runs OpenCV's own Jacobi SVD: both restatements (numpy in cv2_oracle, C++ in the port) are
+    BIT-identical to it for every row count 2..24; from 25 rows on (where this wheel hands over to LAPACK) the two
+    restatements stay bit-identical to each other."""
+    import ctypes as C
+    import cv2
+    from oracle import cv2_oracle as o
+    lib = native.load()
+    rng = np.random.default_rng(0)
+    for N in list(range(2, 25)) * 6 + [25, 60, 333, 1900] * 4:
+        x0, y0, sl = rng.integers(0, 3800), rng.integers(0, 2100), rng.uniform(-0.95, 0.95)
+        xs = (x0 + np.arange(N)).astype(np.float32)
+        ys = np.round(y0 + sl * np.arange(N) + rng.normal(0, 0.4, N)).astype(np.float32)
+        if rng.random() < 0.3:
+            xs = xs + rng.normal(0, 0.3, N).astype(np.float32)  # undistorted (non-integer) coordinates
+        A = np.ascontiguousarray(np.stack([xs, np.ones(N, np.float32)], 1))
+        B = np.ascontiguousarray(ys)
+        py = o.jacobi_svd_solve_f32(A, B.reshape(-1, 1))
+        cc = np.zeros(2, np.float32)
+        lib.orc_svd_solve_f32(A.ctypes.data_as(C.c_void_p), N, B.ctypes.data_as(C.c_void_p), cc.ctypes.data_as(C.c_void_p))
+        assert (py == cc).all(), N
+        if N < 25:
+            ref = cv2.solve(A, B.reshape(-1, 1), flags=cv2.DECOMP_SVD)[1].ravel()
+            assert (ref == py).all(), (N, ref, py)
+    for _ in range(200):  # the 2x2 systems of getCrossPoint
+        A = np.array([[rng.uniform(-1, 1), -1.0], [-1.0, rng.uniform(-1, 1)]], np.float32)
+        if rng.random() < 0.5:
+            A = A[::-1].copy()
+        B = rng.uniform(-4000, 4000, 2).astype(np.float32)
+        ref = cv2.solve(A, B.reshape(2, 1), flags=cv2.DECOMP_SVD)[1].ravel()
+        cc = np.zeros(2, np.float32)
+        lib.orc_svd_solve_f32(A.ctypes.data_as(C.c_void_p), 2, B.ctypes.data_as(C.c_void_p), cc.ctypes.data_as(C.c_void_p))
+        assert (ref == cc).all()
+
+
 def test_native_oracle_equals_cv2_oracle_synthetic_1080p(built):
-    """End to end on a C3-shaped frame.  LINES corners differ by ~1e-3 px between OpenCV's f32 SVD line fit and
-    an f64 fit; planar PnP of a near-frontal marker has two minima, and such a corner change can flip which one
-    cv2's 20-iteration LM reaches.  So the pose is checked strictly on IDENTICAL corners (cv2.solvePnP on the
-    native oracle's corners), and directly for the well-conditioned majority."""
+    """End to end on C3-shaped frames (seed 5 holds near-frontal markers whose planar PnP is bistable).  Both oracles fit
+    the LINES sides with OpenCV's f32 Jacobi SVD, so corners are bit-identical and EVERY pose agrees within 1e-4."""
     import cv2
     from oracle import cv2_oracle as o
     from aruco_b200 import synth
-    g, truth = synth.render_frame(1920, 1080, 50, seed=5, sigma=2.0)
+    for seed in (5, 8):
+        g, truth = synth.render_frame(1920, 1080, 50, seed=seed, sigma=2.0)
+        K, D = synth.camera_for(1920, 1080)
+        a = native.detect(g, Params(), K, D, 0.05)
+        b = o.detect(g, Params(), K, D, 0.05)
+        assert (a["thres"] == b["thres"]).all()
+        assert [m["id"] for m in a["markers"]] == [m["id"] for m in b["markers"]]
+        assert set(m["id"] for m in a["markers"]) <= set(truth["ids"]) and len(a["markers"]) >= 45
+        for x, y in zip(a["markers"], b["markers"]):
+            assert (x["corners"] == y["corners"]).all()
+            ok, rv, tv = cv2.solvePnP(o.object_points(0.05), x["corners"].reshape(4, 1, 2), K, D.reshape(1, 5))
+            assert rel_err(x["rvec"], rv.ravel()) < POSE_RTOL and rel_err(x["tvec"], tv.ravel()) < POSE_RTOL
+            assert rel_err(x["rvec"], y["rvec"]) < POSE_RTOL and rel_err(x["tvec"], y["tvec"]) < POSE_RTOL
+
+
+def test_lapack_line_fit_is_within_the_corner_bar(built):
+    """cv2.solve of this wheel (LAPACK sgesdd from 25 rows on) against OpenCV's Jacobi: LINES corners differ by ~1e-3 px
+    (f32 rounding of an ill-scaled system), far inside the 0.01 px bar; the pose of a few near-frontal markers is
+    sensitive to that (two close minima of planar PnP) -- >= 97 % still agree within 1e-4."""
+    from oracle import cv2_oracle as o
+    from aruco_b200 import synth
     K, D = synth.camera_for(1920, 1080)
-    a = native.detect(g, Params(), K, D, 0.05)
-    b = o.detect(g, Params(), K, D, 0.05)
-    assert (a["thres"] == b["thres"]).all()
-    assert [m["id"] for m in a["markers"]] == [m["id"] for m in b["markers"]]
-    assert set(m["id"] for m in a["markers"]) <= set(truth["ids"]) and len(a["markers"]) >= 45
-    direct = 0
-    for x, y in zip(a["markers"], b["markers"]):
-        assert np.abs(x["corners"] - y["corners"]).max() < CORNER_TOL
-        ok, rv, tv = cv2.solvePnP(o.object_points(0.05), x["corners"].reshape(4, 1, 2), K, D.reshape(1, 5))
-        assert rel_err(x["rvec"], rv.ravel()) < POSE_RTOL and rel_err(x["tvec"], tv.ravel()) < POSE_RTOL
-        direct += rel_err(x["rvec"], y["rvec"]) < POSE_RTOL and rel_err(x["tvec"], y["tvec"]) < POSE_RTOL
-    assert direct >= 0.85 * len(a["markers"])
+    tot = agree = 0
+    worst = 0.0
+    for seed in (0, 1, 5, 8):
+        g, _ = synth.render_frame(1920, 1080, 50, seed=seed, sigma=2.0)
+        a = o.detect(g, Params(), K, D, 0.05)
+        o.LINES_SOLVER = "cv2"
+        try:
+            b = o.detect(g, Params(), K, D, 0.05)
+        finally:
+            o.LINES_SOLVER = "jacobi"
+        assert [m["id"] for m in a["markers"]] == [m["id"] for m in b["markers"]]
+        for x, y in zip(a["markers"], b["markers"]):
+            worst = max(worst, float(np.abs(x["corners"] - y["corners"]).max()))
+            tot += 1
+            agree += rel_err(x["rvec"], y["rvec"]) < POSE_RTOL and rel_err(x["tvec"], y["tvec"]) < POSE_RTOL
+    assert worst < CORNER_TOL and agree >= 0.97 * tot, (worst, agree, tot)
 
 
 @pytest.mark.parametrize("name,kw", [("single", dict(corner_method=1)), ("board", dict(corner_method=1)),
