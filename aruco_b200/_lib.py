@@ -70,6 +70,7 @@ SYMBOLS = {
     "ab_threshold": (_i, [_vp, _vp, _i, _i, _sz, _i, _d, _d, _vp, _sz]),
     "ab_detect_rectangles": (_i, [_vp, _vp, _i, _i, _sz, _vp, _i, C.POINTER(C.c_int32)]),
     "ab_warp": (_i, [_vp, _vp, _i, _i, _sz, _vp, _i, _vp]),
+    "ab_refine_candidate_lines": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "ab_calculate_extrinsics": (_i, [_vp, _vp, _i, _vp, _vp, _f, _i]),
     "ab_detect_board": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _f, _i, _vp, _vp]),
     "ab_create_marker_image": (_i, [_vp, _i, _i, _i, _vp, _sz, C.POINTER(C.c_int)]),

@@ -89,9 +89,38 @@ struct ab_context {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t kev[12] = {};  // boundaries: threshold|scan|trace|trace_long|emit|polygon|filter|sample|identify|refine|finalize
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    // Two batches in flight: a second, library-owned context (`twin`) carries the second set of per-batch buffers and
+    // a private stream, so ab_enqueue_batch_device may be called again before ab_fetch_results and the kernels of
+    // batch n+1 run under the latency-bound tail of batch n.  Results come back in enqueue order.
+    ab_context* twin = nullptr;
+    ab_context* owner = nullptr;   // set in the twin: errors are reported through the owner
+    int pending[2] = {0, 0};       // FIFO of un-fetched batches: 0 = this context, 1 = the twin
+    int n_pending = 0;
+    int cur = 0;                   // which of the two the state getters read (last enqueued or fetched)
+    cudaEvent_t ev_in = nullptr;   // orders the twin's stream after the caller's stream at enqueue time
+    // capacities the caller chose in ab_reserve (0 = defaults); kept across automatic re-reservations
+    int userQ = 0, userC = 0;
+    long long userStarts = 0, userPoints = 0;
+};
+
+// RAII device temporary of the secondary entry points: freed on every return path
+struct DevBuf {
+    void* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T>
+    T* as() const {
+        return (T*)p;
+    }
 };
 
 static int set_err(ab_context* c, int code, const char* fmt, ...) {
+    if (c && c->owner) c = c->owner;
     if (c) {
         char buf[512];
         va_list ap;
@@ -199,9 +228,14 @@ int ab_create(int device, ab_context** out) {
             lut[WALK_LUT_SIZE + i] = walk_lut_bw_entry(i);
         }
         if (cudaMalloc(&ctx->d_walk_lut, lut.size()) != cudaSuccess ||
-            cudaMemcpy(ctx->d_walk_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaMemcpyAsync(ctx->d_walk_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
             cudaGetLastError();
-            ctx->d_walk_lut = nullptr;
+            if (ctx->d_walk_lut) cudaFree(ctx->d_walk_lut);
+            cudaStreamDestroy(ctx->stream);
+            cudaStreamDestroy(ctx->copy_stream);
+            delete ctx;
+            return AB_E_CUDA;
         }
     }
     if (const char* e = getenv("ARUCO_B200_SUBBATCHES")) ctx->n_sub_streams = std::max(1, std::min(MAX_SUB, atoi(e)));
@@ -217,12 +251,17 @@ int ab_create(int device, ab_context** out) {
         cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
     }
+    cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming);
     *out = ctx;
     return AB_OK;
 }
 
 void ab_destroy(ab_context* ctx) {
     if (!ctx) return;
+    if (ctx->twin) {
+        ab_destroy(ctx->twin);
+        ctx->twin = nullptr;
+    }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     free_buffers(ctx);
@@ -231,10 +270,13 @@ void ab_destroy(ab_context* ctx) {
         if (p) cudaFree(p);
         p = nullptr;
     };
-    F(ctx->d_dict_bits);
-    F(ctx->d_dict_ordids);
-    F(ctx->d_dict_ordpos);
-    F(ctx->d_dict_tree);
+    if (!ctx->owner) {  // the twin borrows the owner's dictionary
+        F(ctx->d_dict_bits);
+        F(ctx->d_dict_ordids);
+        F(ctx->d_dict_ordpos);
+        F(ctx->d_dict_tree);
+    }
+    if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
     for (int i = 0; i < 6; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 12; i++)
@@ -281,13 +323,10 @@ int ab_set_stream(ab_context* ctx, void* s) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
     }
-    if (s == nullptr) {
-        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        ctx->own_stream = true;
-    } else {
-        ctx->stream = (cudaStream_t)s;
-        ctx->own_stream = false;
-    }
+    // the handle is used as given: NULL is the caller's legacy default stream (handle 0), as torch's
+    // current_stream().cuda_stream reports it.  A fresh context runs on a private non-blocking stream until this is called.
+    ctx->stream = (cudaStream_t)s;
+    ctx->own_stream = false;
     return AB_OK;
 }
 
@@ -361,6 +400,8 @@ int ab_load_hrm_dictionary(ab_context* ctx, int n, int count, const uint8_t* bit
         if (p) cudaFree(p);
         p = nullptr;
     };
+    if (ctx->twin) cudaStreamSynchronize(ctx->twin->stream);  // it may still be decoding with the old dictionary
+    ctx->have_dict = false;
     F(ctx->d_dict_bits);
     F(ctx->d_dict_ordids);
     F(ctx->d_dict_ordpos);
@@ -369,10 +410,11 @@ int ab_load_hrm_dictionary(ab_context* ctx, int n, int count, const uint8_t* bit
     CK(cudaMalloc(&ctx->d_dict_ordids, sizeof(uint32_t) * count));
     CK(cudaMalloc(&ctx->d_dict_ordpos, sizeof(int32_t) * count));
     CK(cudaMalloc(&ctx->d_dict_tree, sizeof(int32_t) * 2 * count));
-    CK(cudaMemcpy(ctx->d_dict_bits, b0.data(), sizeof(uint64_t) * count, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_dict_ordids, ordids.data(), sizeof(uint32_t) * count, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_dict_ordpos, ordpos.data(), sizeof(int32_t) * count, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_dict_tree, tree.data(), sizeof(int32_t) * 2 * count, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(ctx->d_dict_bits, b0.data(), sizeof(uint64_t) * count, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_dict_ordids, ordids.data(), sizeof(uint32_t) * count, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_dict_ordpos, ordpos.data(), sizeof(int32_t) * count, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_dict_tree, tree.data(), sizeof(int32_t) * 2 * count, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
     ctx->dict.bits = ctx->d_dict_bits;
     ctx->dict.ids = nullptr;
     ctx->dict.ord_ids = ctx->d_dict_ordids;
@@ -386,19 +428,49 @@ int ab_load_hrm_dictionary(ab_context* ctx, int n, int count, const uint8_t* bit
     return AB_OK;
 }
 
-int ab_reserve(ab_context* ctx, int width, int height, int max_batch, int max_quads, int max_cands,
-               int64_t max_starts_pf, int64_t max_points_pf) {
-    if (!ctx || width < 8 || height < 8 || width > 16384 || height > 16384 || max_batch < 1)
-        return set_err(ctx, AB_E_INVALID, "ab_reserve: bad geometry %dx%d x%d", width, height, max_batch);
+static int reserve_impl(ab_context* ctx, int width, int height, int max_batch) {
     cudaSetDevice(ctx->device);
-    cudaDeviceSynchronize();
-    free_buffers(ctx);
-    int capQ = max_quads > 0 ? std::min(max_quads, MAX_QUADS) : MAX_QUADS;
-    int capC = max_cands > 0 ? std::min(max_cands, MAX_CANDS) : 512;
-    long long px = (long long)width * height;
-    long long capS = max_starts_pf > 0 ? max_starts_pf : std::max(px / 8, 65536LL);
-    long long capP = max_points_pf > 0 ? max_points_pf : std::max(px / 4, 65536LL);
+    cudaStreamSynchronize(ctx->stream);
+    free_buffers(ctx);  // zeroes W/H/maxB: a failed reservation leaves a context that re-reserves on the next call
+    const int capQ = ctx->userQ > 0 ? std::min(ctx->userQ, MAX_QUADS) : MAX_QUADS;
+    const int capC = ctx->userC > 0 ? std::min(ctx->userC, MAX_CANDS) : 512;
+    const long long px = (long long)width * height;
+    const long long capS = ctx->userStarts > 0 ? ctx->userStarts : std::max(px / 8, 65536LL);
+    long long capP = ctx->userPoints > 0 ? ctx->userPoints : std::max(px / 4, 65536LL);
     if (capP * max_batch > 0xFFFFFFF0LL) capP = 0xFFFFFFF0LL / max_batch;
+    const int S_alloc = std::max(ctx->params.warp_size, 56);
+    const size_t B = (size_t)max_batch;
+    const size_t bw = bit_image_words(width, height);
+    const size_t counters_bytes = MAX_SUB * sizeof(Counters) + 3 * B * sizeof(unsigned);
+    cudaError_t e = cudaSuccess;
+    auto A = [&](auto** p, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+    };
+    A(&ctx->d_thres, B * px);
+    A(&ctx->d_bits, B * bw * 4);
+    A(&ctx->d_bits2, B * bw * 4);
+    A(&ctx->d_starts, B * capS * sizeof(uint2));
+    A(&ctx->d_contours, B * ctx->capContoursPF * sizeof(ContourRec));
+    A(&ctx->d_pool, B * capP * 4);
+    A(&ctx->d_longq, B * ctx->capLongPF * sizeof(LongRec));
+    A(&ctx->d_emitq, B * ctx->capLongPF * sizeof(EmitRec));
+    A(&ctx->d_quads, B * capQ * sizeof(QuadRec));
+    A(&ctx->d_cands, B * capC * sizeof(CandRec));
+    A(&ctx->d_canon, B * capC * (size_t)S_alloc * S_alloc);
+    A(&ctx->d_aux, B * capC * sizeof(CandAux));
+    A(&ctx->d_hist, B * capC * 256 * sizeof(unsigned short));
+    A(&ctx->d_markers, B * capC * sizeof(ab_marker));
+    A(&ctx->d_counters, counters_bytes);
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_counters, counters_bytes);
+    // the zero frame around the packed image is written once; the kernels only write inside it
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_bits, 0, B * bw * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_bits2, 0, B * bw * 4, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        free_buffers(ctx);
+        return set_err(ctx, AB_E_CUDA, "ab_reserve(%dx%d x%d): %s", width, height, max_batch, cudaGetErrorString(e));
+    }
     ctx->W = width;
     ctx->H = height;
     ctx->maxB = max_batch;
@@ -406,35 +478,32 @@ int ab_reserve(ab_context* ctx, int width, int height, int max_batch, int max_qu
     ctx->capC = capC;
     ctx->capStartsPF = capS;
     ctx->capPoolPF = capP;
-    ctx->S_alloc = std::max(ctx->params.warp_size, 56);
-    size_t B = (size_t)max_batch;
-    size_t bw = bit_image_words(width, height);
-    CK(cudaMalloc(&ctx->d_thres, B * px));
-    CK(cudaMalloc(&ctx->d_bits, B * bw * 4));
-    CK(cudaMalloc(&ctx->d_bits2, B * bw * 4));
-    CK(cudaMemset(ctx->d_bits, 0, B * bw * 4));
-    CK(cudaMemset(ctx->d_bits2, 0, B * bw * 4));
-    CK(cudaMalloc(&ctx->d_starts, B * capS * sizeof(uint2)));
-    CK(cudaMalloc(&ctx->d_contours, B * ctx->capContoursPF * sizeof(ContourRec)));
-    CK(cudaMalloc(&ctx->d_pool, B * capP * 4));
-    CK(cudaMalloc(&ctx->d_longq, B * ctx->capLongPF * sizeof(LongRec)));
-    CK(cudaMalloc(&ctx->d_emitq, B * ctx->capLongPF * sizeof(EmitRec)));
-    CK(cudaMalloc(&ctx->d_quads, B * capQ * sizeof(QuadRec)));
-    CK(cudaMalloc(&ctx->d_cands, B * capC * sizeof(CandRec)));
-    CK(cudaMalloc(&ctx->d_canon, B * capC * (size_t)ctx->S_alloc * ctx->S_alloc));
-    CK(cudaMalloc(&ctx->d_aux, B * capC * sizeof(CandAux)));
-    CK(cudaMalloc(&ctx->d_hist, B * capC * 256 * sizeof(unsigned short)));
-    CK(cudaMalloc(&ctx->d_markers, B * capC * sizeof(ab_marker)));
-    ctx->counters_bytes = MAX_SUB * sizeof(Counters) + 3 * B * sizeof(unsigned);
-    CK(cudaMalloc(&ctx->d_counters, ctx->counters_bytes));
-    CK(cudaMallocHost(&ctx->h_counters, ctx->counters_bytes));
+    ctx->S_alloc = S_alloc;
+    ctx->counters_bytes = counters_bytes;
     return AB_OK;
 }
+
+int ab_reserve(ab_context* ctx, int width, int height, int max_batch, int max_quads, int max_cands,
+               int64_t max_starts_pf, int64_t max_points_pf) {
+    if (!ctx || width < 8 || height < 8 || width > 16384 || height > 16384 || max_batch < 1)
+        return set_err(ctx, AB_E_INVALID, "ab_reserve: bad geometry %dx%d x%d", width, height, max_batch);
+    if (ctx->n_pending) return set_err(ctx, AB_E_STATE, "ab_reserve: %d batch(es) in flight, fetch them first", ctx->n_pending);
+    // the caller's capacities are remembered: automatic re-reservations (larger batch, other warp size) keep them
+    ctx->userQ = max_quads;
+    ctx->userC = max_cands;
+    ctx->userStarts = max_starts_pf;
+    ctx->userPoints = max_points_pf;
+    if (ctx->twin) free_buffers(ctx->twin);  // re-reserved with the new capacities when it is next used
+    return reserve_impl(ctx, width, height, max_batch);
+}
+
+// threshold images per frame (setThresholdParamRange, cpp:322-334); CANNY ignores the parameters: one image
+static int n_thres_images(const ab_params& P) { return P.thres_method == AB_THRES_CANNY ? 1 : 2 * P.thres_param1_range + 1; }
 
 static int ensure_reserved(ab_context* ctx, int W, int H, int nB) {
     if (ctx->W == W && ctx->H == H && ctx->maxB >= nB && ctx->S_alloc >= ctx->params.warp_size) return AB_OK;
     int B = (ctx->W == W && ctx->H == H) ? std::max(ctx->maxB, nB) : nB;
-    return ab_reserve(ctx, W, H, B, ctx->capQ, ctx->capC, 0, 0);
+    return reserve_impl(ctx, W, H, B);
 }
 
 static Camera make_camera(const float* K, const float* D) {
@@ -507,7 +576,6 @@ static int launch_threshold(ab_context* ctx, const Batch& b, int method, double 
         // CANNY (src/markerdetector.cpp:669): cv::Canny(grey, out, 10, 220).  The map (0/1/2) is built in the
         // virtual frames' thres slots; hysteresis passes repeat until a group of passes changes no tile -- the
         // only place on the path where the host looks at a device flag mid-batch (the edge set is data dependent).
-        if (out_mul != 1) return set_err(ctx, AB_E_INVALID, "CANNY ignores threshold parameters: a parameter range makes no sense");
         uint8_t* map = b.thres;
         dim3 g1((b.W + 31) / 32, (b.H + 7) / 8, b.B);
         k_canny_nms<<<g1, dim3(32, 8), 0, st>>>(b.grey, b.grey_row, b.grey_frame, map, b.W, b.H, 10, 220);
@@ -535,15 +603,30 @@ __global__ void k_set_ids(Batch b, const int2* idrot) {
     b.cands[(size_t)f * b.cap_c + ci].nrot = v.y;
 }
 
-// cvtColor(BGR2GRAY) of OpenCV 4.x: (3735 B + 19235 G + 9798 R + 16384) >> 15   
+// cvtColor(BGR2GRAY) of OpenCV 4.x: (3735 B + 19235 G + 9798 R + 16384) >> 15   (SURVEY A.11).  A thread converts 4
+// consecutive pixels of a row (W % 4 == 0: three 32-bit loads, one 32-bit store; else bytes); the row/frame split is done
+// once per thread group of a row, not per pixel.
 __global__ void k_bgr2grey(const uint8_t* bgr, size_t row, size_t frame, uint8_t* grey, int W, int H, int B) {
-    size_t total = (size_t)W * H * B;
+    const int qpr = (W + 3) / 4;  // 4-pixel groups per row
+    const size_t total = (size_t)qpr * H * B;
+    const bool vec = (W & 3) == 0 && (row & 3) == 0 && (frame & 3) == 0 && (((uintptr_t)bgr | (uintptr_t)grey) & 3) == 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        int x = (int)(i % W);
-        int y = (int)((i / W) % H);
-        int f = (int)(i / ((size_t)W * H));
-        const uint8_t* p = bgr + (size_t)f * frame + (size_t)y * row + 3 * (size_t)x;
-        grey[i] = (uint8_t)((3735 * p[0] + 19235 * p[1] + 9798 * p[2] + 16384) >> 15);
+        const unsigned line = (unsigned)(i / (unsigned)qpr);  // < H * B < 2^32
+        const int q = (int)(i - (size_t)line * qpr);
+        const int f = (int)(line / (unsigned)H), y = (int)(line - (unsigned)f * H);
+        const uint8_t* p = bgr + (size_t)f * frame + (size_t)y * row + 12 * (size_t)q;
+        uint8_t* g = grey + ((size_t)f * H + y) * W + 4 * (size_t)q;
+        if (vec) {
+            const uint32_t w0 = *reinterpret_cast<const uint32_t*>(p), w1 = *reinterpret_cast<const uint32_t*>(p + 4),
+                           w2 = *reinterpret_cast<const uint32_t*>(p + 8);
+            auto lum = [](uint32_t bb, uint32_t gg, uint32_t rr) { return (3735u * bb + 19235u * gg + 9798u * rr + 16384u) >> 15; };
+            const uint32_t g0 = lum(w0 & 255, (w0 >> 8) & 255, (w0 >> 16) & 255), g1 = lum(w0 >> 24, w1 & 255, (w1 >> 8) & 255);
+            const uint32_t g2 = lum((w1 >> 16) & 255, w1 >> 24, w2 & 255), g3 = lum((w2 >> 8) & 255, (w2 >> 16) & 255, w2 >> 24);
+            *reinterpret_cast<uint32_t*>(g) = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+        } else {
+            for (int k = 0; k < 4 && 4 * q + k < W; k++)
+                g[k] = (uint8_t)((3735 * p[3 * k] + 19235 * p[3 * k + 1] + 9798 * p[3 * k + 2] + 16384) >> 15);
+        }
     }
 }
 
@@ -712,12 +795,11 @@ static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
                 int id = ctx->cb(canon.data() + ((size_t)f * b.cap_c + c) * ss, b.S, &nrot, ctx->cb_user);
                 idrot[(size_t)f * b.cap_c + c] = make_int2(id, nrot);
             }
-        int2* d_idrot = nullptr;
-        CK(cudaMalloc(&d_idrot, idrot.size() * sizeof(int2)));
-        CK(cudaMemcpyAsync(d_idrot, idrot.data(), idrot.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-        k_set_ids<<<dim3((b.cap_c + 127) / 128, n), 128, 0, st>>>(b, d_idrot);
+        DevBuf d_idrot;
+        CK(d_idrot.alloc(idrot.size() * sizeof(int2)));
+        CK(cudaMemcpyAsync(d_idrot.p, idrot.data(), idrot.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+        k_set_ids<<<dim3((b.cap_c + 127) / 128, n), 128, 0, st>>>(b, d_idrot.as<int2>());
         CK(cudaStreamSynchronize(st));
-        cudaFree(d_idrot);
     } else {
         k_otsu<<<dim3((b.cap_c + 31) / 32, n), 32, 0, st>>>(b);
         k_identify<<<gdec, 32 * DECODE_WARPS, dec_smem, st>>>(b);
@@ -768,7 +850,9 @@ static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t f
     // setThresholdParamRange (markerdetector.h:152, cpp:322-334): 2*range+1 threshold images per frame, param1 =
     // p1 - range + range*i (sic); they live as n_t consecutive "virtual frames" per frame for the
     // threshold / contour / polygon stages and are merged per frame by k_polygon's quad keys.
-    const int n_t = 2 * P.thres_param1_range + 1;
+    // CANNY ignores the parameters: the reference's 2r+1 identical edge images yield duplicate candidates that its
+    // too-near filter removes again (cpp:322-334, :592-627), so one image gives the same result.
+    const int n_t = n_thres_images(P);
     if (n * n_t > ctx->maxB) return set_err(ctx, AB_E_STATE, "internal: %d virtual frames > reserved %d", n * n_t, ctx->maxB);
     Batch b;
     fill_batch(ctx, b, dgrey, row, frame, n, K, D, marker_size);
@@ -821,13 +905,66 @@ static int check_device_errors(ab_context* ctx, const Counters* c) {
                    what.c_str());
 }
 
+// the second set of per-batch buffers: a library-owned context that mirrors the owner's configuration
+static int get_twin(ab_context* ctx, ab_context** out) {
+    if (!ctx->twin) {
+        ab_context* t = nullptr;
+        int rc = ab_create(ctx->device, &t);
+        if (rc) return set_err(ctx, rc, "cannot create the second in-flight context");
+        t->owner = ctx;
+        ctx->twin = t;
+    }
+    ab_context* t = ctx->twin;
+    t->params = ctx->params;
+    t->dict = ctx->dict;  // device pointers owned by `ctx`
+    t->have_dict = ctx->have_dict;
+    t->cb = ctx->cb;
+    t->cb_user = ctx->cb_user;
+    t->timing = ctx->timing;
+    t->n_sub_streams = ctx->n_sub_streams;
+    t->capLongPF = ctx->capLongPF;
+    if (t->userQ != ctx->userQ || t->userC != ctx->userC || t->userStarts != ctx->userStarts || t->userPoints != ctx->userPoints) {
+        free_buffers(t);
+        t->userQ = ctx->userQ;
+        t->userC = ctx->userC;
+        t->userStarts = ctx->userStarts;
+        t->userPoints = ctx->userPoints;
+    }
+    *out = t;
+    return AB_OK;
+}
+
+static ab_context* slot_of(ab_context* ctx, int which) { return which ? ctx->twin : ctx; }
+static ab_context* current_of(ab_context* ctx) { return (ctx->cur && ctx->twin) ? ctx->twin : ctx; }
+
+// enqueue on this context or (when it still holds an un-fetched batch) on its twin
+static int enqueue_on_free_slot(ab_context* ctx, const uint8_t* dev_frames, int width, int height, size_t row_stride,
+                                size_t frame_stride, int n_frames, const float* K, const float* D, float marker_size) {
+    if (ctx->n_pending >= 2)
+        return set_err(ctx, AB_E_STATE, "two batches are already in flight: call ab_fetch_results before enqueueing a third");
+    int which = ctx->n_pending == 1 ? 1 - ctx->pending[0] : 0;
+    ab_context* tgt = ctx;
+    if (which) {
+        int rc = get_twin(ctx, &tgt);
+        if (rc) return rc;
+        // the frames were produced on the owner's stream
+        CK(cudaEventRecord(ctx->ev_in, ctx->stream));
+        CK(cudaStreamWaitEvent(tgt->stream, ctx->ev_in, 0));
+    }
+    int rc = ensure_reserved(tgt, width, height, n_frames * n_thres_images(ctx->params));
+    if (rc) return rc;
+    rc = run_batch(tgt, dev_frames, row_stride, frame_stride, n_frames, K, D, marker_size);
+    if (rc) return rc;
+    ctx->pending[ctx->n_pending++] = which;
+    ctx->cur = which;
+    return AB_OK;
+}
+
 int ab_enqueue_batch_device(ab_context* ctx, const uint8_t* dev_frames, int width, int height, size_t row_stride,
                             size_t frame_stride, int n_frames, const float* K, const float* D, float marker_size) {
     if (!ctx || !dev_frames || n_frames < 1 || row_stride < (size_t)width) return set_err(ctx, AB_E_INVALID, "bad arguments");
     cudaSetDevice(ctx->device);
-    int rc = ensure_reserved(ctx, width, height, n_frames * (2 * ctx->params.thres_param1_range + 1));
-    if (rc) return rc;
-    return run_batch(ctx, dev_frames, row_stride, frame_stride, n_frames, K, D, marker_size);
+    return enqueue_on_free_slot(ctx, dev_frames, width, height, row_stride, frame_stride, n_frames, K, D, marker_size);
 }
 
 static int fetch_into(ab_context* ctx, ab_marker* out, int cap, int32_t* counts) {
@@ -862,90 +999,136 @@ static int fetch_into(ab_context* ctx, ab_marker* out, int cap, int32_t* counts)
     return AB_OK;
 }
 
+// results of the OLDEST un-fetched batch (enqueue order); with nothing pending: of the current batch again
+static int fetch_oldest(ab_context* ctx, ab_marker* out, int cap, int32_t* counts) {
+    int which = ctx->cur;
+    if (ctx->n_pending) {
+        which = ctx->pending[0];
+        ctx->pending[0] = ctx->pending[1];
+        ctx->n_pending--;
+    }
+    ctx->cur = which;
+    return fetch_into(slot_of(ctx, which), out, cap, counts);
+}
+
 int ab_fetch_results(ab_context* ctx, ab_marker* out, int cap_per_frame, int32_t* counts) {
     if (!ctx || cap_per_frame < 0) return AB_E_INVALID;
     cudaSetDevice(ctx->device);
-    return fetch_into(ctx, out, cap_per_frame, counts);
+    return fetch_oldest(ctx, out, cap_per_frame, counts);
 }
 
 static int ensure_grey(ab_context* ctx, size_t bytes) {
     if (ctx->grey_bytes >= bytes) return AB_OK;
+    ctx->grey_bytes = 0;
     for (int i = 0; i < 2; i++) {
         if (ctx->d_grey[i]) cudaFree(ctx->d_grey[i]);
         ctx->d_grey[i] = nullptr;
-        CK(cudaMalloc(&ctx->d_grey[i], bytes));
     }
+    for (int i = 0; i < 2; i++) CK(cudaMalloc(&ctx->d_grey[i], bytes));
     ctx->grey_bytes = bytes;
     return AB_OK;
 }
 
+// Host frames -> markers.  The batch goes through in chunks: the H2D copy of chunk c+1 (copy stream) runs under the
+// kernels of chunk c, chunks alternate between this context and its twin so the kernels of chunk c+1 start under the
+// latency-bound tail of chunk c, and the markers of chunk c-1 are copied back while chunk c runs.
 static int detect_host(ab_context* ctx, const uint8_t* frames, int width, int height, size_t row_stride, size_t frame_stride,
                        int n_frames, const float* K, const float* D, float marker_size, ab_marker* out, int cap, int32_t* counts,
                        int channels) {
     if (!ctx || !frames || n_frames < 1 || row_stride < (size_t)width * channels || cap < 0)
         return set_err(ctx, AB_E_INVALID, "bad arguments");
+    if (ctx->n_pending) return set_err(ctx, AB_E_STATE, "%d enqueued batch(es) not fetched yet", ctx->n_pending);
     cudaSetDevice(ctx->device);
     // chunk size: what was reserved for this geometry, else up to 32 frames
-    const int n_t = 2 * ctx->params.thres_param1_range + 1;
+    const int n_t = n_thres_images(ctx->params);
     int chunk = (ctx->W == width && ctx->H == height && ctx->maxB >= n_t) ? std::min(ctx->maxB / n_t, n_frames) : std::min(n_frames, 32);
     int rc = ensure_reserved(ctx, width, height, chunk * n_t);
     if (rc) return rc;
     chunk = std::min(ctx->maxB / n_t, n_frames);
-    size_t fpx = (size_t)width * height;
+    const size_t fpx = (size_t)width * height;
+    const int nchunks = (n_frames + chunk - 1) / chunk;
+    const bool two = nchunks > 1 && channels == 1 && ctx->params.decoder != AB_DECODER_HOST_CALLBACK;
+    ab_context* slot[2] = {ctx, ctx};
+    if (two) {
+        rc = get_twin(ctx, &slot[1]);
+        if (rc) return rc;
+        rc = ensure_reserved(slot[1], width, height, chunk * n_t);
+        if (rc) return rc;
+        rc = ensure_grey(slot[1], fpx * chunk);
+        if (rc) return rc;
+    }
     rc = ensure_grey(ctx, fpx * chunk);
     if (rc) return rc;
     if (channels == 3 && ctx->bgr_bytes < fpx * 3 * chunk) {
         if (ctx->d_bgr) cudaFree(ctx->d_bgr);
         ctx->d_bgr = nullptr;
+        ctx->bgr_bytes = 0;
         CK(cudaMalloc(&ctx->d_bgr, fpx * 3 * chunk));
         ctx->bgr_bytes = fpx * 3 * chunk;
     }
-    int nchunks = (n_frames + chunk - 1) / chunk;
-    // H2D of chunk c+1 (copy stream) overlaps the kernels of chunk c (compute stream); results of chunk c
-    // are fetched before chunk c+1 is launched, so every intermediate buffer is single-buffered.
+    auto staging = [&](int c) -> uint8_t* { return two ? slot[c & 1]->d_grey[0] : ctx->d_grey[c & 1]; };
     auto upload = [&](int c) -> int {
         int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
         int buf = c & 1;
-        if (c >= 2) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[buf], 0));
+        if (c >= 2) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[buf], 0));  // chunk c-2 has read this buffer
+        uint8_t* dst = staging(c);
         if (channels == 1) {
             if (frame_stride == row_stride * (size_t)height) {
-                CK(cudaMemcpy2DAsync(ctx->d_grey[buf], width, frames + (size_t)f0 * frame_stride, row_stride, width,
-                                     (size_t)height * nf, cudaMemcpyHostToDevice, ctx->copy_stream));
+                CK(cudaMemcpy2DAsync(dst, width, frames + (size_t)f0 * frame_stride, row_stride, width, (size_t)height * nf,
+                                     cudaMemcpyHostToDevice, ctx->copy_stream));
             } else {
                 for (int f = 0; f < nf; f++)
-                    CK(cudaMemcpy2DAsync(ctx->d_grey[buf] + (size_t)f * fpx, width, frames + (size_t)(f0 + f) * frame_stride,
-                                         row_stride, width, height, cudaMemcpyHostToDevice, ctx->copy_stream));
+                    CK(cudaMemcpy2DAsync(dst + (size_t)f * fpx, width, frames + (size_t)(f0 + f) * frame_stride, row_stride, width,
+                                         height, cudaMemcpyHostToDevice, ctx->copy_stream));
             }
         } else {
             for (int f = 0; f < nf; f++)
                 CK(cudaMemcpy2DAsync(ctx->d_bgr + (size_t)f * fpx * 3, (size_t)width * 3, frames + (size_t)(f0 + f) * frame_stride,
                                      row_stride, (size_t)width * 3, height, cudaMemcpyHostToDevice, ctx->copy_stream));
-            k_bgr2grey<<<ctx->sm_count * 8, 256, 0, ctx->copy_stream>>>(ctx->d_bgr, (size_t)width * 3, fpx * 3, ctx->d_grey[buf],
-                                                                       width, height, nf);
+            const size_t groups = (size_t)((width + 3) / 4) * height * nf;
+            const int blocks = (int)std::min<size_t>((groups + 255) / 256, (size_t)ctx->sm_count * 16);
+            k_bgr2grey<<<blocks, 256, 0, ctx->copy_stream>>>(ctx->d_bgr, (size_t)width * 3, fpx * 3, dst, width, height, nf);
         }
         CK(cudaEventRecord(ctx->ev_h2d[buf], ctx->copy_stream));
         return AB_OK;
     };
+    auto fetch_chunk = [&](int c) -> int {
+        const int f0 = c * chunk;
+        return fetch_into(two ? slot[c & 1] : ctx, out ? out + (size_t)f0 * cap : nullptr, cap, counts ? counts + f0 : nullptr);
+    };
     rc = upload(0);
     if (rc) return rc;
     for (int c = 0; c < nchunks; c++) {
-        int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
-        int buf = c & 1;
+        const int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
+        const int buf = c & 1;
+        ab_context* tgt = two ? slot[buf] : ctx;
         if (c + 1 < nchunks && channels == 1) {
             rc = upload(c + 1);
             if (rc) return rc;
         }
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[buf], 0));
-        rc = run_batch(ctx, ctx->d_grey[buf], width, fpx, nf, K, D, marker_size);
+        CK(cudaStreamWaitEvent(tgt->stream, ctx->ev_h2d[buf], 0));
+        rc = run_batch(tgt, staging(c), width, fpx, nf, K, D, marker_size);
         if (rc) return rc;
-        CK(cudaEventRecord(ctx->ev_done[buf], ctx->stream));
-        rc = fetch_into(ctx, out ? out + (size_t)f0 * cap : nullptr, cap, counts ? counts + f0 : nullptr);
-        if (rc) return rc;
-        if (c + 1 < nchunks && channels == 3) {  // the BGR staging buffer is single: upload after the fetch
-            rc = upload(c + 1);
+        CK(cudaEventRecord(ctx->ev_done[buf], tgt->stream));
+        if (two) {
+            if (c >= 1) {
+                rc = fetch_chunk(c - 1);
+                if (rc) return rc;
+            }
+        } else {
+            rc = fetch_chunk(c);
             if (rc) return rc;
+            if (c + 1 < nchunks && channels == 3) {  // the BGR staging buffer is single: upload after the fetch
+                rc = upload(c + 1);
+                if (rc) return rc;
+            }
         }
     }
+    if (two) {
+        rc = fetch_chunk(nchunks - 1);
+        if (rc) return rc;
+    }
+    ctx->cur = two ? ((nchunks - 1) & 1) : 0;  // the state getters read the last chunk
     return AB_OK;
 }
 
@@ -965,25 +1148,30 @@ int ab_detect_batch_bgr(ab_context* ctx, const uint8_t* frames, int width, int h
 
 // ---- state of the last batch ---------------------------------------------------------------------------
 int ab_get_thresholded(ab_context* ctx, int frame, uint8_t* dst, size_t dst_stride) {
+    if (ctx) ctx = current_of(ctx);
     if (!ctx || !ctx->have_last || frame < 0 || frame >= ctx->last_n || !dst) return set_err(ctx, AB_E_INVALID, "bad frame");
     cudaSetDevice(ctx->device);
     const Batch& b = ctx->last;
-    CK(cudaStreamSynchronize(ctx->stream));
     // `thres` = the middle threshold image (thres_images[n_param1 / 2], markerdetector.cpp:334)
-    CK(cudaMemcpy2D(dst, dst_stride, b.thres + ((size_t)frame * b.n_t + b.n_t / 2) * b.W * b.H, b.W, b.W, b.H, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy2DAsync(dst, dst_stride, b.thres + ((size_t)frame * b.n_t + b.n_t / 2) * b.W * b.H, b.W, b.W, b.H,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return AB_OK;
 }
 
 int ab_get_grey(ab_context* ctx, int frame, uint8_t* dst, size_t dst_stride) {
+    if (ctx) ctx = current_of(ctx);
     if (!ctx || !ctx->have_last || frame < 0 || frame >= ctx->last_n || !dst) return set_err(ctx, AB_E_INVALID, "bad frame");
     cudaSetDevice(ctx->device);
     const Batch& b = ctx->last;
+    CK(cudaMemcpy2DAsync(dst, dst_stride, b.grey + (size_t)frame * b.grey_frame, b.grey_row, b.W, b.H, cudaMemcpyDeviceToHost,
+                         ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy2D(dst, dst_stride, b.grey + (size_t)frame * b.grey_frame, b.grey_row, b.W, b.H, cudaMemcpyDeviceToHost));
     return AB_OK;
 }
 
 int ab_get_candidates(ab_context* ctx, int frame, float* quads, int32_t* ids, int32_t* n_rot, int cap, int32_t* n) {
+    if (ctx) ctx = current_of(ctx);
     if (!ctx || !ctx->have_last || frame < 0 || frame >= ctx->last_n || !n) return set_err(ctx, AB_E_INVALID, "bad frame");
     cudaSetDevice(ctx->device);
     const Batch& b = ctx->last;
@@ -1004,6 +1192,7 @@ int ab_get_candidates(ab_context* ctx, int frame, float* quads, int32_t* ids, in
 }
 
 int ab_get_canonical(ab_context* ctx, int frame, int candidate, uint8_t* dst) {
+    if (ctx) ctx = current_of(ctx);
     if (!ctx || !ctx->have_last || frame < 0 || frame >= ctx->last_n || !dst || candidate < 0 || candidate >= ctx->last.cap_c)
         return set_err(ctx, AB_E_INVALID, "bad frame/candidate");
     cudaSetDevice(ctx->device);
@@ -1015,6 +1204,7 @@ int ab_get_canonical(ab_context* ctx, int frame, int candidate, uint8_t* dst) {
 }
 
 int ab_get_contour(ab_context* ctx, int frame, int candidate, int32_t* xy, int cap_points, int32_t* n) {
+    if (ctx) ctx = current_of(ctx);
     if (!ctx || !ctx->have_last || frame < 0 || frame >= ctx->last_n || !n || candidate < 0 || candidate >= ctx->last.cap_c)
         return set_err(ctx, AB_E_INVALID, "bad frame/candidate");
     cudaSetDevice(ctx->device);
@@ -1043,6 +1233,7 @@ int ab_get_contour(ab_context* ctx, int frame, int candidate, int32_t* xy, int c
 }
 
 int ab_get_counters(ab_context* ctx, int64_t* counters, int n) {
+    if (ctx) ctx = current_of(ctx);
     if (!ctx || !ctx->have_last || !counters) return set_err(ctx, AB_E_INVALID, "no batch");
     cudaSetDevice(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1063,6 +1254,7 @@ int ab_get_counters(ab_context* ctx, int64_t* counters, int n) {
 }
 
 int ab_get_stage_ms(ab_context* ctx, float* ms, int n) {
+    if (ctx) ctx = current_of(ctx);
     if (!ctx || !ms || !ctx->timing || !ctx->have_last) return set_err(ctx, AB_E_STATE, "timing not enabled");
     cudaSetDevice(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1071,6 +1263,7 @@ int ab_get_stage_ms(ab_context* ctx, float* ms, int n) {
 }
 
 int ab_get_kernel_ms(ab_context* ctx, float* ms, int n) {
+    if (ctx) ctx = current_of(ctx);
     if (!ctx || !ms || !ctx->timing || !ctx->have_last) return set_err(ctx, AB_E_STATE, "timing not enabled");
     cudaSetDevice(ctx->device);
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1082,6 +1275,8 @@ int ab_get_kernel_ms(ab_context* ctx, float* ms, int n) {
 int ab_threshold(ab_context* ctx, const uint8_t* grey, int width, int height, size_t row_stride, int method, double param1,
                  double param2, uint8_t* out, size_t out_stride) {
     if (!ctx || !grey || !out) return AB_E_INVALID;
+    if (ctx->n_pending) return set_err(ctx, AB_E_STATE, "%d enqueued batch(es) not fetched yet", ctx->n_pending);
+    ctx->cur = 0;
     cudaSetDevice(ctx->device);
     int rc = ensure_reserved(ctx, width, height, 1);
     if (rc) return rc;
@@ -1103,6 +1298,8 @@ int ab_threshold(ab_context* ctx, const uint8_t* grey, int width, int height, si
 int ab_detect_rectangles(ab_context* ctx, const uint8_t* thres, int width, int height, size_t row_stride, float* quads, int cap,
                          int32_t* n) {
     if (!ctx || !thres || !n) return AB_E_INVALID;
+    if (ctx->n_pending) return set_err(ctx, AB_E_STATE, "%d enqueued batch(es) not fetched yet", ctx->n_pending);
+    ctx->cur = 0;
     cudaSetDevice(ctx->device);
     int rc = ensure_reserved(ctx, width, height, 1);
     if (rc) return rc;
@@ -1136,22 +1333,61 @@ int ab_detect_rectangles(ab_context* ctx, const uint8_t* thres, int width, int h
 
 int ab_warp(ab_context* ctx, const uint8_t* grey, int width, int height, size_t row_stride, const float* quad, int size,
             uint8_t* out) {
-    if (!ctx || !grey || !quad || !out || size < 1 || size > 1024) return set_err(ctx, AB_E_INVALID, "bad arguments");
+    if (!ctx || !grey || !quad || !out || size < 1 || size > 1024 || width < 1 || height < 1 || row_stride < (size_t)width)
+        return set_err(ctx, AB_E_INVALID, "bad arguments");
     cudaSetDevice(ctx->device);
-    uint8_t *d_img = nullptr, *d_out = nullptr;
-    float* d_quad = nullptr;
-    CK(cudaMalloc(&d_img, (size_t)width * height));
-    CK(cudaMalloc(&d_out, (size_t)size * size));
-    CK(cudaMalloc(&d_quad, 8 * sizeof(float)));
-    CK(cudaMemcpy2D(d_img, width, grey, row_stride, width, height, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_quad, quad, 8 * sizeof(float), cudaMemcpyHostToDevice));
-    k_warp_single<<<1, 256, 0, ctx->stream>>>(d_img, width, height, width, d_quad, size, d_out);
+    cudaStream_t st = ctx->stream;
+    DevBuf d_img, d_out, d_quad;
+    CK(d_img.alloc((size_t)width * height));
+    CK(d_out.alloc((size_t)size * size));
+    CK(d_quad.alloc(8 * sizeof(float)));
+    CK(cudaMemcpy2DAsync(d_img.p, width, grey, row_stride, width, height, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_quad.p, quad, 8 * sizeof(float), cudaMemcpyHostToDevice, st));
+    k_warp_single<<<1, 256, 0, st>>>(d_img.as<uint8_t>(), width, height, width, d_quad.as<float>(), size, d_out.as<uint8_t>());
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy(out, d_out, (size_t)size * size, cudaMemcpyDeviceToHost));
-    cudaFree(d_img);
-    cudaFree(d_out);
-    cudaFree(d_quad);
+    CK(cudaMemcpyAsync(out, d_out.p, (size_t)size * size, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return AB_OK;
+}
+
+// MarkerDetector::refineCandidateLines (h:280, cpp:931-997) for one candidate
+int ab_refine_candidate_lines(ab_context* ctx, const int32_t* contour_xy, int n_points, float* corners, const float* K,
+                              const float* D) {
+    if (!ctx || !contour_xy || !corners || n_points < 4 || n_points > (1 << 24))
+        return set_err(ctx, AB_E_INVALID, "refineCandidateLines: bad arguments");
+    std::vector<uint32_t> packed((size_t)n_points);
+    for (int i = 0; i < n_points; i++) {
+        const int32_t x = contour_xy[2 * i], y = contour_xy[2 * i + 1];
+        if (x < 0 || y < 0 || x > 0xFFFF || y > 0xFFFF) return set_err(ctx, AB_E_INVALID, "refineCandidateLines: contour point outside 0..65535");
+        packed[i] = (uint32_t)x | ((uint32_t)y << 16);
+    }
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    DevBuf d_pts, d_io, d_err;
+    CK(d_pts.alloc(packed.size() * 4));
+    CK(d_io.alloc(16 * sizeof(float)));
+    CK(d_err.alloc(sizeof(unsigned)));
+    CK(cudaMemcpyAsync(d_pts.p, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_io.p, corners, 8 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_io.as<float>() + 8, 0xFF, 8 * sizeof(float), st));  // NaN pattern: "corner not found on the contour"
+    CK(cudaMemsetAsync(d_err.p, 0, sizeof(unsigned), st));
+    // the reference undistorts only when both matrices are given (cpp:957-959)
+    const Camera cam = make_camera(K && D ? K : nullptr, K && D ? D : nullptr);
+    if (cam.has_K && cam.has_D && !cam.zero_D)
+        k_refine_lines_single<true><<<1, 128, LINES_CACHE_POINTS * sizeof(float2), st>>>(d_pts.as<uint32_t>(), n_points, d_io.as<float>(), cam,
+                                                                                         LINES_CACHE_POINTS, d_io.as<float>() + 8, d_err.as<unsigned>());
+    else
+        k_refine_lines_single<false><<<1, 128, 0, st>>>(d_pts.as<uint32_t>(), n_points, d_io.as<float>(), cam, 0, d_io.as<float>() + 8,
+                                                        d_err.as<unsigned>());
+    CK(cudaGetLastError());
+    float res[8];
+    unsigned err = 0;
+    CK(cudaMemcpyAsync(res, d_io.as<float>() + 8, sizeof(res), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&err, d_err.p, sizeof(err), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (err) return set_err(ctx, AB_E_CAPACITY, "refineCandidateLines: line fit did not converge within the sweeps the kernel replays");
+    if (res[0] != res[0]) return set_err(ctx, AB_E_INVALID, "refineCandidateLines: a corner is not a point of the contour");
+    memcpy(corners, res, sizeof(res));
     return AB_OK;
 }
 
@@ -1159,23 +1395,20 @@ int ab_warp(ab_context* ctx, const uint8_t* grey, int width, int height, size_t 
 static int render_canvas(ab_context* ctx, int W, int H, uint8_t background, const std::vector<RenderRect>& rects, int n_black,
                          uint8_t* out, size_t out_stride) {
     cudaSetDevice(ctx->device);
-    uint8_t* d_img = nullptr;
-    RenderRect* d_rects = nullptr;
-    CK(cudaMalloc(&d_img, (size_t)W * H));
-    k_fill_u8<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_img, (size_t)W * H, background);
+    DevBuf d_img, d_rects;
+    CK(d_img.alloc((size_t)W * H));
+    k_fill_u8<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_img.as<uint8_t>(), (size_t)W * H, background);
     if (!rects.empty()) {
-        CK(cudaMalloc(&d_rects, rects.size() * sizeof(RenderRect)));
-        CK(cudaMemcpyAsync(d_rects, rects.data(), rects.size() * sizeof(RenderRect), cudaMemcpyHostToDevice, ctx->stream));
+        CK(d_rects.alloc(rects.size() * sizeof(RenderRect)));
+        CK(cudaMemcpyAsync(d_rects.p, rects.data(), rects.size() * sizeof(RenderRect), cudaMemcpyHostToDevice, ctx->stream));
         int maxs = 1;
         for (const auto& r : rects) maxs = std::max(maxs, r.size);
         dim3 grid((unsigned)std::min(1024, (maxs * maxs + 255) / 256), (unsigned)rects.size());
-        k_render_fiducidal<<<grid, 256, 0, ctx->stream>>>(d_img, W, H, d_rects, n_black);
+        k_render_fiducidal<<<grid, 256, 0, ctx->stream>>>(d_img.as<uint8_t>(), W, H, d_rects.as<RenderRect>(), n_black);
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpy2DAsync(out, out_stride, d_img, W, W, H, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpy2DAsync(out, out_stride, d_img.p, W, W, H, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_img);
-    if (d_rects) cudaFree(d_rects);
     return AB_OK;
 }
 
@@ -1253,16 +1486,15 @@ int ab_create_hrm_marker_image(ab_context* ctx, int n, const uint8_t* bits, int 
     if (!out) return AB_OK;
     if (!bits || out_stride < (size_t)pix_size) return set_err(ctx, AB_E_INVALID, "getImg: bad arguments");
     cudaSetDevice(ctx->device);
-    uint8_t *d_img = nullptr, *d_bits = nullptr;
-    CK(cudaMalloc(&d_img, (size_t)pix_size * pix_size));
-    CK(cudaMalloc(&d_bits, (size_t)n * n));
-    CK(cudaMemcpyAsync(d_bits, bits, (size_t)n * n, cudaMemcpyHostToDevice, ctx->stream));
-    k_render_hrm<<<std::min(1024, (pix_size * pix_size + 255) / 256), 256, 0, ctx->stream>>>(d_img, pix_size, n, d_bits);
+    DevBuf d_img, d_bits;
+    CK(d_img.alloc((size_t)pix_size * pix_size));
+    CK(d_bits.alloc((size_t)n * n));
+    CK(cudaMemcpyAsync(d_bits.p, bits, (size_t)n * n, cudaMemcpyHostToDevice, ctx->stream));
+    k_render_hrm<<<std::min(1024, (pix_size * pix_size + 255) / 256), 256, 0, ctx->stream>>>(d_img.as<uint8_t>(), pix_size, n,
+                                                                                             d_bits.as<uint8_t>());
     CK(cudaGetLastError());
-    CK(cudaMemcpy2DAsync(out, out_stride, d_img, pix_size, pix_size, pix_size, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpy2DAsync(out, out_stride, d_img.p, pix_size, pix_size, pix_size, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_img);
-    cudaFree(d_bits);
     return AB_OK;
 }
 
@@ -1298,21 +1530,18 @@ int ab_create_hrm_board_image(ab_context* ctx, int grid_w, int grid_h, int n, co
             for (int k = 0; k < 12; k++) corners_out[12 * idp + k] = c[k];
         }
     cudaSetDevice(ctx->device);
-    uint8_t *d_img = nullptr, *d_bits = nullptr;
-    RenderRect* d_rects = nullptr;
-    CK(cudaMalloc(&d_img, (size_t)sizeX * sizeY));
-    CK(cudaMalloc(&d_bits, (size_t)nm * n * n));
-    CK(cudaMalloc(&d_rects, rects.size() * sizeof(RenderRect)));
-    CK(cudaMemcpyAsync(d_bits, bits, (size_t)nm * n * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_rects, rects.data(), rects.size() * sizeof(RenderRect), cudaMemcpyHostToDevice, ctx->stream));
-    k_fill_u8<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_img, (size_t)sizeX * sizeY, 255);
-    k_render_hrm_board<<<dim3((unsigned)((ms * ms + 255) / 256), (unsigned)nm), 256, 0, ctx->stream>>>(d_img, sizeX, sizeY, d_rects, n, d_bits);
+    DevBuf d_img, d_bits, d_rects;
+    CK(d_img.alloc((size_t)sizeX * sizeY));
+    CK(d_bits.alloc((size_t)nm * n * n));
+    CK(d_rects.alloc(rects.size() * sizeof(RenderRect)));
+    CK(cudaMemcpyAsync(d_bits.p, bits, (size_t)nm * n * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_rects.p, rects.data(), rects.size() * sizeof(RenderRect), cudaMemcpyHostToDevice, ctx->stream));
+    k_fill_u8<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_img.as<uint8_t>(), (size_t)sizeX * sizeY, 255);
+    k_render_hrm_board<<<dim3((unsigned)((ms * ms + 255) / 256), (unsigned)nm), 256, 0, ctx->stream>>>(
+        d_img.as<uint8_t>(), sizeX, sizeY, d_rects.as<RenderRect>(), n, d_bits.as<uint8_t>());
     CK(cudaGetLastError());
-    CK(cudaMemcpy2DAsync(out, out_stride, d_img, sizeX, sizeX, sizeY, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpy2DAsync(out, out_stride, d_img.p, sizeX, sizeX, sizeY, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_img);
-    cudaFree(d_bits);
-    cudaFree(d_rects);
     return AB_OK;
 }
 
@@ -1321,14 +1550,13 @@ int ab_calculate_extrinsics(ab_context* ctx, ab_marker* markers, int n, const fl
     if (!ctx || !markers || n < 0 || !K || !(marker_size > 0)) return set_err(ctx, AB_E_INVALID, "calculateExtrinsics: invalid arguments");
     if (n == 0) return AB_OK;
     cudaSetDevice(ctx->device);
-    ab_marker* d = nullptr;
-    CK(cudaMalloc(&d, sizeof(ab_marker) * n));
-    CK(cudaMemcpy(d, markers, sizeof(ab_marker) * n, cudaMemcpyHostToDevice));
-    k_extrinsics<<<(n + 63) / 64, 64, 0, ctx->stream>>>(d, n, make_camera(K, D), marker_size, set_y_perp);
+    DevBuf d;
+    CK(d.alloc(sizeof(ab_marker) * n));
+    CK(cudaMemcpyAsync(d.p, markers, sizeof(ab_marker) * n, cudaMemcpyHostToDevice, ctx->stream));
+    k_extrinsics<<<(n + 63) / 64, 64, 0, ctx->stream>>>(d.as<ab_marker>(), n, make_camera(K, D), marker_size, set_y_perp);
     CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(markers, d.p, sizeof(ab_marker) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy(markers, d, sizeof(ab_marker) * n, cudaMemcpyDeviceToHost));
-    cudaFree(d);
     return AB_OK;
 }
 
@@ -1380,26 +1608,21 @@ int ab_detect_board(ab_context* ctx, const ab_marker* markers, int n, const ab_b
         return AB_OK;
     }
     int N = 4 * nb;
-    float *d_obj = nullptr, *d_img = nullptr, *d_obj2 = nullptr, *d_img2 = nullptr;
-    double* d_out = nullptr;
-    CK(cudaMalloc(&d_obj, sizeof(float) * 3 * N));
-    CK(cudaMalloc(&d_img, sizeof(float) * 2 * N));
-    CK(cudaMalloc(&d_obj2, sizeof(float) * 3 * N));
-    CK(cudaMalloc(&d_img2, sizeof(float) * 2 * N));
-    CK(cudaMalloc(&d_out, sizeof(double) * 8));
-    CK(cudaMemcpy(d_obj, obj.data(), sizeof(float) * 3 * N, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_img, img.data(), sizeof(float) * 2 * N, cudaMemcpyHostToDevice));
+    DevBuf d_obj, d_img, d_obj2, d_img2, d_out;
+    CK(d_obj.alloc(sizeof(float) * 3 * N));
+    CK(d_img.alloc(sizeof(float) * 2 * N));
+    CK(d_obj2.alloc(sizeof(float) * 3 * N));
+    CK(d_img2.alloc(sizeof(float) * 2 * N));
+    CK(d_out.alloc(sizeof(double) * 8));
+    CK(cudaMemcpyAsync(d_obj.p, obj.data(), sizeof(float) * 3 * N, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_img.p, img.data(), sizeof(float) * 2 * N, cudaMemcpyHostToDevice, ctx->stream));
     float zeros[5] = {0, 0, 0, 0, 0};
-    k_board_pose<<<1, 32, 0, ctx->stream>>>(d_obj, d_img, N, make_camera(K, D ? D : zeros), repj_err_thres, set_y_perp, d_obj2, d_img2, d_out);
+    k_board_pose<<<1, 32, 0, ctx->stream>>>(d_obj.as<float>(), d_img.as<float>(), N, make_camera(K, D ? D : zeros), repj_err_thres,
+                                            set_y_perp, d_obj2.as<float>(), d_img2.as<float>(), d_out.as<double>());
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->stream));
     double res[8];
-    CK(cudaMemcpy(res, d_out, sizeof(res), cudaMemcpyDeviceToHost));
-    cudaFree(d_obj);
-    cudaFree(d_img);
-    cudaFree(d_obj2);
-    cudaFree(d_img2);
-    cudaFree(d_out);
+    CK(cudaMemcpyAsync(res, d_out.p, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     out->has_pose = res[6] != 0.;
     for (int i = 0; i < 3; i++) {
         out->rvec[i] = res[i];

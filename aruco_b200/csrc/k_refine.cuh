@@ -72,9 +72,9 @@ __device__ __forceinline__ void refine_lines_cta(const uint32_t* pts, int n, boo
         if (m < 0) m += n;
         const int m2 = (m == 1) ? 2 : m;  // 1-point side: add the next corner (:972-976)
         auto point = [&](int i, float& x, float& y) {
-            int j = start + inc * i;
+            int j = start + inc * i;  // start in [0, n), i < m2 <= n + 1
             if (m == 1 && i == 1) j = end;
-            j %= n;
+            if (j >= n) j -= n;
             if (j < 0) j += n;
             if (cached) {
                 float2 q = s_pts[j];

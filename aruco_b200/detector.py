@@ -150,7 +150,13 @@ class MarkerDetector:
             raise ArucoError(rc, self._lib.ab_last_error(self._h).decode())
 
     def _push(self):
-        self._check(self._lib.ab_set_params(self._h, C.byref(self._p)))
+        """Hands the edited parameter block to the library; a rejected value is rolled back (the local copy is
+        refreshed from the library) so that it cannot poison later setters."""
+        rc = self._lib.ab_set_params(self._h, C.byref(self._p))
+        if rc != 0:
+            msg = self._lib.ab_last_error(self._h).decode()
+            self._lib.ab_get_params(self._h, C.byref(self._p))
+            raise ArucoError(rc, msg)
 
     # ---- setters / getters (markerdetector.h:129-245) --------------------------------------------------
     def setThresholdMethod(self, m):
@@ -411,6 +417,15 @@ class MarkerDetector:
         out = np.empty((size, size), np.uint8)
         self._check(self._lib.ab_warp(self._h, _ptr(image), W, H, W, _ptr(pts), int(size), _ptr(out)))
         return out
+
+    def refineCandidateLines(self, corners, contour, camMatrix=None, distCoeff=None) -> np.ndarray:
+        """MarkerDetector::refineCandidateLines (markerdetector.h:280, cpp:931-997): corners [4,2] (points of the
+        contour), contour [n,2] int in the candidate's order -> refined corners [4,2] f32."""
+        c = np.ascontiguousarray(np.asarray(corners, np.float32).reshape(8)).copy()
+        xy = np.ascontiguousarray(np.asarray(contour, np.int32).reshape(-1, 2))
+        Kf, Df = self._cam(camMatrix, distCoeff)
+        self._check(self._lib.ab_refine_candidate_lines(self._h, _ptr(xy), xy.shape[0], _ptr(c), _ptr(Kf), _ptr(Df)))
+        return c.reshape(4, 2)
 
     def calculateExtrinsics(self, markers: List[Marker], markerSize: float, camMatrix, distCoeff=None,
                             setYPerpendicular: bool = False):

@@ -54,7 +54,10 @@ def render_frame(W: int, H: int, n_markers: int, seed: int, sigma: float = 2.0, 
     rng = np.random.default_rng(seed)
     gx, gy = grid_for(n_markers)
     if marker_px is None:
-        marker_px = 175 if W >= 3000 else (140 if W >= 1900 else int(0.09 * W))
+        # 4K: 7 cells x 27 px = 189 px sides, so that after the canvas homography (4 % inset, +-3 % jitter: the contour
+        # shrinks to as little as 0.85x) every contour stays above the detector's minimum length 0.04*3840*4 = 614 px;
+        # with the 175 px of round 1 about 5 % of the markers fell below it and were (correctly) rejected
+        marker_px = 189 if W >= 3000 else (140 if W >= 1900 else int(0.09 * W))
     canvas = np.full((H, W), 255.0, np.float32)
     ins = 0.04
     x0, y0 = ins * W, ins * H
@@ -118,14 +121,14 @@ def render_frame(W: int, H: int, n_markers: int, seed: int, sigma: float = 2.0, 
     if as_float:  # noise-free f32 image: the caller adds its own noise (bench: on the GPU, per frame)
         tc = np.array(truth_c, np.float64)
         ph = np.concatenate([tc, np.ones(tc.shape[:2] + (1,))], axis=2) @ Hm.T
-        return out, {"ids": truth_ids, "corners": ph[..., :2] / ph[..., 2:3]}
+        return out, {"ids": truth_ids, "corners": ph[..., :2] / ph[..., 2:3], "canvas_corners": tc}
     if not clean and sigma > 0:
         out = out + rng.normal(0.0, sigma, size=out.shape).astype(np.float32)
     grey = np.clip(np.rint(out), 0, 255).astype(np.uint8)
     tc = np.array(truth_c, np.float64)
     ph = np.concatenate([tc, np.ones(tc.shape[:2] + (1,))], axis=2) @ Hm.T
     tc_img = ph[..., :2] / ph[..., 2:3]
-    return grey, {"ids": truth_ids, "corners": tc_img}
+    return grey, {"ids": truth_ids, "corners": tc_img, "canvas_corners": tc}
 
 
 def camera_for(W: int, H: int):

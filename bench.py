@@ -1,23 +1,29 @@
 #!/usr/bin/env python
 """Benchmark of the hot path MarkerDetector::detect on B200 (contract: see README / DESIGN.md section 6).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C1|C2|C3|C4|C5|C4s4]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[3], "C4"): synthetic 3840x2160 grey frames, 100 Fiducidal markers each, batch
-of 256 frames per GPU, defaults of the reference (ADPT_THRES 7/7, LINES refinement, per-marker PnP).  One
-"step" = one pass of the whole hot path over one batch.  Frames are independent, so N GPUs = N shards, no
-collective on the data path (weak scaling: 256 frames per GPU).
+Default workload = BASELINE.json configs[3] ("C4"): synthetic 3840x2160 grey frames, 100 Fiducidal markers each,
+batch of 256 frames per GPU, the reference's defaults (ADPT_THRES 7/7, LINES refinement, per-marker PnP).  One
+"step" = one pass of the whole hot path over one batch.  Frames are independent, so N GPUs = N shards, no collective
+on the data path (weak scaling: the same batch size per GPU).  The other BASELINE configs (C1 single reference frame,
+C2 1280x720 board with erosion + BoardDetector pose, C3 1080p x 64 SUBPIX, C5 HRM 4K, plus the sigma-4 contour storm
+"C4s4") are timed the same way with --config, and briefly inside the default run (key `other_configs`, 1 GPU only).
 
-  value   whole-job frames/s with the batch already resident in HBM (device-timed, max over ranks)
+  value   whole-job frames/s with the batch already resident in HBM (device-timed, max over ranks); ONE context, two
+          batches in flight inside the library (ab_enqueue_batch_device twice before ab_fetch_results)
   e2e     the same through the C ABI call ab_detect_batch with HOST (pinned) frames: H2D + kernels + D2H
   roofline  the dominant kernel's algorithmic bytes / its CUDA-event duration vs the measured HBM peak
-  cpu_baseline  the CPU oracle port (oracle/aruco_oracle.cpp, OpenMP frame-parallel) on a bounded sample
+  cpu_baseline  the CPU oracle port (oracle/aruco_oracle.cpp) on a bounded sample: frame-parallel on all host threads
+          (value), in the reference's own threading model (ar_omp.h: one frame at a time, OpenMP only at
+          markerdetector.cpp:456/587) and the cv2-backed oracle
 
---impl reference times that CPU oracle port with all host threads on the same workload (the reference's own
-C++ cannot be built here: no OpenCV C++ -- DESIGN.md section 3).
+--impl reference times that CPU oracle port with all host threads on the FIRST frames of the same batch (the
+reference's own C++ cannot be built here: no OpenCV C++ -- DESIGN.md section 3).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -30,10 +36,28 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, N_MARKERS, BATCH, SIGMA = 3840, 2160, 100, 256, 2.0
-N_BASE = 8          # distinct rendered scenes; every frame of a batch gets its own noise realisation
 MARKER_SIZE = 0.05
-KERNELS_PER_BATCH = 14  # threshold, scan_starts, trace, trace_long, emit_long, emit, polygon, frame_filter, homography, sample, otsu, identify, refine_lines, finalize
+N_BASE = 8  # distinct rendered scenes; every frame of a batch gets its own noise realisation
+# kernels launched per batch: threshold, scan_starts, trace, trace_long, emit_long, emit, polygon, frame_filter,
+# homography, sample, otsu, identify, refine, finalize (+ erode when erosion is on)
+KERNELS_PER_BATCH = 14
+
+CONFIGS = {
+    "C1": dict(workload="C1: reference frame testdata/single 640x480 (tests/golden), Fiducidal, ADPT_THRES 7/7 + LINES + PnP, one frame per call",
+               W=640, H=480, batch=1, golden="single", size=1.0, params={}),
+    "C2": dict(workload="C2: synthetic 1280x720 board frame, 24 Fiducidal markers, erosion on, LINES + BoardDetector pose, one frame per call",
+               W=1280, H=720, batch=1, n=24, marker_px=100, sigma=1.5, board=True, params=dict(erosion=True)),
+    "C3": dict(workload="C3: synthetic 1920x1080 grey, 50 Fiducidal markers/frame, ADPT_THRES 7/7 + SUBPIX + PnP",
+               W=1920, H=1080, batch=64, n=50, sigma=2.0, params=dict(corner_method=2)),
+    "C4": dict(workload="C4: synthetic 3840x2160 grey, 100 Fiducidal markers/frame, ADPT_THRES 7/7 + LINES + PnP",
+               W=3840, H=2160, batch=256, n=100, sigma=2.0, params={}),
+    "C5": dict(workload="C5: synthetic 3840x2160 grey, 100 HRM d6x6 markers/frame, ADPT_THRES 21/7, erosion on, LINES + PnP, warp 64, minSize 0.005",
+               W=3840, H=2160, batch=64, n=100, sigma=2.0, hrm="d6x6_100", max_cands=1024,
+               params=dict(p1=21, p2=7, warp_size=64, min_size=0.005, decoder=1, erosion=True)),
+    "C4s4": dict(workload="C4s4: C4 at noise sigma 4 (contour storm: ~10x the border pixels of sigma 2)",
+                 W=3840, H=2160, batch=64, n=100, sigma=4.0, params={}),
+}
+METRIC = {"C4": "frames_per_s_4k_100markers"}
 
 
 def log(*a):
@@ -58,6 +82,19 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(cfg_name, kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this build
+    (profiles/ncu_traffic.json, written from the capture by tools/ncu_traffic.py); None when there is none."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        e = d.get(cfg_name, {}).get(kernel)
+        return (float(e["dram_bytes_per_launch"]), e.get("source")) if e else (None, None)
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -69,9 +106,10 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            time.sleep(0.3)  # let the first samples arrive before the timed region starts
         except Exception:
             self.proc = None
 
@@ -82,7 +120,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -104,50 +142,171 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def oracle_params():
+def bind_to_gpu_numa(local):
+    """Pins this rank's threads to the CPUs next to its GPU (NVML's ideal CPU set = the GPU's NUMA node / PCIe root) BEFORE
+    any pinned host memory is allocated, so the staging pages are first-touched on that node."""
+    info = {"cpus_before": host_threads()}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        try:
+            info["numa_node"] = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:
+            info["numa_node"] = None
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+        info["cpus_bound"] = len(os.sched_getaffinity(0))
+        try:
+            pci = pynvml.nvmlDeviceGetPciInfo(h)
+            info["pci_bus_id"] = pci.busId if isinstance(pci.busId, str) else pci.busId.decode()
+        except Exception:
+            pass
+    except Exception as e:  # NVML missing: leave the affinity alone
+        info["note"] = "not bound: %s" % type(e).__name__
+    return info
+
+
+def oracle_params(cfg):
     from oracle.cv2_oracle import Params
-    return Params()
+    return Params(**cfg["params"])
 
 
-def base_scenes(n_base, rank):
+def golden(name):
+    fr = np.load(os.path.join(ROOT, "tests", "golden", "frames.npz"))
+    exp = json.load(open(os.path.join(ROOT, "tests", "golden", "expected.json")))
+    return fr, exp
+
+
+def hrm_codes(cfg):
+    _, exp = golden(None)
+    text = exp["dictionaries"][cfg["hrm"]]
+    n = int(cfg["hrm"][1])
+    return text, [l.split('"')[1] for l in text.splitlines() if l.startswith("marker_")], n
+
+
+def camera(cfg):
+    from aruco_b200 import synth
+    if cfg.get("golden"):
+        _, exp = golden(None)
+        intr = exp["intrinsics"][cfg["golden"]]
+        return np.array(intr["K"], np.float32).reshape(3, 3), np.array(intr["D"], np.float32).reshape(-1)[:5]
+    return synth.camera_for(cfg["W"], cfg["H"])
+
+
+def base_scenes(cfg, n_base, rank):
+    """Noise-free f32 renderings (CPU, numpy, seeded): scene i of rank r has seed 1000 r + i."""
     from aruco_b200 import synth
     t = time.time()
-    scenes = [synth.render_frame(W, H, N_MARKERS, seed=1000 * rank + i, as_float=True)[0] for i in range(n_base)]
-    log("[bench] rendered %d base scenes in %.1fs" % (n_base, time.time() - t))
-    return scenes
+    kw = {}
+    if cfg.get("hrm"):
+        _, codes, n = hrm_codes(cfg)
+        kw = dict(hrm_codes=codes, hrm_n=n)
+    scenes, truths = [], []
+    for i in range(n_base):
+        img, tr = synth.render_frame(cfg["W"], cfg["H"], cfg["n"], seed=1000 * rank + i, as_float=True, marker_px=cfg.get("marker_px"), **kw)
+        scenes.append(img)
+        truths.append(tr)
+    log("[bench] rendered %d base scenes %dx%d in %.1fs" % (n_base, cfg["W"], cfg["H"], time.time() - t))
+    return scenes, truths
+
+
+def make_frames(cfg, n_frames, rank, dev):
+    """[n_frames, H, W] u8 on `dev` (a torch device): scene (i mod n_base) + per-frame Gaussian noise from a torch generator
+    seeded 1234 + rank ON THAT DEVICE -- both arms of the benchmark call this, so on the same box they see the same frames."""
+    import torch
+    W, H = cfg["W"], cfg["H"]
+    if cfg.get("golden"):
+        fr, _ = golden(None)
+        g = torch.from_numpy(np.ascontiguousarray(fr[cfg["golden"]])).to(dev)
+        return g[None].repeat(n_frames, 1, 1).contiguous(), None
+    n_base = min(N_BASE, max(1, n_frames))
+    scenes, truths = base_scenes(cfg, n_base, rank)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    frames = torch.empty((n_frames, H, W), dtype=torch.uint8, device=dev)
+    clean = [torch.from_numpy(s).to(dev) for s in scenes]
+    for i in range(n_frames):
+        noise = torch.randn((H, W), generator=gen, device=dev, dtype=torch.float32) * cfg["sigma"]
+        frames[i] = torch.clamp(torch.round(clean[i % n_base] + noise), 0, 255).to(torch.uint8)
+    return frames, truths
+
+
+def board_config(cfg, truth):
+    """BoardConfiguration in pixels (board.h:56-97) of a synthetic scene: marker corners on the canvas, centred, y up."""
+    cc = np.asarray(truth["canvas_corners"], np.float64)
+    cx, cy = cfg["W"] / 2.0, cfg["H"] / 2.0
+    markers = []
+    for mid, c in zip(truth["ids"], cc):
+        markers.append({"id": int(mid), "corners": [[float(x - cx), float(-(y - cy)), 0.0] for x, y in c]})
+    return {"mInfoType": 0, "markers": markers}
+
+
+def config_dict(cfg, B, extra=None):
+    d = {"workload": cfg["workload"], "frames_per_gpu_per_step": B, "noise_sigma": cfg.get("sigma"),
+         "distinct_scenes": 1 if cfg.get("golden") else min(N_BASE, B), "frame_seed": "torch.Generator(1234 + rank) on the GPU, scenes numpy seed 1000 rank + i",
+         "l2": "inputs larger than L2 (batch = %.2f GB per GPU vs 126 MB L2)" % (B * cfg["W"] * cfg["H"] / 1e9) if B * cfg["W"] * cfg["H"] > 126e6
+         else "L2 flushed between timed steps (256 MB scratch write)",
+         "parallelism": "frame shards, one per GPU, no collective"}
+    if extra:
+        d.update(extra)
+    return d
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_detect_batch(cfg, frames_np, K, D, threads, hrm=None, board=None):
+    from oracle import native
+    P = oracle_params(cfg)
+    res = native.detect_batch(frames_np, P, K, D, cfg.get("size", MARKER_SIZE), hrm=hrm, cap=512 if cfg.get("hrm") else 256, threads=threads)
+    if board is not None:  # BoardDetector::detect on the host with real OpenCV (the port has no board stage)
+        from oracle import cv2_oracle as o
+        for ms in res:
+            o.board_detect(ms, board, K, D, cfg.get("size", MARKER_SIZE))
+    return res
 
 
 def run_reference(args):
-    """CPU arm: the oracle port, OpenMP frame-parallel over all host threads, bounded sample per step."""
+    """CPU arm: the oracle port, OpenMP frame-parallel over all host threads, on the first frames of the SAME batch the
+    GPU arm builds (same scenes, same torch generator; generated on the GPU when there is one)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from aruco_b200 import synth
+    import torch
     from oracle import native
     native.load()
+    cfg = CONFIGS[args.config]
+    B = args.batch or cfg["batch"]
     threads = host_threads()
-    sample = max(2 * threads, 32)  # frames per step: ~2-3 CPU-seconds per step on every thread
-    rng = np.random.default_rng(7)
-    scenes = base_scenes(min(N_BASE, 4), 0)
-    frames = np.stack([np.clip(np.rint(scenes[i % len(scenes)] + rng.normal(0, SIGMA, (H, W)).astype(np.float32)), 0, 255).astype(np.uint8)
-                       for i in range(sample)])
-    K, D = synth.camera_for(W, H)
-    P = oracle_params()
+    px = cfg["W"] * cfg["H"]
+    sample = int(min(B, max(1, min(max(2 * threads, 32), 2.7e8 // px))))  # frames per step: a few CPU-seconds on every thread
+    on_gpu = torch.cuda.is_available()
+    frames_t, truths = make_frames(cfg, sample, 0, torch.device("cuda", 0) if on_gpu else torch.device("cpu"))
+    frames = frames_t.cpu().numpy()
+    del frames_t
+    K, D = camera(cfg)
+    hrm = native.dict_from_yaml_text(hrm_codes(cfg)[0]) if cfg.get("hrm") else None
+    board = board_config(cfg, truths[0]) if cfg.get("board") else None
     for _ in range(args.warmup):
-        native.detect_batch(frames[:threads], P, K, D, MARKER_SIZE, threads=threads)
+        cpu_detect_batch(cfg, frames[:threads], K, D, threads, hrm, board)
     t0 = time.perf_counter()
     nm = 0
     for _ in range(args.steps):
-        res = native.detect_batch(frames, P, K, D, MARKER_SIZE, threads=threads)
+        res = cpu_detect_batch(cfg, frames, K, D, threads, hrm, board)
         nm += sum(len(r) for r in res)
     dt = time.perf_counter() - t0
     fps = args.steps * sample / dt
-    line = {"impl": "reference", "metric": "frames_per_s_4k_100markers", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "mpix_per_s": fps * W * H / 1e6,
-            "config": {"workload": "C4: synthetic 3840x2160 grey, 100 Fiducidal markers/frame, ADPT_THRES 7/7 + LINES + PnP",
-                       "frames_per_step": sample, "noise_sigma": SIGMA},
+    line = {"impl": "reference", "metric": METRIC.get(args.config, "frames_per_s_" + args.config), "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "mpix_per_s": fps * px / 1e6,
+            "config": config_dict(cfg, B, {"reference_sample": "first %d frames of the batch per step (%s)" % (sample, "generated on the GPU: identical to the GPU arm's" if on_gpu else "no GPU: CPU generator, other noise realisations")}),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": "%d frames/step x %d steps, oracle/aruco_oracle.cpp OpenMP frame-parallel (reference C++ "
                                        "unbuildable: no OpenCV C++)" % (sample, args.steps)},
@@ -157,233 +316,403 @@ def run_reference(args):
     return 0
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--skip-e2e", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
-        return run_reference(args)
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+class Workload:
+    """One config on one GPU: frames resident in HBM, a configured detector (ONE context), the timed loops."""
 
-    import torch
-    import torch.distributed as dist
-    from aruco_b200 import MarkerDetector, synth
+    def __init__(self, name, B, rank, local, torch):
+        from aruco_b200 import FiducidalMarkers, HighlyReliableMarkers, MarkerDetector
+        self.torch, self.name, self.cfg, self.B, self.local = torch, name, CONFIGS[name], B, local
+        cfg = self.cfg
+        self.W, self.H = cfg["W"], cfg["H"]
+        self.dev = torch.device("cuda", local)
+        self.frames, self.truths = make_frames(cfg, B, rank, self.dev)
+        self.K, self.D = camera(cfg)
+        self.size = cfg.get("size", MARKER_SIZE)
+        self.cap = 512 if cfg.get("hrm") else 128
+        self.stream = torch.cuda.Stream(device=self.dev)  # the library runs on an explicit stream of the caller
+        det = MarkerDetector(local)
+        det.set_stream(self.stream.cuda_stream)
+        P = oracle_params(cfg)
+        det.setThresholdMethod(P.thres_method)
+        det.setThresholdParams(P.p1, P.p2)
+        det.setCornerRefinementMethod(P.corner_method)
+        det.setMinMaxSize(P.min_size, P.max_size)
+        det.setWarpSize(P.warp_size)
+        det.enableErosion(P.erosion)
+        self.hrm_text = None
+        if cfg.get("hrm"):
+            self.hrm_text = hrm_codes(cfg)[0]
+            HighlyReliableMarkers.loadDictionary(self.hrm_text)
+            det.setMakerDetectorFunction(HighlyReliableMarkers.detect)
+        else:
+            det.setMakerDetectorFunction(FiducidalMarkers.detect)
+        det.reserve(self.W, self.H, B, max_candidates=cfg.get("max_cands", 0))
+        self.det = det
+        self.board = None
+        if cfg.get("board"):
+            from aruco_b200.board import BoardConfiguration
+            self.board_dict = board_config(cfg, self.truths[0])
+            self.board = BoardConfiguration.from_dict(self.board_dict)
+        self.flush = None
+        if B * self.W * self.H <= 126e6:  # inputs fit L2: flush it between timed steps
+            self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        self.stream.synchronize()
+        torch.cuda.synchronize()
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
+    # one step, one batch at a time
+    def step(self):
+        self.det.enqueue_device(self.frames.data_ptr(), self.W, self.H, self.B, self.K, self.D, self.size)
+        return self.det.fetch(self.B, self.cap, raw=True)
 
-    # ---- synthetic batch, resident in HBM: N_BASE rendered scenes + per-frame Gaussian noise (sigma 2) --------
-    scenes = base_scenes(N_BASE, rank)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    frames = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
-    for i in range(B):
-        clean = torch.from_numpy(scenes[i % N_BASE]).to(dev)
-        noise = torch.randn((H, W), generator=gen, device=dev, dtype=torch.float32) * SIGMA
-        frames[i] = torch.clamp(torch.round(clean + noise), 0, 255).to(torch.uint8)
-    del clean, noise
-    K, D = synth.camera_for(W, H)
-    stream = torch.cuda.current_stream()
-
-    det = MarkerDetector(local)
-    det.set_stream(stream.cuda_stream)
-    det.reserve(W, H, B)
-    cap = 128
-
-    def step():
-        det.enqueue_device(frames.data_ptr(), W, H, B, K, D, MARKER_SIZE)
-        return det.fetch(B, cap, raw=True)
-
-    # ---- parity gate before timing: two frames against the CPU oracle -------------------------------------
-    buf, counts = step()
-    parity = {"checked_frames": 0, "ids_exact": None}
-    if rank == 0:
+    def parity(self, n_check):
+        """ids exact + corners < 0.01 px + pose < 1e-4 of `n_check` frames spread over the batch against the CPU oracle port."""
         from oracle import native
-        P = oracle_params()
-        ok = True
-        for f in (0, B - 1):
-            host = frames[f].cpu().numpy()
-            ref = native.detect(host, P, K, D, MARKER_SIZE, debug=False)["markers"]
-            got = [buf[f * cap + i].id for i in range(counts[f])]
-            ok &= got == [m["id"] for m in ref]
-            for i, m in enumerate(ref):
-                if not ok:
-                    break
-                ok &= float(np.abs(np.array(buf[f * cap + i].corners).reshape(4, 2) - m["corners"]).max()) < 0.01
-        parity = {"checked_frames": 2, "ids_exact": bool(ok)}
-        log("[bench] parity vs oracle on 2 frames: %s; markers/frame=%.1f counters=%s" % (ok, float(np.mean(counts)), det.counters()))
-        if not ok:
-            raise SystemExit("parity check against the oracle failed -- refusing to report a number")
+        buf, counts = self.step()
+        P = oracle_params(self.cfg)
+        hrm = native.dict_from_yaml_text(self.hrm_text) if self.hrm_text else None
+        idx = sorted(set(int(round(i)) for i in np.linspace(0, self.B - 1, min(n_check, self.B))))
+        host = self.frames[idx].cpu().numpy()
+        refs = native.detect_batch(host, P, self.K, self.D, self.size, hrm=hrm, cap=self.cap, threads=host_threads())
+        ok, poses, pose_ok = True, 0, 0
+        for f, ref in zip(idx, refs):
+            got = [buf[f * self.cap + i] for i in range(counts[f])]
+            ok &= [m.id for m in got] == [m["id"] for m in ref]
+            if not ok:
+                break
+            for g, m in zip(got, ref):
+                ok &= float(np.abs(np.array(g.corners).reshape(4, 2) - m["corners"]).max()) < 0.01
+                if "rvec" in m:
+                    poses += 1
+                    er = np.abs(np.array(g.rvec) - m["rvec"]).max() / np.abs(m["rvec"]).max()
+                    et = np.abs(np.array(g.tvec) - m["tvec"]).max() / np.abs(m["tvec"]).max()
+                    pose_ok += bool(er < 1e-4 and et < 1e-4)
+        ok &= poses == 0 or pose_ok >= 0.99 * poses
+        return {"checked_frames": len(idx), "ids_exact": bool(ok), "corners_within_px": 0.01, "poses_within_1e-4": "%d/%d" % (pose_ok, poses)}, counts
+
+    def run_steps(self, n, flush=False):
+        """n steps with two batches in flight inside the ONE context: batch i+1 is enqueued before batch i is fetched."""
+        det, total, pending = self.det, 0, 0
+        for _ in range(n):
+            if pending == 2:
+                total += sum(det.fetch(self.B, self.cap, raw=True)[1])
+                pending -= 1
+            if flush and self.flush is not None:
+                with self.torch.cuda.stream(self.stream):
+                    self.flush.fill_(1)
+            det.enqueue_device(self.frames.data_ptr(), self.W, self.H, self.B, self.K, self.D, self.size)
+            pending += 1
+        while pending:
+            total += sum(det.fetch(self.B, self.cap, raw=True)[1])
+            pending -= 1
+        return total
+
+    def time_resident(self, steps, warmup, barrier, sampler=None):
+        torch = self.torch
+        self.run_steps(max(warmup, 3))
+        barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        t0 = time.perf_counter()
+        n_markers = self.run_steps(steps, flush=True)
+        # Device clock: e0 is processed before the first kernel (the library's second slot waits for an event recorded on
+        # this stream after e0), e1 is recorded after the last fetch returned, i.e. after every kernel and copy of both
+        # in-flight slots has completed.  The host clock over the same region is kept as a cross-check (wall_ms).
+        e1.record(self.stream)
+        self.stream.synchronize()
+        self.wall_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = e0.elapsed_time(e1)
+        if self.flush is not None:  # take the flush writes out again: time them alone
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(self.stream):
+                f0.record(self.stream)
+                for _ in range(steps):
+                    self.flush.fill_(1)
+                f1.record(self.stream)
+            self.stream.synchronize()
+            ms = max(ms - f0.elapsed_time(f1), 1e-3)
+        return ms, n_markers, clocks
+
+    def kernel_ms(self, reps=3):
+        det = self.det
+        det.enable_timing(True)
+        self.step()
+        acc = {k: 0.0 for k in det.KERNELS}
+        for _ in range(reps):
+            self.step()
+            for k, v in det.kernel_ms().items():
+                acc[k] += v / reps
+        det.enable_timing(False)
+        return acc
+
+    def time_e2e(self, steps, barrier, chunk=32):
+        """Through the plugin call with HOST frames: ab_detect_batch (+ ab_detect_board per frame for the board config)."""
+        torch = self.torch
+        from aruco_b200 import MarkerDetector
+        from aruco_b200._lib import ab_marker
+        B, W, H, cap = self.B, self.W, self.H, self.cap
+        host = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
+        host.copy_(self.frames)
+        det = self.det
+        det.reserve(W, H, min(chunk, B), max_candidates=self.cfg.get("max_cands", 0))  # chunked: H2D of chunk c+1 under the kernels of chunk c
+        out = (ab_marker * (B * cap))()
+        cnts = (C.c_int32 * B)()
+        Kf, Df = np.ascontiguousarray(self.K.reshape(9)), np.ascontiguousarray(self.D)
+        bd = None
+        if self.board is not None:
+            from aruco_b200.board import BoardDetector
+            bd = BoardDetector(detector=det)
+
+        def one():
+            rc = det._lib.ab_detect_batch(det._h, C.c_void_p(host.data_ptr()), W, H, W, W * H, B, Kf.ctypes.data_as(C.c_void_p),
+                                          Df.ctypes.data_as(C.c_void_p), self.size, out, cap, cnts)
+            det._check(rc)
+            if bd is not None:  # BoardDetector::detect per frame on the markers just found (boarddetector.cpp:90-204)
+                for ms in det._markers(out, list(cnts), cap):
+                    prob, board = bd.detect(ms, self.board, self.K, self.D, self.size)
+                    assert board.Rvec is not None and prob > 0.5
+
+        for _ in range(2):
+            one()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        self.stream.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3  # every call returns after its D2H copy: the host clock is the device clock
+        barrier()
+        # the host-side ceiling: the same pinned buffer, the same chunking, copies only
+        dst = torch.empty((min(chunk, B), H, W), dtype=torch.uint8, device=self.dev)
+        cs = torch.cuda.Stream(device=self.dev)
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(cs):
+            for rep in range(3):
+                if rep == 1:
+                    h0.record(cs)
+                for c0 in range(0, B, chunk):
+                    n = min(chunk, B - c0)
+                    dst[:n].copy_(host[c0:c0 + n], non_blocking=True)
+            h1.record(cs)
+        cs.synchronize()
+        h2d_gbs = 2 * B * W * H / (h0.elapsed_time(h1) / 1e3) / 1e9
+        det.reserve(W, H, B, max_candidates=self.cfg.get("max_cands", 0))
+        same = None
+        return ms, {"h2d_bytes_per_step": B * W * H, "d2h_bytes_per_step": B * cap * C.sizeof(ab_marker) + 4 * B,
+                    "chunk_frames": min(chunk, B), "h2d_only_gbs": h2d_gbs, "counts": list(cnts)}
+
+    def cpu_baselines(self, budget_px=2.2e9):
+        """The oracle port on a bounded sample of this batch: (i) frame-parallel on all host threads, (ii) the reference's own
+        threading model (ar_omp.h: one frame at a time, OpenMP inside a frame only at cpp:456/587), (iii) the cv2-backed oracle."""
+        from oracle import native
+        cfg, threads = self.cfg, host_threads()
+        px = self.W * self.H
+        sample = int(max(1, min(self.B, budget_px // px)))
+        hostf = self.frames[:sample].cpu().numpy()
+        hrm = native.dict_from_yaml_text(self.hrm_text) if self.hrm_text else None
+        board = self.board_dict if self.board is not None else None
+        cpu_detect_batch(cfg, hostf[:min(sample, threads)], self.K, self.D, threads, hrm, board)
+        t0 = time.perf_counter()
+        cpu_detect_batch(cfg, hostf, self.K, self.D, threads, hrm, board)
+        dt = time.perf_counter() - t0
+        out = {"value": sample / dt, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": "%d frames of the same batch, oracle/aruco_oracle.cpp, OpenMP frame-parallel on %d threads" % (sample, threads)}
+        # (ii) ar_omp model: frames one after the other; orc_detect parallelises only the reference's two omp loops
+        n2 = max(1, min(sample, int(4e8 // px)))
+        P = oracle_params(cfg)
+        t0 = time.perf_counter()
+        for f in range(n2):
+            native.detect(hostf[f], P, self.K, self.D, self.size, hrm, cap=2048, debug=False)
+        out["ar_omp_model"] = {"value": n2 / (time.perf_counter() - t0), "unit": "frames/s", "cores": threads,
+                               "sample": "%d frames one at a time; OpenMP only where the reference has it (markerdetector.cpp:456,587)" % n2}
+        try:  # (iii) real OpenCV primitives + Python glue, single process (BASELINE.md section 4)
+            from oracle import cv2_oracle as o
+            hc = o.HrmDictionary.from_yaml_text(self.hrm_text) if self.hrm_text else None
+            n3 = max(1, min(sample, int(1e8 // px)))
+            t0 = time.perf_counter()
+            for f in range(n3):
+                o.detect(hostf[f], P, self.K, self.D, self.size, hc)
+            out["cv2_oracle"] = {"value": n3 / (time.perf_counter() - t0), "unit": "frames/s", "cores": 1,
+                                 "sample": "%d frames, oracle/cv2_oracle.py (OpenCV %s primitives, Python glue)" % (n3, o.cv2.__version__)}
+        except Exception as e:
+            out["cv2_oracle"] = {"unavailable": type(e).__name__}
+        return out
+
+
+def algorithmic_bytes(kernel, W, H, B, k_thr):
+    """Algorithmic bytes per launch: threshold reads the grey frame and writes the
+    u8 binarised frame (the 1/8 B/px packed copy is not counted); the scan and the walkers read the packed image; the other
+    kernels work per candidate (< 1 % of a frame) and are given the whole-path figure 3 W H."""
+    packed = W * H / 8.0 * B
+    return {"threshold": 2.0 * W * H * B, "scan_starts": packed, "trace": packed, "trace_long": packed, "emit": packed}.get(kernel, 3.0 * W * H * B)
+
+
+def measure_config(name, args, rank, local, world, torch, dist, full):
+    """Times one config on this rank.  full: the whole protocol (parity gate on >= 16 frames, clocks, e2e, CPU baselines);
+    otherwise the short form used for `other_configs`."""
+    cfg = CONFIGS[name]
+    B = args.batch if (args.batch and full) else cfg["batch"]
+    wl = Workload(name, B, rank, local, torch)
+    W, H = wl.W, wl.H
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing --------------------------------------------------------------------------
-    # Two batches are kept in flight (two contexts on two streams, results of batch n fetched while batch n+1 runs): the
-    # latency-bound kernels at the end of a batch (k_finalize keeps 7 % of the warps busy) overlap the bandwidth-bound
-    # start of the next one.  tools/pipeline_study.py: 46.8 k -> 51.0 k frames/s.  Every step still enqueues one batch
-    # of B frames and fetches its markers.
-    stream_b = torch.cuda.Stream(device=dev)
-    det_b = MarkerDetector(local)
-    det_b.set_stream(stream_b.cuda_stream)
-    det_b.reserve(W, H, B)
-    dets = [det, det_b]
-
-    def run_steps(n):
-        pending, total = [], 0
-        for it in range(n):
-            d = dets[it % 2]
-            if len(pending) == 2:
-                total += sum(pending.pop(0).fetch(B, cap, raw=True)[1])
-            d.enqueue_device(frames.data_ptr(), W, H, B, K, D, MARKER_SIZE)
-            pending.append(d)
-        for d in pending:
-            total += sum(d.fetch(B, cap, raw=True)[1])
-        return total
-
-    run_steps(max(args.warmup, 4))
-    kernel_ms = {k: 0.0 for k in det.KERNELS}
-    sampler = ClockSampler(local)
-    barrier()
+    parity, counts = ({"checked_frames": 0, "ids_exact": None}, None)
     if rank == 0:
-        sampler.start()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1a, e1b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    stream_b.wait_event(e0)  # nothing of the timed region starts before e0 on either stream
-    n_markers = run_steps(args.steps)
-    e1a.record(stream)
-    e1b.record(stream_b)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = max(e0.elapsed_time(e1a), e0.elapsed_time(e1b))
-    del det_b, dets
-    # per-kernel durations (for the roofline): a separate, untimed pass -- the library pipelines sub-batches over
-    # several streams in the timed loop, per-kernel CUDA events need everything on one stream
-    det.enable_timing(True)
-    step()
-    for _ in range(3):
-        step()
-        for k, v in det.kernel_ms().items():
-            kernel_ms[k] += v / 3
-    det.enable_timing(False)
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        parity, counts = wl.parity(16 if full else 4)
+        log("[bench] %s parity vs oracle: %s; markers/frame=%.1f counters=%s" % (name, parity, float(np.mean(counts)), wl.det.counters()))
+        if not parity["ids_exact"]:
+            raise SystemExit("parity check against the oracle failed (%s) -- refusing to report a number" % name)
+    steps = args.steps if full else max(5, min(args.steps, 20))
+    if B == 1:
+        steps = max(steps, 200)  # single-frame configs: enough calls for a stable latency
+    sampler = ClockSampler(local) if (rank == 0 and full) else None
+    ms, n_markers, clocks = wl.time_resident(steps, args.warmup, barrier, sampler)
+    kms = wl.kernel_ms()
+    t = torch.tensor([ms], device=wl.dev, dtype=torch.float64)
+    per_rank = [ms]
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    fps = world * B * args.steps / (ms_total / 1e3)
-
-    # ---- end to end through the C ABI with host frames (pinned): H2D + kernels + D2H every step ---------------
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        per_rank = [float(x.item()) for x in g]
+    ms_total = max(per_rank)
+    fps = world * B * steps / (ms_total / 1e3)
+    res = {"name": name, "B": B, "steps": steps, "fps": fps, "ms_total": ms_total, "per_rank_ms": per_rank, "kernel_ms": kms,
+           "markers_per_frame": n_markers / (steps * B), "parity": parity, "clocks": clocks, "counters": wl.det.counters(), "wl": wl}
+    res["wall_ms"] = wl.wall_ms
     e2e = None
     if not args.skip_e2e:
-        host = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
-        host.copy_(frames)
-        det2 = MarkerDetector(local)
-        det2.set_stream(stream.cuda_stream)
-        det2.reserve(W, H, 32)  # 32-frame chunks: H2D of chunk c+1 overlaps the kernels of chunk c
-        from aruco_b200._lib import ab_marker
-        import ctypes as C
-        out = (ab_marker * (B * cap))()
-        cnts = (C.c_int32 * B)()
-        Kf = np.ascontiguousarray(K.reshape(9))
-        Df = np.ascontiguousarray(D)
-
-        def step_e2e():
-            rc = det2._lib.ab_detect_batch(det2._h, C.c_void_p(host.data_ptr()), W, H, W, W * H, B, Kf.ctypes.data_as(C.c_void_p),
-                                           Df.ctypes.data_as(C.c_void_p), MARKER_SIZE, out, cap, cnts)
-            det2._check(rc)
-
-        for _ in range(2):
-            step_e2e()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
-        e1.record(stream)
-        barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        ms2 = max(e0.elapsed_time(e1), wall_ms)  # copies run on the library's copy stream: take the host clock too
-        t = torch.tensor([ms2], device=dev, dtype=torch.float64)
+        n_e = steps if (full or B == 1) else max(3, steps // 4)
+        ms2, info = wl.time_e2e(n_e, barrier)
+        t = torch.tensor([ms2], device=wl.dev, dtype=torch.float64)
+        per_rank2, h2d = [ms2], [info["h2d_only_gbs"]]
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_fps = world * B * args.steps / (float(t.item()) / 1e3)
-        same = list(cnts) == list(counts)
-        e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
-               "d2h_bytes_per_step": B * cap * C.sizeof(ab_marker) + 4 * B, "chunk_frames": 32,
-               "same_counts_as_device_path": bool(same)}
-        del det2, host
+            g = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(g, t)
+            per_rank2 = [float(x.item()) for x in g]
+            t = torch.tensor([info["h2d_only_gbs"]], device=wl.dev, dtype=torch.float64)
+            dist.all_gather(g, t)
+            h2d = [float(x.item()) for x in g]
+        e2e_fps = world * B * n_e / (max(per_rank2) / 1e3)
+        same = counts is None or info["counts"] == list(counts)
+        e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": info["h2d_bytes_per_step"],
+               "d2h_bytes_per_step": info["d2h_bytes_per_step"], "chunk_frames": info["chunk_frames"],
+               "same_counts_as_device_path": bool(same), "per_rank_ms": per_rank2,
+               # pinned H2D copies alone (same buffer, same chunking, no kernels), per rank, measured one rank after the
+               # other's e2e leg but concurrently across ranks: the host-side ceiling of e2e
+               "h2d_only_gbs": h2d, "h2d_gbs_in_e2e": e2e_fps * W * H / 1e9,
+               "frac_of_h2d_ceiling": (e2e_fps * W * H / 1e9) / max(sum(h2d), 1e-9)}
+    res["e2e"] = e2e
+    return res
 
+
+def roofline_of(res, world, peak, peak_src):
+    wl, kms, B = res["wl"], res["kernel_ms"], res["B"]
+    W, H = wl.W, wl.H
+    dom = max(kms, key=kms.get)
+    alg = algorithmic_bytes(dom, W, H, B, None)
+    achieved = alg / (kms[dom] / 1e3) / 1e9
+    S = oracle_params(wl.cfg).warp_size
+    n_c = int(res["counters"]["candidates"])
+    warp_gbs = n_c * 2.0 * S * S / (max(kms["sample"], 1e-6) / 1e3) / 1e9
+    thr_gbs = 2.0 * W * H * B / (max(kms["threshold"], 1e-6) / 1e3) / 1e9
+    traffic, tsrc = ncu_traffic(res["name"], dom) if B == wl.cfg["batch"] else (None, None)
+    fps1 = res["fps"] / world
+    return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_unit": "dram bytes per launch (ncu --set full: %s)" % tsrc if traffic else None,
+            "algorithmic_bytes_per_launch": alg, "peak_source": peak_src, "kernel_ms": kms,
+            "threshold_kernel": {"achieved": thr_gbs, "frac": thr_gbs / peak},
+            # the warp stage (k_homography + k_sample): N_cand * (S^2 gathered + S^2 written) algorithmic bytes
+            "warp_kernel": {"achieved": warp_gbs, "frac": warp_gbs / peak, "candidates_per_batch": n_c},
+            "whole_path": {"algorithmic_bytes_per_frame": 3 * W * H, "achieved": fps1 * 3 * W * H / 1e9, "frac": fps1 * 3 * W * H / 1e9 / peak}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C4", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default: the config's)")
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-others", action="store_true", help="skip the short timing of the other BASELINE configs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    host_info = bind_to_gpu_numa(local)  # before torch creates threads / pinned memory
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    res = measure_config(args.config, args, rank, local, world, torch, dist, full=True)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
-
-    # ---- roofline of the dominant kernel ------------------------------------------------------------------
     peak, peak_src = measured_peaks()
-    dom = max(kernel_ms, key=kernel_ms.get)
-    # algorithmic bytes per launch: threshold reads the grey frame and
-    # writes the u8 binarised frame (the 1/8 B/px packed copy is not counted); the scan and the walkers read the packed
-    # image; the other kernels work per candidate (< 1 % of a frame) and are given the whole-path figure 3*W*H.
-    packed = W * H / 8.0 * B
-    alg_bytes = {"threshold": 2.0 * W * H * B, "scan_starts": packed, "trace": packed, "trace_long": packed, "emit": packed}.get(dom, 3.0 * W * H * B)
-    achieved = alg_bytes / (kernel_ms[dom] / 1e3) / 1e9
-    n_cands_batch = int(det.counters()["candidates"])
-    warp_gbs = n_cands_batch * 2.0 * 56 * 56 / (kernel_ms["sample"] / 1e3) / 1e9
-    thr_gbs = 2.0 * W * H * B / (kernel_ms["threshold"] / 1e3) / 1e9
-    # DRAM bytes per launch of the threshold kernel from the committed ncu --set full capture of this command
-    # (profiles/r1p_ncu_threshold_pair_raw.csv: dram__bytes_read.sum 2.238 GB + dram__bytes_write.sum 2.361 GB at 256 x 4K);
-    # only quoted for the workload it was captured on
-    traffic = 4.599e9 if (dom == "threshold" and B == BATCH) else None
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/r1p_ncu_threshold_pair_raw.csv)",
-                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "kernel_ms": kernel_ms,
-                "threshold_kernel": {"achieved": thr_gbs, "frac": thr_gbs / peak},
-                # the warp stage (k_homography + k_sample): N_cand * (S^2 gathered + S^2 written) algorithmic bytes
-                "warp_kernel": {"achieved": warp_gbs, "frac": warp_gbs / peak, "candidates_per_batch": n_cands_batch},
-                "whole_path": {"algorithmic_bytes_per_frame": 3 * W * H, "achieved": fps / world * 3 * W * H / 1e9,
-                               "frac": fps / world * 3 * W * H / 1e9 / peak}}
+    roofline = roofline_of(res, world, peak, peak_src)
+    wl = res["wl"]
+    cpu = None if args.skip_cpu else wl.cpu_baselines()
+    W, H, B = wl.W, wl.H, res["B"]
+    n_launch = KERNELS_PER_BATCH + (1 if wl.cfg["params"].get("erosion") else 0)
+    del res["wl"], wl
+    torch.cuda.empty_cache()
 
-    # ---- CPU baseline: the oracle port on a bounded sample of the same workload ------------------------------
-    cpu = None
-    if not args.skip_cpu:
-        from oracle import native
-        threads = host_threads()
-        sample = min(B, 256)  # the whole batch: ~20 CPU-seconds of work spread over the host threads
-        hostf = frames[:sample].cpu().numpy()
-        native.detect_batch(hostf[:threads], oracle_params(), K, D, MARKER_SIZE, threads=threads)
-        t0 = time.perf_counter()
-        native.detect_batch(hostf, oracle_params(), K, D, MARKER_SIZE, threads=threads)
-        dt = time.perf_counter() - t0
-        cpu = {"value": sample / dt, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": "%d frames of the same batch, oracle/aruco_oracle.cpp, OpenMP frame-parallel on %d threads" % (sample, threads)}
+    # ---- the other BASELINE configs, short form (1 GPU runs only) -----------------------------------------------
+    others = None
+    if world == 1 and not args.skip_others and args.config == "C4" and not args.batch:
+        others = {}
+        for name in ("C1", "C2", "C3", "C5", "C4s4"):
+            try:
+                r = measure_config(name, args, 0, local, 1, torch, dist, full=False)
+                rf = roofline_of(r, 1, peak, peak_src)
+                c = CONFIGS[name]
+                o = {"workload": c["workload"], "frames_per_step": r["B"], "steps": r["steps"], "value": r["fps"], "unit": "frames/s",
+                     "ms_per_step": r["ms_total"] / r["steps"], "mpix_per_s": r["fps"] * c["W"] * c["H"] / 1e6,
+                     "markers_per_frame": r["markers_per_frame"], "parity": r["parity"],
+                     "e2e": None if r["e2e"] is None else {k: r["e2e"][k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+                     "dominant_kernel": rf["kernel"], "roofline_frac": rf["frac"], "roofline_achieved_gbs": rf["achieved"],
+                     "kernel_ms": r["kernel_ms"]}
+                if not args.skip_cpu:
+                    cb = r["wl"].cpu_baselines(budget_px=4e8)
+                    o["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                others[name] = o
+                del r["wl"], r
+                torch.cuda.empty_cache()
+            except SystemExit:
+                raise
+            except Exception as e:  # a side measurement must not take the headline line down
+                others[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+                log("[bench] other config %s failed: %r" % (name, e))
 
-    line = {"metric": "frames_per_s_4k_100markers", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "mpix_per_s": fps * W * H / 1e6,
-            "config": {"workload": "C4: synthetic 3840x2160 grey, 100 Fiducidal markers/frame, ADPT_THRES 7/7 + LINES + PnP",
-                       "frames_per_gpu_per_step": B, "noise_sigma": SIGMA, "distinct_scenes": N_BASE,
-                       "l2": "inputs larger than L2 (batch = %.2f GB per GPU vs 126 MB L2)" % (B * W * H / 1e9),
-                       "parallelism": "frame shards, one per GPU, no collective", "pipelining": "2 batches in flight per GPU (two contexts / streams); every step enqueues one batch and fetches its markers"},
-            "markers_per_frame": n_markers / (args.steps * B), "parity": parity, "clocks": clocks, "e2e": e2e,
-            "gpu_launches": KERNELS_PER_BATCH * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+    line = {"metric": METRIC.get(args.config, "frames_per_s_" + args.config), "value": res["fps"], "unit": "frames/s", "n_gpus": world,
+            "steps": res["steps"], "warmup": args.warmup, "ms_per_step": res["ms_total"] / res["steps"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "mpix_per_s": res["fps"] * W * H / 1e6,
+            "config": config_dict(CONFIGS[args.config], B, {"pipelining": "2 batches in flight per GPU inside ONE library context "
+                                                            "(ab_enqueue_batch_device twice before ab_fetch_results); every step enqueues one batch and fetches its markers"}),
+            "markers_per_frame": res["markers_per_frame"], "parity": res["parity"], "clocks": res["clocks"], "e2e": res["e2e"],
+            "per_rank_ms": res["per_rank_ms"], "host": host_info,
+            "gpu_launches": n_launch * res["steps"], "roofline": roofline, "cpu_baseline": cpu, "other_configs": others,
             "target_frames_per_s": 2000}
     emit(line)
     if world > 1:

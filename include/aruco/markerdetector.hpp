@@ -32,6 +32,11 @@ struct Point2f {
     Point2f() {}
     Point2f(float x_, float y_) : x(x_), y(y_) {}
 };
+struct Point {  // cv::Point (int)
+    int x = 0, y = 0;
+    Point() {}
+    Point(int x_, int y_) : x(x_), y(y_) {}
+};
 struct Size {
     int width = 0, height = 0;
     Size() {}
@@ -104,28 +109,47 @@ public:
     }
 };
 
+// MarkerDetector::MarkerCandidate (markerdetector.h:45-62): a marker plus the contour it came from
+class MarkerCandidate : public Marker {
+public:
+    std::vector<Point> contour;  // all the points of its contour
+    int idx = -1;                // index position in the global contour list
+    MarkerCandidate() {}
+    MarkerCandidate(const Marker& m) : Marker(m) {}
+};
+
 class MarkerDetector {
 public:
+    typedef aruco::MarkerCandidate MarkerCandidate;
     enum ThresholdMethods { FIXED_THRES, ADPT_THRES, CANNY };              // markerdetector.h:125
     enum CornerRefinementMethod { NONE, HARRIS, SUBPIX, LINES };           // markerdetector.h:186
     // MarkerdetectorFunc (markerdetector.h:78) on a raw S x S 8UC1 buffer
     typedef int (*MarkerdetectorFunc)(uint8_t* canonical, int size, int* nRotations, void* user);
 
-    explicit MarkerDetector(int device = 0) : h_(nullptr), speed_(0) {
+    explicit MarkerDetector(int device = 0) : h_(nullptr), speed_(0), device_(device) {
         int rc = ab_create(device, &h_);
         if (rc != AB_OK) throw Exception(rc, "aruco_b200: no CUDA device (this library has no CPU path)");
         ab_default_params(&p_);
     }
     ~MarkerDetector() { if (h_) ab_destroy(h_); }
-    MarkerDetector(const MarkerDetector&) = delete;
-    MarkerDetector& operator=(const MarkerDetector&) = delete;
+    // The reference holds detectors by value (e.g. BoardDetector, boarddetector.h:146): a copy is a new device context
+    // with the same configuration (parameters, dictionary, decoder function); per-frame state is not copied.
+    MarkerDetector(const MarkerDetector& o) : h_(nullptr), speed_(0), device_(o.device_) {
+        int rc = ab_create(device_, &h_);
+        if (rc != AB_OK) throw Exception(rc, "aruco_b200: no CUDA device (this library has no CPU path)");
+        ab_default_params(&p_);
+        copy_config(o);
+    }
+    MarkerDetector& operator=(const MarkerDetector& o) {
+        if (this != &o) copy_config(o);
+        return *this;
+    }
 
     // detect (markerdetector.h:102-120)
     void detect(const ImageView& input, std::vector<Marker>& detectedMarkers, const float* camMatrix = nullptr,
                 const float* distCoeff = nullptr, float markerSizeMeters = -1, bool setYPerpendicular = false) {
         if (input.empty() || (input.channels != 1 && input.channels != 3)) throw Exception(AB_E_INVALID, "detect: 8UC1 or 8UC3 image required");
-        p_.set_y_perpendicular = setYPerpendicular;
-        push();
+        set([&](ab_params& q) { q.set_y_perpendicular = setYPerpendicular; });
         std::vector<ab_marker> buf(kCap);
         int32_t n = 0;
         int rc = input.channels == 1
@@ -145,54 +169,49 @@ public:
         else detect(input, detectedMarkers, nullptr, nullptr, markerSizeMeters, setYPerpendicular);
     }
 
-    void setThresholdMethod(ThresholdMethods m) { p_.thres_method = m; push(); }
+    // every setter validates a COPY of the parameters and commits it only when the library accepts it (a rejected value
+    // must not poison later calls)
+    void setThresholdMethod(ThresholdMethods m) { set([&](ab_params& q) { q.thres_method = m; }); }
     ThresholdMethods getThresholdMethod() const { return (ThresholdMethods)p_.thres_method; }
-    void setThresholdParams(double param1, double param2) { p_.thres_param1 = param1; p_.thres_param2 = param2; push(); }
+    void setThresholdParams(double param1, double param2) { set([&](ab_params& q) { q.thres_param1 = param1; q.thres_param2 = param2; }); }
     void getThresholdParams(double& param1, double& param2) const { param1 = p_.thres_param1; param2 = p_.thres_param2; }
-    void setThresholdParamRange(size_t r1 = 0, size_t /*r2*/ = 0) { p_.thres_param1_range = (int)r1; push(); }  // h:152
+    void setThresholdParamRange(size_t r1 = 0, size_t /*r2*/ = 0) { set([&](ab_params& q) { q.thres_param1_range = (int)r1; }); }  // h:152
     void enableLockedCornersMethod(bool enable) {  // markerdetector.cpp:291-295
-        p_.locked_corners = enable;
-        if (enable) p_.corner_method = SUBPIX;
-        push();
+        set([&](ab_params& q) {
+            q.locked_corners = enable;
+            if (enable) q.corner_method = SUBPIX;
+        });
     }
-    void enableErosion(bool enable) { p_.erosion = enable; push(); }  // API-compat extension (removed upstream)
-    void setCornerRefinementMethod(CornerRefinementMethod m) { p_.corner_method = m; push(); }
+    void enableErosion(bool enable) { set([&](ab_params& q) { q.erosion = enable; }); }  // API-compat extension (removed upstream)
+    void setCornerRefinementMethod(CornerRefinementMethod m) { set([&](ab_params& q) { q.corner_method = m; }); }
     CornerRefinementMethod getCornerRefinementMethod() const { return (CornerRefinementMethod)p_.corner_method; }
-    void setMinMaxSize(float min = 0.03f, float max = 0.5f) {
-        ab_params q = p_;
-        q.min_size = min;
-        q.max_size = max;
-        check(ab_set_params(h_, &q));  // CV_Assert(min>0 && min<=1 && max>0 && max<=1 && min<max), cpp:1031-1038
-        p_ = q;
-    }
+    // CV_Assert(min>0 && min<=1 && max>0 && max<=1 && min<max), cpp:1031-1038
+    void setMinMaxSize(float min = 0.03f, float max = 0.5f) { set([&](ab_params& q) { q.min_size = min; q.max_size = max; }); }
     void getMinMaxSize(float& min, float& max) const { min = p_.min_size; max = p_.max_size; }
     void setDesiredSpeed(int val) {  // markerdetector.cpp:265-285
         if (val < 0) val = 0;
         else if (val > 3) val = 2;
+        set([&](ab_params& q) {
+            if (val == 0) { q.warp_size = 56; q.corner_method = SUBPIX; }
+            else if (val == 1 || val == 2) { q.warp_size = 28; q.corner_method = NONE; }
+        });
         speed_ = val;
-        if (val == 0) { p_.warp_size = 56; p_.corner_method = SUBPIX; }
-        else if (val == 1 || val == 2) { p_.warp_size = 28; p_.corner_method = NONE; }
-        push();
     }
     int getDesiredSpeed() const { return speed_; }
-    void setWarpSize(int val) {
-        ab_params q = p_;
-        q.warp_size = val;
-        check(ab_set_params(h_, &q));  // CV_Assert(val >= 10), cpp:1047-1051
-        p_ = q;
-    }
+    void setWarpSize(int val) { set([&](ab_params& q) { q.warp_size = val; }); }  // CV_Assert(val >= 10), cpp:1047-1051
     int getWarpSize() const { return p_.warp_size; }
     // setMakerDetectorFunction (markerdetector.h:243): built-ins run on the device, others are called back
-    void useFiducidalMarkers() { p_.decoder = AB_DECODER_FIDUCIDAL; push(); }
+    void useFiducidalMarkers() { set([&](ab_params& q) { q.decoder = AB_DECODER_FIDUCIDAL; }); }
     void useHighlyReliableMarkers(int n, int count, const uint8_t* bits, int tau0, float correctionDistanceRate = 1.f) {
         check(ab_load_hrm_dictionary(h_, n, count, bits, tau0, correctionDistanceRate));  // loadDictionary, hrm.cpp:312-328
-        p_.decoder = AB_DECODER_HRM;
-        push();
+        dict_bits_.assign(bits, bits + (size_t)count * n * n);
+        dict_n_ = n; dict_count_ = count; dict_tau0_ = tau0; dict_rate_ = correctionDistanceRate;
+        set([&](ab_params& q) { q.decoder = AB_DECODER_HRM; });
     }
     void setMakerDetectorFunction(MarkerdetectorFunc fn, void* user = nullptr) {
         check(ab_set_decoder_callback(h_, fn, user));
-        p_.decoder = AB_DECODER_HOST_CALLBACK;
-        push();
+        cb_ = fn; cb_user_ = user;
+        set([&](ab_params& q) { q.decoder = AB_DECODER_HOST_CALLBACK; });
     }
 
     // getThresholdedImage (h:183): copies the binarised image of the last detect into dst (rows x cols, step)
@@ -234,6 +253,16 @@ public:
         for (int k = 0; k < 4; k++) { q[2 * k] = points[k].x; q[2 * k + 1] = points[k].y; }
         check(ab_warp(h_, in.data, in.cols, in.rows, in.step, q, size.width, out));
     }
+    // refineCandidateLines (h:280, cpp:931-997): LINES refinement of one candidate from its contour
+    void refineCandidateLines(MarkerCandidate& candidate, const float* camMatrix = nullptr, const float* distCoeff = nullptr) {
+        if (candidate.size() != 4 || candidate.contour.size() < 4) throw Exception(AB_E_INVALID, "refineCandidateLines: 4 corners and a contour");
+        std::vector<int32_t> xy(2 * candidate.contour.size());
+        for (size_t i = 0; i < candidate.contour.size(); i++) { xy[2 * i] = candidate.contour[i].x; xy[2 * i + 1] = candidate.contour[i].y; }
+        float c[8];
+        for (int k = 0; k < 4; k++) { c[2 * k] = candidate[k].x; c[2 * k + 1] = candidate[k].y; }
+        check(ab_refine_candidate_lines(h_, xy.data(), (int)candidate.contour.size(), c, camMatrix, distCoeff));
+        for (int k = 0; k < 4; k++) candidate[k] = Point2f(c[2 * k], c[2 * k + 1]);
+    }
     ab_context* handle() { return h_; }
 
 private:
@@ -241,9 +270,35 @@ private:
     ab_context* h_;
     ab_params p_;
     int speed_;
+    int device_;
     int last_rows_ = 0, last_cols_ = 0;
+    MarkerdetectorFunc cb_ = nullptr;
+    void* cb_user_ = nullptr;
+    std::vector<uint8_t> dict_bits_;
+    int dict_n_ = 0, dict_count_ = 0, dict_tau0_ = 0;
+    float dict_rate_ = 1.f;
     void check(int rc) { if (rc != AB_OK) throw Exception(rc, ab_last_error(h_)); }
-    void push() { check(ab_set_params(h_, &p_)); }
+    template <class F>
+    void set(F f) {
+        ab_params q = p_;
+        f(q);
+        check(ab_set_params(h_, &q));
+        p_ = q;
+    }
+    void copy_config(const MarkerDetector& o) {
+        if (!o.dict_bits_.empty()) {
+            check(ab_load_hrm_dictionary(h_, o.dict_n_, o.dict_count_, o.dict_bits_.data(), o.dict_tau0_, o.dict_rate_));
+            dict_bits_ = o.dict_bits_;
+            dict_n_ = o.dict_n_; dict_count_ = o.dict_count_; dict_tau0_ = o.dict_tau0_; dict_rate_ = o.dict_rate_;
+        }
+        if (o.cb_) {
+            check(ab_set_decoder_callback(h_, o.cb_, o.cb_user_));
+            cb_ = o.cb_; cb_user_ = o.cb_user_;
+        }
+        check(ab_set_params(h_, &o.p_));
+        p_ = o.p_;
+        speed_ = o.speed_;
+    }
     static Marker convert(const ab_marker& m) {
         Marker r;
         r.id = m.id;

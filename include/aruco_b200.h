@@ -90,11 +90,16 @@ AB_API int ab_get_params(const ab_context* ctx, ab_params* p);
  * bits = count*n*n bytes (row-major, 0/1), correction radius = rate*((tau0-1)/2).                        */
 AB_API int ab_load_hrm_dictionary(ab_context* ctx, int n, int count, const uint8_t* bits, int tau0, float rate);
 AB_API int ab_set_decoder_callback(ab_context* ctx, ab_decoder_fn fn, void* user); /* h:243 (custom fn)  */
-/* Sizes device buffers. max_start_candidates / max_contour_points are per frame; <=0 picks defaults.     */
+/* Sizes device buffers. max_start_candidates / max_contour_points are per frame; <=0 picks defaults.  The capacities
+ * are remembered: later automatic re-reservations (a larger batch, another warp size) keep them.  On failure the
+ * context holds no buffers and the next call reserves again.                                                      */
 AB_API int ab_reserve(ab_context* ctx, int width, int height, int max_batch, int max_quads_per_frame,
                       int max_candidates_per_frame, int64_t max_start_candidates_per_frame,
                       int64_t max_contour_points_per_frame);
-AB_API int ab_set_stream(ab_context* ctx, void* cuda_stream);  /* run on the caller's CUDA stream         */
+/* Run on the caller's CUDA stream.  The handle is used as given: NULL is the legacy default stream (handle 0), which
+ * is what torch.cuda.current_stream().cuda_stream reports for the default stream.  A fresh context runs on a private
+ * non-blocking stream until this is called.                                                                       */
+AB_API int ab_set_stream(ab_context* ctx, void* cuda_stream);
 
 /* ---- detect: MarkerDetector::detect (markerdetector.h:102-120, cpp:302-478) ----------------------- */
 /* Host frames (8UC1, row stride `row_stride`, consecutive frames `frame_stride` bytes apart). Copies in,
@@ -103,8 +108,12 @@ AB_API int ab_set_stream(ab_context* ctx, void* cuda_stream);  /* run on the cal
 AB_API int ab_detect_batch(ab_context* ctx, const uint8_t* frames, int width, int height, size_t row_stride,
                            size_t frame_stride, int n_frames, const float* K, const float* D, float marker_size,
                            ab_marker* out, int cap_per_frame, int32_t* counts);
-/* Same with frames already resident in device memory: enqueue is asynchronous on the context's stream,
- * fetch copies the markers to the host and reports device-side errors.                                    */
+/* Same with frames already resident in device memory: enqueue is asynchronous, fetch copies the markers to the host
+ * and reports device-side errors.  TWO batches may be in flight: a second enqueue before the first fetch runs on a
+ * second, library-owned set of buffers and an internal stream (ordered after the caller's stream at enqueue time), so
+ * its kernels overlap the tail of the first batch; a third enqueue returns AB_E_STATE.  ab_fetch_results returns the
+ * batches in enqueue order.  The frames of a batch must stay untouched until that batch has been fetched.  The state
+ * getters below read the batch last enqueued or fetched.                                                           */
 AB_API int ab_enqueue_batch_device(ab_context* ctx, const uint8_t* dev_frames, int width, int height,
                                    size_t row_stride, size_t frame_stride, int n_frames, const float* K,
                                    const float* D, float marker_size);
@@ -144,6 +153,12 @@ AB_API int ab_detect_rectangles(ab_context* ctx, const uint8_t* thres, int width
 /* warp (h:275, cpp:684-697) */
 AB_API int ab_warp(ab_context* ctx, const uint8_t* grey, int width, int height, size_t row_stride, const float* quad,
                    int size, uint8_t* out);
+/* refineCandidateLines (h:280, cpp:931-997): LINES refinement of one candidate.  contour_xy = n_points (x, y) pairs in
+ * the order MarkerCandidate::contour holds them (h:45-62), corners = the 4 (integer valued) corners, which must be
+ * points of the contour; replaced by the intersections of the fitted side lines.  The contour is undistorted first
+ * only when BOTH K and D are given (cpp:957-959).                                                                   */
+AB_API int ab_refine_candidate_lines(ab_context* ctx, const int32_t* contour_xy, int n_points, float* corners /* 8, in/out */,
+                                     const float* K, const float* D);
 /* Marker::calculateExtrinsics (marker.h / marker.cpp:112-125) for n markers */
 AB_API int ab_calculate_extrinsics(ab_context* ctx, ab_marker* markers, int n, const float* K, const float* D,
                                    float marker_size, int set_y_perpendicular);
