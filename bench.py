@@ -146,6 +146,8 @@ def bind_to_gpu_numa(local):
     """Pins this rank's threads to the CPUs next to its GPU (NVML's ideal CPU set = the GPU's NUMA node / PCIe root) BEFORE
     any pinned host memory is allocated, so the staging pages are first-touched on that node."""
     info = {"cpus_before": host_threads()}
+    global _ALL_CPUS
+    _ALL_CPUS = os.sched_getaffinity(0)
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -170,6 +172,18 @@ def bind_to_gpu_numa(local):
     except Exception as e:  # NVML missing: leave the affinity alone
         info["note"] = "not bound: %s" % type(e).__name__
     return info
+
+
+_ALL_CPUS = None
+
+
+def unbind_cpus():
+    """Back to every core the process was given (the CPU baseline legs use all of them)."""
+    if _ALL_CPUS:
+        try:
+            os.sched_setaffinity(0, _ALL_CPUS)
+        except Exception:
+            pass
 
 
 def oracle_params(cfg):
@@ -669,6 +683,7 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return 0
+    unbind_cpus()
     peak, peak_src = measured_peaks()
     roofline = roofline_of(res, world, peak, peak_src)
     wl = res["wl"]
