@@ -13,6 +13,7 @@
 #include "ab_device.cuh"
 #include "k_threshold.cuh"
 #include "k_threshold_pair.cuh"
+#include "k_threshold_tma.cuh"
 #include "k_canny.cuh"
 #include "k_contours.cuh"
 #include "k_polygon.cuh"
@@ -30,8 +31,10 @@ constexpr int MAX_SUB = 4;  // sub-batches (streams) a batch can be pipelined ov
 struct ab_context {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // every kernel / copy of this context runs here (private, non-blocking)
     bool own_stream = true;
+    cudaStream_t user_stream = nullptr;  // ab_set_stream: the caller's stream; each enqueue is ordered after it
+    bool has_user_stream = false;
     cudaStream_t copy_stream = nullptr;
     cudaStream_t sub_stream[MAX_SUB] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
@@ -97,6 +100,7 @@ struct ab_context {
     int pending[2] = {0, 0};       // FIFO of un-fetched batches: 0 = this context, 1 = the twin
     int n_pending = 0;
     int cur = 0;                   // which of the two the state getters read (last enqueued or fetched)
+    bool worker_call = false;      // inside ab_threshold (thresHold never erodes: the u8 image must be written)
     cudaEvent_t ev_in = nullptr;   // orders the twin's stream after the caller's stream at enqueue time
     // capacities the caller chose in ab_reserve (0 = defaults); kept across automatic re-reservations
     int userQ = 0, userC = 0;
@@ -318,15 +322,11 @@ int ab_get_params(const ab_context* ctx, ab_params* p) {
 
 int ab_set_stream(ab_context* ctx, void* s) {
     if (!ctx) return AB_E_INVALID;
-    cudaSetDevice(ctx->device);
-    if (ctx->own_stream && ctx->stream) {
-        cudaStreamSynchronize(ctx->stream);
-        cudaStreamDestroy(ctx->stream);
-    }
-    // the handle is used as given: NULL is the caller's legacy default stream (handle 0), as torch's
-    // current_stream().cuda_stream reports it.  A fresh context runs on a private non-blocking stream until this is called.
-    ctx->stream = (cudaStream_t)s;
-    ctx->own_stream = false;
+    // The handle is used as given: NULL is the caller's legacy default stream (handle 0), which is what torch reports for
+    // its default stream.  The library keeps launching on its own streams (one per in-flight batch, so that two batches can
+    // overlap); every enqueue first records an event on the caller's stream and makes its stream wait for it.
+    ctx->user_stream = (cudaStream_t)s;
+    ctx->has_user_stream = true;
     return AB_OK;
 }
 
@@ -562,12 +562,14 @@ static int launch_threshold(ab_context* ctx, const Batch& b, int method, double 
         a.aligned4 = ((((uintptr_t)b.grey) | b.grey_row | b.grey_frame) & 3) == 0;
         a.out_mul = out_mul;
         a.out_off = out_off;
+        a.skip_u8 = ctx->params.erosion != 0 && !ctx->worker_call;  // k_erode writes the (eroded) u8 image
         int nth = (a.TWo + 2 * a.R4) / 4;
         nth = (nth + 31) & ~31;
         size_t SPAN = 4 * (size_t)nth;
         size_t smem = (((size_t)k * SPAN + 15) & ~(size_t)15) + 4 * SPAN + nth;
         dim3 grid((b.W + a.TWo - 1) / a.TWo, (b.H + a.RH - 1) / a.RH, b.B);
-        if (!launch_threshold_pair(a, b.B, st) && !launch_threshold_fast(a, b.B, st)) k_threshold_adaptive<<<grid, nth, smem, st>>>(a);
+        if (!launch_threshold_tma(a, b.B, st) && !launch_threshold_pair(a, b.B, st) && !launch_threshold_fast(a, b.B, st))
+            k_threshold_adaptive<<<grid, nth, smem, st>>>(a);
     } else if (method == AB_THRES_FIXED) {
         int thr = (int)floor(p1);
         k_threshold_fixed<<<ctx->sm_count * 8, 256, 0, st>>>(b.grey, b.grey_row, b.grey_frame, b.thres, b.bits, b.bits_words,
@@ -947,8 +949,9 @@ static int enqueue_on_free_slot(ab_context* ctx, const uint8_t* dev_frames, int 
     if (which) {
         int rc = get_twin(ctx, &tgt);
         if (rc) return rc;
-        // the frames were produced on the owner's stream
-        CK(cudaEventRecord(ctx->ev_in, ctx->stream));
+    }
+    if (ctx->has_user_stream) {  // the frames were produced on the caller's stream
+        CK(cudaEventRecord(ctx->ev_in, ctx->user_stream));
         CK(cudaStreamWaitEvent(tgt->stream, ctx->ev_in, 0));
     }
     int rc = ensure_reserved(tgt, width, height, n_frames * n_thres_images(ctx->params));
@@ -1288,7 +1291,9 @@ int ab_threshold(ab_context* ctx, const uint8_t* grey, int width, int height, si
     CK(cudaMemcpy2DAsync(ctx->d_grey[0], width, grey, row_stride, width, height, cudaMemcpyHostToDevice, ctx->stream));
     Batch b;
     fill_batch(ctx, b, ctx->d_grey[0], width, (size_t)width * height, 1, nullptr, nullptr, -1.f);
+    ctx->worker_call = true;
     rc = launch_threshold(ctx, b, method, param1, param2);
+    ctx->worker_call = false;
     if (rc) return rc;
     CK(cudaMemcpy2DAsync(out, out_stride, b.thres, width, width, height, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -26,6 +26,7 @@ struct ThrArgs {
     int TWo, RH, R4;
     int aligned4;  // source rows allow 32-bit loads
     int out_mul, out_off;  // output (virtual) frame = f * out_mul + out_off  (setThresholdParamRange: several images per frame)
+    int skip_u8;           // erosion follows and writes the u8 image itself: kernels that honour this write only the packed image
 };
 
 __global__ void k_threshold_adaptive(ThrArgs a) {
@@ -139,40 +140,50 @@ __global__ void k_threshold_fixed(const uint8_t* grey, size_t grey_row, size_t g
     }
 }
 
-// 3x3 erosion (cv::erode(thres, Mat()), out-of-image = 255) on the packed image; rewrites thres and bits.
+// 3x3 erosion (cv::erode(thres, Mat()), out-of-image = 255) on the packed image: 32 pixels per AND.  Writes the eroded
+// packed image and the eroded u8 image (the threshold kernel skips its own u8 store when erosion is on, so the binarised
+// frame is written to HBM once).  One thread per 32-pixel word: nine word loads (three rows, L1/L2 hits), two shifts and
+// four ANDs per row, then the 32 result bytes go out as two 16-byte stores.
+__device__ __forceinline__ uint32_t bits4_to_bytes(uint32_t n) {  // bit j of the nibble -> byte j = 0x00 / 0xFF
+    return (((n & 15u) * 0x00204081u) & 0x01010101u) * 0xFFu;
+}
 __global__ void k_erode(const uint32_t* in, uint32_t* out, uint8_t* thres, size_t bits_words, int W, int H, int wpr, int B) {
-    int ww = (W + 31) >> 5;
-    size_t total = (size_t)ww * H * B;
+    const int ww = (W + 31) >> 5;
+    const size_t total = (size_t)ww * H * B;
+    const bool vec = (W & 15) == 0 && (((uintptr_t)thres) & 15) == 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        int w = (int)(i % ww);
-        int y = (int)((i / ww) % H);
-        int f = (int)(i / ((size_t)ww * H));
+        const unsigned line = (unsigned)(i / (unsigned)ww);  // f * H + y < 2^32
+        const int w = (int)(i - (size_t)line * ww);
+        const int f = (int)(line / (unsigned)H), y = (int)(line - (unsigned)f * H);
         const uint32_t* base = in + (size_t)f * bits_words;
-        int nvalid = min(32, W - 32 * w);
-        uint32_t vmask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+        const int nvalid = min(32, W - 32 * w);
+        const uint32_t vmask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
         uint32_t acc = 0xFFFFFFFFu;
+#pragma unroll
         for (int dy = -1; dy <= 1; dy++) {
-            int yy = y + dy;
-            uint32_t cur, prv, nxt;
-            if (yy < 0 || yy >= H) {
-                cur = prv = nxt = 0xFFFFFFFFu;
-            } else {
-                const uint32_t* row = base + bit_word_index(wpr, BIT_PAD + w, yy);
-                cur = row[0] | ~vmask;                          // pixels beyond W count as 255
-                prv = (w == 0) ? 0xFFFFFFFFu : row[-BIT_TILE];  // pixels left of 0 count as 255
-                nxt = (w == ww - 1) ? 0xFFFFFFFFu : row[BIT_TILE];
-                if (w == ww - 2) {
-                    int nv2 = W - 32 * (w + 1);
-                    if (nv2 < 32) nxt |= ~((1u << nv2) - 1u);
-                }
+            const int yy = y + dy;
+            if (yy < 0 || yy >= H) continue;  // rows outside the image count as 255
+            const uint32_t* row = base + bit_word_index(wpr, BIT_PAD + w, yy);
+            const uint32_t cur = row[0] | ~vmask;                          // pixels beyond W count as 255
+            const uint32_t prv = (w == 0) ? 0xFFFFFFFFu : row[-BIT_TILE];  // pixels left of 0 count as 255
+            uint32_t nxt = (w == ww - 1) ? 0xFFFFFFFFu : row[BIT_TILE];
+            if (w == ww - 2) {
+                const int nv2 = W - 32 * (w + 1);
+                if (nv2 < 32) nxt |= ~((1u << nv2) - 1u);
             }
-            uint32_t l = (cur << 1) | (prv >> 31), rr = (cur >> 1) | (nxt << 31);
-            acc &= cur & l & rr;
+            acc &= cur & ((cur << 1) | (prv >> 31)) & ((cur >> 1) | (nxt << 31));
         }
         acc &= vmask;
         out[(size_t)f * bits_words + bit_word_index(wpr, BIT_PAD + w, y)] = acc;
         uint8_t* orow = thres + ((size_t)f * H + y) * W + 32 * w;
-        for (int j = 0; j < nvalid; j++) orow[j] = (acc >> j) & 1u ? 255 : 0;
+        if (vec && nvalid >= 16) {
+            *reinterpret_cast<uint4*>(orow) = make_uint4(bits4_to_bytes(acc), bits4_to_bytes(acc >> 4), bits4_to_bytes(acc >> 8), bits4_to_bytes(acc >> 12));
+            if (nvalid == 32)
+                *reinterpret_cast<uint4*>(orow + 16) =
+                    make_uint4(bits4_to_bytes(acc >> 16), bits4_to_bytes(acc >> 20), bits4_to_bytes(acc >> 24), bits4_to_bytes(acc >> 28));
+        } else {
+            for (int j = 0; j < nvalid; j++) orow[j] = (acc >> j) & 1u ? 255 : 0;
+        }
     }
 }
 

@@ -96,9 +96,12 @@ AB_API int ab_set_decoder_callback(ab_context* ctx, ab_decoder_fn fn, void* user
 AB_API int ab_reserve(ab_context* ctx, int width, int height, int max_batch, int max_quads_per_frame,
                       int max_candidates_per_frame, int64_t max_start_candidates_per_frame,
                       int64_t max_contour_points_per_frame);
-/* Run on the caller's CUDA stream.  The handle is used as given: NULL is the legacy default stream (handle 0), which
- * is what torch.cuda.current_stream().cuda_stream reports for the default stream.  A fresh context runs on a private
- * non-blocking stream until this is called.                                                                       */
+/* Names the caller's CUDA stream: every ab_enqueue_batch_device is ordered after the work already submitted to it (an
+ * event is recorded there and the library's own stream waits for it), so frames produced on that stream need no host
+ * synchronisation.  The handle is used as given: NULL is the legacy default stream (handle 0), which is what
+ * torch.cuda.current_stream().cuda_stream reports for the default stream.  The library launches on private streams (one
+ * per in-flight batch); results are ordered by ab_fetch_results.  Without this call nothing is ordered: the frames must be
+ * complete on the device when they are enqueued.                                                                  */
 AB_API int ab_set_stream(ab_context* ctx, void* cuda_stream);
 
 /* ---- detect: MarkerDetector::detect (markerdetector.h:102-120, cpp:302-478) ----------------------- */
@@ -110,8 +113,7 @@ AB_API int ab_detect_batch(ab_context* ctx, const uint8_t* frames, int width, in
                            ab_marker* out, int cap_per_frame, int32_t* counts);
 /* Same with frames already resident in device memory: enqueue is asynchronous, fetch copies the markers to the host
  * and reports device-side errors.  TWO batches may be in flight: a second enqueue before the first fetch runs on a
- * second, library-owned set of buffers and an internal stream (ordered after the caller's stream at enqueue time), so
- * its kernels overlap the tail of the first batch; a third enqueue returns AB_E_STATE.  ab_fetch_results returns the
+ * second, library-owned set of buffers and a second internal stream, so its kernels overlap the tail of the first batch; a third enqueue returns AB_E_STATE.  ab_fetch_results returns the
  * batches in enqueue order.  The frames of a batch must stay untouched until that batch has been fetched.  The state
  * getters below read the batch last enqueued or fetched.                                                           */
 AB_API int ab_enqueue_batch_device(ab_context* ctx, const uint8_t* dev_frames, int width, int height,
