@@ -28,6 +28,15 @@
 #ifndef AB_THT_MINB
 #define AB_THT_MINB 1
 #endif
+#ifndef AB_THT_RPB
+#define AB_THT_RPB 2  // rows per CTA barrier: 2, or 0 = K (half a group)
+#endif
+#ifndef AB_THT_OWN
+#define AB_THT_OWN 1  // a thread's own column sums stay in registers (two 16-byte shared loads per row instead of three)
+#endif
+#ifndef AB_THT_PREF_TO
+#define AB_THT_PREF_TO 96
+#endif
 
 namespace ab {
 
@@ -76,13 +85,16 @@ __global__ void __launch_bounds__(TO + 32, AB_THT_MINB) k_threshold_tma(const __
     constexpr int ROWB = TW + 32;              // staged bytes per row: columns X0-16 .. X0+TW+15 (TMA: 16-byte aligned start)
     constexpr int ROWP = (ROWB + 127) & ~127;  // row pitch in shared memory: TMA destinations are 128-byte aligned
     constexpr int RH = (AB_THT_RH / GR) * GR;  // output rows per CTA
+    constexpr int RPB = AB_THT_RPB ? AB_THT_RPB : K;  // rows published per CTA barrier
+    constexpr bool OWN = AB_THT_OWN && RPB == 2 && R4 == 4;
+    static_assert(GR % RPB == 0, "rows per barrier must divide the group");
     static_assert(ROWB % 16 == 0 && R4 <= 8, "TMA box: inner extent must be a multiple of 16 bytes");
     // dynamic shared memory: staged rows (groups, then the 2R priming rows) | 4 column-sum rows (two buffers of two) | barriers
     extern __shared__ __align__(128) uint8_t tht_smem[];
     constexpr int STAGE_BYTES = (NG * GR + 2 * R) * ROWP;
     uint8_t* stage = tht_smem;
     uint32_t* cs = reinterpret_cast<uint32_t*>(tht_smem + STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tht_smem + STAGE_BYTES + 4 * BUF_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tht_smem + STAGE_BYTES + 2 * RPB * BUF_BYTES);
     const int t = threadIdx.x;
     const int X0 = blockIdx.x * TW, y0 = blockIdx.y * RH, f = blockIdx.z;
     const int nout = min(RH, a.H - y0);
@@ -169,10 +181,16 @@ __global__ void __launch_bounds__(TO + 32, AB_THT_MINB) k_threshold_tma(const __
 #pragma unroll
     for (int j = 2 * R; j < K; j++) ring[j][0] = ring[j][1] = ring[j][2] = ring[j][3] = 0u;
     // horizontal window sums, comparison and stores of one output row whose column sums sit at shared offset `rd`
-    auto emit_row = [&](uint32_t rd, const uint32_t* c, bool row_ok) {
+    auto emit_row = [&](uint32_t rd, const uint32_t* c, bool row_ok, const uint32_t* own) {
         uint32_t w[NV];
+        if (OWN) {  // the middle four entries are this thread's own sums
+            lds128(rd, w[0], w[1], w[2], w[3]);
+            w[4] = own[0], w[5] = own[1], w[6] = own[2], w[7] = own[3];
+            lds128(rd + 32u, w[8], w[9], w[10], w[11]);
+        } else {
 #pragma unroll
-        for (int q = 0; q < NV / 4; q++) lds128(rd + 16u * q, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+            for (int q = 0; q < NV / 4; q++) lds128(rd + 16u * q, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        }
         uint32_t S0 = GC;
 #pragma unroll
         for (int d = R4 - R; d <= R4 + R; d++) S0 += w[d];
@@ -207,17 +225,22 @@ __global__ void __launch_bounds__(TO + 32, AB_THT_MINB) k_threshold_tma(const __
     auto body = [&](uint32_t gbase, int o, auto tail) {
         constexpr bool TAIL = decltype(tail)::value;
 #pragma unroll
-        for (int jj = 0; jj < GR; jj += 2) {
-            accumulate(gbase + (uint32_t)(jj * ROWP), ring[(2 * R + jj) % K], false);
-            sts128(s_wr + boff, V0, V1, V2, V3);
-            accumulate(gbase + (uint32_t)((jj + 1) * ROWP), ring[(2 * R + jj + 1) % K], false);
-            sts128(s_wr + boff + BUF_BYTES, V0, V1, V2, V3);
+        for (int jj = 0; jj < GR; jj += RPB) {
+            uint32_t own[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int q = 0; q < RPB; q++) {
+                accumulate(gbase + (uint32_t)((jj + q) * ROWP), ring[(2 * R + jj + q) % K], false);
+                sts128(s_wr + boff + q * BUF_BYTES, V0, V1, V2, V3);
+                if (OWN && q == 0) own[0] = V0, own[1] = V1, own[2] = V2, own[3] = V3;
+            }
             __syncthreads();
             if (is_out) {
-                emit_row(s_rd + boff, ring[(R + jj) % K], !TAIL || o + jj < nout);
-                emit_row(s_rd + boff + BUF_BYTES, ring[(R + jj + 1) % K], !TAIL || o + jj + 1 < nout);
+                const uint32_t cur[4] = {V0, V1, V2, V3};
+#pragma unroll
+                for (int q = 0; q < RPB; q++)
+                    emit_row(s_rd + boff + q * BUF_BYTES, ring[(R + jj + q) % K], !TAIL || o + jj + q < nout, q == 0 ? own : cur);
             }
-            boff = 2 * BUF_BYTES - boff;
+            boff = RPB * BUF_BYTES - boff;
         }
     };
     for (int g = 0; g < ngroups; g++) {
@@ -247,6 +270,7 @@ inline ab_encode_tiled_fn tensor_map_encoder() {
 
 // the TO whose tile width 8*TO divides W (widest first); 0 if none
 inline int threshold_tma_tile(int W) {
+    if (W % (8 * AB_THT_PREF_TO) == 0) return AB_THT_PREF_TO;
     for (int to : {96, 120, 80, 64, 40})  // (8 TO + 32) / 4 <= 256: the TMA box limit
         if (W % (8 * to) == 0) return to;
     return 0;
@@ -254,7 +278,8 @@ inline int threshold_tma_tile(int W) {
 
 constexpr size_t threshold_tma_smem(int K, int TO) {
     const int R = K / 2, R4 = (R + 3) & ~3, HO = 4 * TO, TW = 2 * HO, CSW = HO + 2 * R4;
-    return (size_t)(AB_THT_NG * 2 * K + 2 * R) * (size_t)((TW + 32 + 127) & ~127) + 4 * (size_t)CSW * 4 + 8 * (AB_THT_NG + 1);
+    const int RPB = AB_THT_RPB ? AB_THT_RPB : K;
+    return (size_t)(AB_THT_NG * 2 * K + 2 * R) * (size_t)((TW + 32 + 127) & ~127) + 2 * RPB * (size_t)CSW * 4 + 8 * (AB_THT_NG + 1);
 }
 template <class KERNEL>
 inline void threshold_tma_launch(KERNEL kern, dim3 grid, int threads, size_t smem, cudaStream_t st, const CUtensorMap& map, const ThrTmaArgs& ta) {
