@@ -5,13 +5,15 @@ CXX       := /usr/bin/g++
 NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 \
              -Xcompiler -fPIC,-fvisibility=hidden --shared -Iinclude
 LIB       := aruco_b200/lib/libaruco_b200.so
-CSRC      := $(wildcard aruco_b200/csrc/*.cu aruco_b200/csrc/*.cuh) include/aruco_b200.h
+CSRC      := $(sort $(wildcard aruco_b200/csrc/*.cu aruco_b200/csrc/*.cuh) include/aruco_b200.h)
+# hash of the product sources, embedded in ab_version(): the test fixture rebuilds when the shipped binary is stale
+SRCHASH   := $(shell cat $(CSRC) | sha256sum | cut -c1-16)
 
 all: $(LIB) oracle hostcheck facade
 
 $(LIB): $(CSRC)
 	@mkdir -p aruco_b200/lib
-	$(NVCC) $(NVFLAGS) -Xptxas -v -o $@ aruco_b200/csrc/aruco_b200.cu 2> aruco_b200/lib/ptxas.log || (cat aruco_b200/lib/ptxas.log; false)
+	$(NVCC) $(NVFLAGS) -DAB_SOURCE_HASH=\"$(SRCHASH)\" -Xptxas -v -o $@ aruco_b200/csrc/aruco_b200.cu 2> aruco_b200/lib/ptxas.log || (cat aruco_b200/lib/ptxas.log; false)
 
 oracle: oracle/_build/liboracle.so
 oracle/_build/liboracle.so: $(wildcard oracle/*.cpp oracle/*.h)

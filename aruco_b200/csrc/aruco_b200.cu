@@ -26,7 +26,11 @@ using namespace ab;
 
 constexpr int MAX_SUB = 4;  // sub-batches (streams) a batch can be pipelined over
 
-#define AB_VERSION "aruco_b200 0.1 (sm_100a)"
+#ifndef AB_SOURCE_HASH
+#define AB_SOURCE_HASH "unknown"
+#endif
+// "src:" = first 16 hex digits of sha256 over the product sources (Makefile SRCHASH; tests/conftest.py checks it)
+#define AB_VERSION "aruco_b200 0.2 (sm_100a) src:" AB_SOURCE_HASH
 
 struct ab_context {
     int device = 0;
@@ -727,13 +731,12 @@ static Batch sub_view(ab_context* ctx, const Batch& w, int f0, int nf, int s) {
     return v;
 }
 
-// LINES refinement: with a distorted camera the undistorted contour of a candidate is cached in shared memory
-constexpr int LINES_CACHE_POINTS = 4096;
-static void launch_refine_lines(const Batch& b, dim3 grid, cudaStream_t st) {
-    if (b.cam.has_K && b.cam.has_D && !b.cam.zero_D)
-        k_refine_lines<true><<<grid, 128, LINES_CACHE_POINTS * sizeof(float2), st>>>(b, LINES_CACHE_POINTS);
-    else
-        k_refine_lines<false><<<grid, 128, 0, st>>>(b, 0);
+// LINES refinement; the contour is undistorted first only with a distorted camera (cpp:957-959; all-zero coefficients
+// make cv::undistortPoints the identity on pixel coordinates, see Camera::zero_D)
+static void launch_refine_lines(const Batch& b, cudaStream_t st) {
+    const dim3 grid(LINES_CTAS_PER_FRAME, b.B);
+    if (b.cam.has_K && b.cam.has_D && !b.cam.zero_D) k_refine_lines<true><<<grid, 128, 0, st>>>(b);
+    else k_refine_lines<false><<<grid, 128, 0, st>>>(b);
 }
 
 // one sub-batch (a view of the batch buffers) on one stream: every stage of the path
@@ -817,7 +820,7 @@ static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
         k_corner_maxima<<<dim3(4 * b.cap_c, n), 64, smem, st>>>(b);
     }
     if (P.corner_method == AB_CORNER_LINES) {
-        launch_refine_lines(b, gcand, st);
+        launch_refine_lines(b, st);
     } else if (P.corner_method == AB_CORNER_HARRIS) {
         k_refine_harris<<<dim3(b.cap_c, n), 128, 0, st>>>(b);
     } else if (P.corner_method == AB_CORNER_SUBPIX) {
@@ -830,6 +833,7 @@ static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
     if (timing) cudaEventRecord(ctx->kev[10], st);
     if (timing) cudaEventRecord(ctx->ev[4], st);
     k_finalize<<<n, 128, 0, st>>>(b);
+    if (b.cam.has_K && b.marker_size > 0) k_pose<<<dim3((b.cap_c + 31) / 32, n), 32, 0, st>>>(b);
     CK(cudaGetLastError());
     if (timing) cudaEventRecord(ctx->kev[11], st);
     if (timing) cudaEventRecord(ctx->ev[5], st);
@@ -1379,11 +1383,9 @@ int ab_refine_candidate_lines(ab_context* ctx, const int32_t* contour_xy, int n_
     // the reference undistorts only when both matrices are given (cpp:957-959)
     const Camera cam = make_camera(K && D ? K : nullptr, K && D ? D : nullptr);
     if (cam.has_K && cam.has_D && !cam.zero_D)
-        k_refine_lines_single<true><<<1, 128, LINES_CACHE_POINTS * sizeof(float2), st>>>(d_pts.as<uint32_t>(), n_points, d_io.as<float>(), cam,
-                                                                                         LINES_CACHE_POINTS, d_io.as<float>() + 8, d_err.as<unsigned>());
+        k_refine_lines_single<true><<<1, 128, 0, st>>>(d_pts.as<uint32_t>(), n_points, d_io.as<float>(), cam, d_io.as<float>() + 8, d_err.as<unsigned>());
     else
-        k_refine_lines_single<false><<<1, 128, 0, st>>>(d_pts.as<uint32_t>(), n_points, d_io.as<float>(), cam, 0, d_io.as<float>() + 8,
-                                                        d_err.as<unsigned>());
+        k_refine_lines_single<false><<<1, 128, 0, st>>>(d_pts.as<uint32_t>(), n_points, d_io.as<float>(), cam, d_io.as<float>() + 8, d_err.as<unsigned>());
     CK(cudaGetLastError());
     float res[8];
     unsigned err = 0;

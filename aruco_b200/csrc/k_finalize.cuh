@@ -1,6 +1,10 @@
-// Stage 5: result assembly (src/markerdetector.cpp:364-382, 416-467), one CTA per frame:
-// corner rotation by nRotations, stable sort by id, duplicate-id removal (keep the larger perimeter),
-// border filter, then one thread per surviving marker runs the planar PnP (cv::solvePnP ITERATIVE) in f64.
+// Stage 5: result assembly (src/markerdetector.cpp:364-382, 416-467).
+//   k_finalize: one CTA per frame -- corner rotation by nRotations, stable sort by id, duplicate-id removal (keep the
+//               larger perimeter), border filter; writes the marker list without poses.
+//   k_pose:     one thread per surviving marker, one WARP per CTA -- planar PnP (cv::solvePnP ITERATIVE) in f64.  The LM
+//               chain of a marker is ~20 dependent iterations; as part of k_finalize (128-thread CTAs, one per frame) the
+//               256 frames of a batch needed two waves over the 148 SMs at 7 % warp occupancy (ncu r1x: 0.44 ms).  Warp
+//               CTAs put all markers of the batch on the device at once: one chain latency instead of two.
 #pragma once
 #include "ab_device.cuh"
 
@@ -83,7 +87,6 @@ __global__ void __launch_bounds__(128) k_finalize(Batch b) {
     }
     __syncthreads();
     ab_marker* out = b.markers + (size_t)f * b.cap_c;
-    const bool pose = b.cam.has_K && b.marker_size > 0;  // (:450)
     for (int p = t; p < n; p += blockDim.x) {
         int o = s_outpos[p];
         if (o < 0) continue;
@@ -94,20 +97,30 @@ __global__ void __launch_bounds__(128) k_finalize(Batch b) {
         m.pad_ = 0.f;
         m.has_pose = 0;
         for (int j = 0; j < 3; j++) m.rvec[j] = m.tvec[j] = 0.0;
-        if (pose) {
-            double r[3] = {0, 0, 0}, tv[3] = {0, 0, 0};
-            if (solve_pnp_marker(b.cam, m.corners, b.marker_size, r, tv)) {
-                if (b.set_y_perp) rotate_x_axis(r);
-                m.has_pose = 1;
-            }
-            for (int j = 0; j < 3; j++) {
-                m.rvec[j] = r[j];
-                m.tvec[j] = tv[j];
-            }
-            m.ssize = b.marker_size;
-        }
         out[o] = m;
     }
+}
+
+// pose of every marker k_finalize kept (:450-467); launched only when a camera and a marker size were given (:450)
+__global__ void __launch_bounds__(32) k_pose(Batch b) {
+    const int f = blockIdx.y, slot = blockIdx.x * 32 + threadIdx.x;
+    if (slot >= (int)b.n_markers[f]) return;
+    ab_marker* m = b.markers + (size_t)f * b.cap_c + slot;
+    float c[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) c[j] = m->corners[j];
+    double r[3] = {0, 0, 0}, tv[3] = {0, 0, 0};
+    int ok = 0;
+    if (solve_pnp_marker(b.cam, c, b.marker_size, r, tv)) {
+        if (b.set_y_perp) rotate_x_axis(r);
+        ok = 1;
+    }
+    for (int j = 0; j < 3; j++) {
+        m->rvec[j] = r[j];
+        m->tvec[j] = tv[j];
+    }
+    m->has_pose = ok;
+    m->ssize = b.marker_size;
 }
 
 // Marker::calculateExtrinsics for an array of markers (public worker)

@@ -27,6 +27,7 @@ __device__ __forceinline__ float warp_max_f(float v) {
 }
 
 constexpr int LINES_MAX_SWEEPS = 8;  // Jacobi sweeps kept for replay (two columns converge in 1-3)
+constexpr int LINES_SIDE_CAP = 512;  // points of a side staged in shared memory (longer sides are re-read from the contour)
 
 // refineCandidateLines for one candidate by one CTA of 128 threads (warp l = side l).  `pts` = the contour in the
 // order the reference holds it (`rev`: read it backwards, :622-625), `c` = the 4 corners (integer valued).
@@ -34,11 +35,11 @@ constexpr int LINES_MAX_SWEEPS = 8;  // Jacobi sweeps kept for replay (two colum
 // = OpenCV's one-sided Jacobi SVD of the columns (coordinate, 1).  The rotated columns are not stored: a sweep
 // re-derives them from the points by replaying the earlier rotations (1-3 of them), so one pass over the side yields
 // the squared norms and dot product the next sweep needs.  f64 sums are tree-reduced (the reference adds
-// sequentially; they only enter through values rounded to f32).  UNDIST: cv::undistortPoints of the contour first
-// (:957-959), cached in shared memory when the contour fits `cache_cap` points.
+// sequentially; they only enter through values rounded to f32).  The first pass stages the side's points (after
+// cv::undistortPoints when UNDIST, :957-959) in shared memory; the later passes read them from there.
 template <bool UNDIST>
 __device__ __forceinline__ void refine_lines_cta(const uint32_t* pts, int n, bool rev, const float* c, const Camera& cam,
-                                                 float2* s_pts, int cache_cap, int* s_ci, float (*s_line)[3], float* refined,
+                                                 float2 (*s_side)[LINES_SIDE_CAP], int* s_ci, float (*s_line)[3], float* refined,
                                                  unsigned int* err) {
     const int t = threadIdx.x, lane = t & 31, l = t >> 5;
     if (t < 4) s_ci[t] = -1;
@@ -46,21 +47,15 @@ __device__ __forceinline__ void refine_lines_cta(const uint32_t* pts, int n, boo
     uint32_t ck[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) ck[k] = (uint32_t)(int)c[2 * k] | ((uint32_t)(int)c[2 * k + 1] << 16);
-    const bool cached = UNDIST && n <= cache_cap;
     for (int j = t; j < n; j += blockDim.x) {
         uint32_t p = rev ? pts[n - 1 - j] : pts[j];
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (p == ck[k]) atomicMax(&s_ci[k], j);  // last match wins (:935-941)
-        if (cached) {
-            float x, y;
-            undistort_point_px(cam, (float)(p & 0xFFFFu), (float)(p >> 16), &x, &y);  // contour points are integer pixels
-            s_pts[j] = make_float2(x, y);
-        }
     }
     __syncthreads();
     const int c0 = s_ci[0], c1 = s_ci[1], c2 = s_ci[2], c3 = s_ci[3];
-    if (c0 < 0 || c1 < 0 || c2 < 0 || c3 < 0) return;  // cannot happen for approxPolyDP vertices
+    if (c0 < 0 || c1 < 0 || c2 < 0 || c3 < 0) return;  // a corner that is not on the contour (cannot happen inside detect)
     bool inverse;
     if (c1 > c0 && (c2 > c1 || c2 < c0)) inverse = false;
     else if (c2 > c1 && c2 < c0) inverse = false;
@@ -71,20 +66,25 @@ __device__ __forceinline__ void refine_lines_cta(const uint32_t* pts, int n, boo
         int m = inverse ? (start - end) : (end - start);
         if (m < 0) m += n;
         const int m2 = (m == 1) ? 2 : m;  // 1-point side: add the next corner (:972-976)
-        auto point = [&](int i, float& x, float& y) {
-            int j = start + inc * i;  // start in [0, n), i < m2 <= n + 1
+        const bool staged = m2 <= LINES_SIDE_CAP;
+        float2* side = s_side[l];
+        auto fetch = [&](int i, float& x, float& y) {  // point i of the side from the contour
+            int j = start + inc * i;                   // start in [0, n), i < m2 <= n + 1
             if (m == 1 && i == 1) j = end;
             if (j >= n) j -= n;
             if (j < 0) j += n;
-            if (cached) {
-                float2 q = s_pts[j];
+            uint32_t p = rev ? pts[n - 1 - j] : pts[j];
+            x = (float)(p & 0xFFFFu);
+            y = (float)(p >> 16);
+            if (UNDIST) undistort_point_px(cam, x, y, &x, &y);  // contour points are integer pixels
+        };
+        auto point = [&](int i, float& x, float& y) {
+            if (staged) {
+                float2 q = side[i];
                 x = q.x;
                 y = q.y;
             } else {
-                uint32_t p = rev ? pts[n - 1 - j] : pts[j];
-                x = (float)(p & 0xFFFFu);
-                y = (float)(p >> 16);
-                if (UNDIST) undistort_point_px(cam, x, y, &x, &y);
+                fetch(i, x, y);
             }
         };
         // pass 0: bounding box decides the parametrisation; column sums of both candidates
@@ -92,7 +92,8 @@ __device__ __forceinline__ void refine_lines_cta(const uint32_t* pts, int n, boo
         double Sx = 0, Sy = 0, Sxx = 0, Syy = 0;
         for (int i = lane; i < m2; i += 32) {
             float x, y;
-            point(i, x, y);
+            fetch(i, x, y);
+            if (staged) side[i] = make_float2(x, y);
             mnx = fminf(mnx, x);
             mxx = fmaxf(mxx, x);
             mny = fminf(mny, y);
@@ -102,6 +103,7 @@ __device__ __forceinline__ void refine_lines_cta(const uint32_t* pts, int n, boo
             Sxx += (double)x * x;
             Syy += (double)y * y;
         }
+        __syncwarp();
         mnx = warp_min_f(mnx);
         mxx = warp_max_f(mxx);
         mny = warp_min_f(mny);
@@ -199,29 +201,34 @@ __device__ __forceinline__ void refine_lines_cta(const uint32_t* pts, int n, boo
     }
 }
 
+// grid = (LINES_CTAS_PER_FRAME, frames): a CTA walks the candidate list of its frame with that stride, so every CTA of the
+// grid has decoded candidates to work on (a CTA per candidate SLOT launched 512 CTAs per frame for ~100 markers)
+constexpr int LINES_CTAS_PER_FRAME = 64;
 template <bool UNDIST>
-__global__ void __launch_bounds__(128) k_refine_lines(Batch b, int cache_cap) {
-    extern __shared__ float2 s_lines_pts[];
+__global__ void __launch_bounds__(128) k_refine_lines(Batch b) {
+    __shared__ float2 s_side[4][LINES_SIDE_CAP];
     __shared__ int s_ci[4];
     __shared__ float s_line[4][3];
-    const int f = blockIdx.y, ci = blockIdx.x;
-    if (ci >= (int)b.n_cands[f]) return;
-    CandRec* cand = b.cands + (size_t)f * b.cap_c + ci;
-    if (cand->id < 0) return;
-    const ContourRec rec = b.contours[cand->contour];
-    // the reference reverses the contour of swapped candidates (:622-625)
-    refine_lines_cta<UNDIST>(b.pool + rec.off, (int)rec.n, cand->swapped != 0, cand->c, b.cam, s_lines_pts, cache_cap, s_ci,
-                             s_line, cand->refined, &b.cnt->err);
+    const int f = blockIdx.y, nc = min((int)b.n_cands[f], b.cap_c);
+    for (int ci = blockIdx.x; ci < nc; ci += gridDim.x) {
+        CandRec* cand = b.cands + (size_t)f * b.cap_c + ci;
+        if (cand->id < 0) continue;
+        const ContourRec rec = b.contours[cand->contour];
+        // the reference reverses the contour of swapped candidates (:622-625)
+        refine_lines_cta<UNDIST>(b.pool + rec.off, (int)rec.n, cand->swapped != 0, cand->c, b.cam, s_side, s_ci, s_line, cand->refined,
+                                 &b.cnt->err);
+        __syncthreads();  // s_ci / s_line / s_side are reused by the next candidate
+    }
 }
 
 // public worker MarkerDetector::refineCandidateLines (h:280): one candidate, contour given by the caller
 template <bool UNDIST>
-__global__ void __launch_bounds__(128) k_refine_lines_single(const uint32_t* pts, int n, const float* corners, Camera cam,
-                                                             int cache_cap, float* out, unsigned int* err) {
-    extern __shared__ float2 s_lines_pts[];
+__global__ void __launch_bounds__(128) k_refine_lines_single(const uint32_t* pts, int n, const float* corners, Camera cam, float* out,
+                                                             unsigned int* err) {
+    __shared__ float2 s_side[4][LINES_SIDE_CAP];
     __shared__ int s_ci[4];
     __shared__ float s_line[4][3];
-    refine_lines_cta<UNDIST>(pts, n, false, corners, cam, s_lines_pts, cache_cap, s_ci, s_line, out, err);
+    refine_lines_cta<UNDIST>(pts, n, false, corners, cam, s_side, s_ci, s_line, out, err);
 }
 
 // bilinear getRectSubPix sample with replicated border, f32 arithmetic in OpenCV's order

@@ -27,6 +27,20 @@ int main(int argc, char** argv) {
             CamParam.resize(aruco::Size(W, H));
         }
         MDetector.detect(aruco::ImageView(img.data(), H, W), Markers, CamParam, size);  // utils/aruco_simple.cpp:77
+        {   // the reference holds detectors by value (boarddetector.h:146): a copy must detect the same markers
+            aruco::MarkerDetector copy(MDetector);
+            std::vector<aruco::Marker> again;
+            copy.detect(aruco::ImageView(img.data(), H, W), again, CamParam, size);
+            bool same = again.size() == Markers.size();
+            for (size_t i = 0; same && i < again.size(); i++)
+                same = again[i].id == Markers[i].id && again[i][0].x == Markers[i][0].x && again[i][2].y == Markers[i][2].y;
+            if (!same) { std::fprintf(stderr, "a copied MarkerDetector detects differently\n"); return 4; }
+            // a rejected setter value must not poison the next call
+            bool threw2 = false;
+            try { copy.setThresholdParamRange(99); } catch (const aruco::Exception&) { threw2 = true; }
+            copy.setThresholdParams(7, 7);
+            if (!threw2) { std::fprintf(stderr, "setThresholdParamRange(99) did not throw\n"); return 5; }
+        }
         for (const auto& m : Markers) {
             std::printf("%d", m.id);
             for (const auto& p : m) std::printf(" %.9g %.9g", p.x, p.y);

@@ -251,3 +251,76 @@ def test_c_abi_strided_and_unaligned_frames(built, frames, expected):
     for i in range(2):
         assert [m.id for m in res[i]] == [m.id for m in ref[i]]
         assert all((a.corners == b.corners).all() for a, b in zip(res[i], ref[i]))
+
+
+def test_refine_candidate_lines_worker(det, frames, expected):
+    """Public worker refineCandidateLines (markerdetector.h:280, cpp:931-997) against the cv2 oracle's restatement, with and
+    without camera (the contour is undistorted only when both matrices are given)."""
+    from conftest import have_cv2
+    if not have_cv2():
+        pytest.skip("cv2 needed")
+    from oracle import cv2_oracle as o
+    K, D = intrinsics(expected, "single")
+    b = o.detect(frames["single"], o.Params(corner_method=0), None, None, -1.0)
+    done = 0
+    for c in b["candidates"]:
+        if c["id"] < 0:
+            continue
+        for cam in ((None, None), (K, D)):
+            ref = o.refine_candidate_lines(np.array(c["quad"], np.float32).reshape(4, 2), c["contour"], cam[0], cam[1])
+            got = det.refineCandidateLines(c["quad"], c["contour"], cam[0], cam[1])
+            assert np.abs(got - ref).max() < 1e-4, (got, ref)
+        done += 1
+    assert done == 6
+    from aruco_b200 import ArucoError
+    with pytest.raises(ArucoError):  # a corner that is not a point of the contour
+        det.refineCandidateLines(np.array([[1, 1], [2, 2], [3, 3], [4, 4]], np.float32), b["candidates"][0]["contour"])
+
+
+def test_two_batches_in_flight(built):
+    """ab_enqueue_batch_device twice before ab_fetch_results: results come back in enqueue order and equal the one-at-a-time
+    results byte for byte; a third enqueue is an error, not an overwrite."""
+    import torch
+    from aruco_b200 import ArucoError, MarkerDetector, synth
+    K, D = synth.camera_for(1920, 1080)
+    fa = np.stack([synth.render_frame(1920, 1080, 50, 80 + i, 2.0)[0] for i in range(3)])
+    fb = np.stack([synth.render_frame(1920, 1080, 50, 90 + i, 2.0)[0] for i in range(3)])
+    da, db = torch.from_numpy(fa).cuda(), torch.from_numpy(fb).cuda()
+    torch.cuda.synchronize()
+    d = MarkerDetector(0)
+    d.set_stream(torch.cuda.current_stream().cuda_stream)  # the default stream: handle 0
+    d.enqueue_device(da.data_ptr(), 1920, 1080, 3, K, D, 0.05)
+    ref_a = d.fetch(3, 128)
+    d.enqueue_device(db.data_ptr(), 1920, 1080, 3, K, D, 0.05)
+    ref_b = d.fetch(3, 128)
+    for rep in range(3):
+        d.enqueue_device(da.data_ptr(), 1920, 1080, 3, K, D, 0.05)
+        d.enqueue_device(db.data_ptr(), 1920, 1080, 3, K, D, 0.05)
+        with pytest.raises(ArucoError) as e:
+            d.enqueue_device(da.data_ptr(), 1920, 1080, 3, K, D, 0.05)
+        assert e.value.code == -5
+        got_a, got_b = d.fetch(3, 128), d.fetch(3, 128)
+        for got, ref in ((got_a, ref_a), (got_b, ref_b)):
+            for f in range(3):
+                assert [m.id for m in got[f]] == [m.id for m in ref[f]] and len(got[f]) >= 45
+                assert all((x.corners == y.corners).all() and (x.Rvec == y.Rvec).all() for x, y in zip(got[f], ref[f]))
+        assert (d.getThresholdedImage(0) == MarkerDetector(0).thresHold(1, fb[0])).all()  # the getters read the batch last fetched
+
+
+def test_canny_with_parameter_range_and_setter_rollback(det, frames):
+    """CANNY ignores the threshold parameters: a parameter range yields the reference's result (its duplicates collapse in the
+    too-near filter).  A rejected setter value is rolled back and does not poison later calls."""
+    from aruco_b200 import ArucoError
+    det.setThresholdMethod(2)
+    try:
+        plain = det.detect(frames["single"])
+        det.setThresholdParamRange(2)
+        ranged = det.detect(frames["single"])
+        assert [m.id for m in plain] == [m.id for m in ranged] and len(plain) >= 5
+        assert all((a.corners == b.corners).all() for a, b in zip(plain, ranged))
+        with pytest.raises(ArucoError):
+            det.setThresholdParamRange(99)
+        det.setThresholdParams(7, 7)  # would re-push the rejected range if it had not been rolled back
+    finally:
+        det.setThresholdParamRange(0)
+        det.setThresholdMethod(1)
