@@ -15,6 +15,11 @@ $(LIB): $(CSRC)
 	@mkdir -p aruco_b200/lib
 	$(NVCC) $(NVFLAGS) -DAB_SOURCE_HASH=\"$(SRCHASH)\" -Xptxas -v -o $@ aruco_b200/csrc/aruco_b200.cu 2> aruco_b200/lib/ptxas.log || (cat aruco_b200/lib/ptxas.log; false)
 
+# the same library with in-kernel index asserts (AB_BOUND, ab_trace.cuh): tools/debug_bounds.sh runs the GPU tests on it
+debug-bounds: aruco_b200/lib/libaruco_b200_dbg.so
+aruco_b200/lib/libaruco_b200_dbg.so: $(CSRC)
+	$(NVCC) $(NVFLAGS) -DAB_DEBUG_BOUNDS -DAB_SOURCE_HASH=\"$(SRCHASH)\" -o $@ aruco_b200/csrc/aruco_b200.cu
+
 oracle: oracle/_build/liboracle.so
 oracle/_build/liboracle.so: $(wildcard oracle/*.cpp oracle/*.h)
 	@mkdir -p oracle/_build
@@ -35,4 +40,4 @@ tests/_build/%: tests/cpp/%.cpp $(FACADE_HDR) $(LIB)
 clean:
 	rm -rf aruco_b200/lib/*.so oracle/_build tests/_build
 
-.PHONY: all oracle hostcheck facade clean
+.PHONY: all oracle hostcheck facade clean debug-bounds

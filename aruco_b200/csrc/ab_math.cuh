@@ -531,6 +531,7 @@ AB_HD void orthonormalize3(double* R) {
 AB_HD void project_marker(const Camera& cam, const double* p, const float* obj, double* uv) {
     double R[9];
     rodrigues_to_mat(p, R);
+#pragma unroll
     for (int i = 0; i < 4; i++) {
         double X = obj[3 * i], Y = obj[3 * i + 1], Z = obj[3 * i + 2];
         double x = R[0] * X + R[1] * Y + R[2] * Z + p[3];
@@ -566,17 +567,25 @@ AB_HD void rodrigues_jacobian(const double* r, double* R, double dR[3][9]) {
     double rv[3] = {r[0] * it, r[1] * it, r[2] * it};
     double rrt[9], rx[9] = {0, -rv[2], rv[1], rv[2], 0, -rv[0], -rv[1], rv[0], 0};
     const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+#pragma unroll
     for (int i = 0; i < 3; i++)
+#pragma unroll
         for (int j = 0; j < 3; j++) rrt[i * 3 + j] = rv[i] * rv[j];
+#pragma unroll
     for (int i = 0; i < 9; i++) R[i] = c * I[i] + c1 * rrt[i] + s * rx[i];
     // R = c I + (1-c) n n^T + s [n]x with n = r/theta
+#pragma unroll
     for (int k = 0; k < 3; k++) {
         // dtheta/dr_k = n_k ; dn_i/dr_k = (delta_ik - n_i n_k)/theta
         double dn[3];
+#pragma unroll
         for (int i = 0; i < 3; i++) dn[i] = ((i == k ? 1. : 0.) - rv[i] * rv[k]) * it;
         double drrt[9], drx[9] = {0, -dn[2], dn[1], dn[2], 0, -dn[0], -dn[1], dn[0], 0};
+#pragma unroll
         for (int i = 0; i < 3; i++)
+#pragma unroll
             for (int j = 0; j < 3; j++) drrt[i * 3 + j] = dn[i] * rv[j] + rv[i] * dn[j];
+#pragma unroll
         for (int i = 0; i < 9; i++)
             dR[k][i] = rv[k] * (-s * I[i] + s * rrt[i] + c * rx[i]) + c1 * drrt[i] + s * drx[i];
     }
@@ -587,6 +596,7 @@ AB_HD void pnp_residual_jacobian(const Camera& cam, const double* p, const float
                                  double J[8][6]) {
     double R[9], dR[3][9];
     rodrigues_jacobian(p, R, dR);
+#pragma unroll
     for (int i = 0; i < 4; i++) {
         double X = obj[3 * i], Y = obj[3 * i + 1], Z = obj[3 * i + 2];
         double x = R[0] * X + R[1] * Y + R[2] * Z + p[3];
@@ -609,10 +619,12 @@ AB_HD void pnp_residual_jacobian(const Camera& cam, const double* p, const float
         // d(xn,yn)/d(x,y,z)
         double dxn[3] = {iz, 0, -xn * iz}, dyn[3] = {0, iz, -yn * iz};
         double du[3], dv[3];  // d(u,v)/d(camera point)
+#pragma unroll
         for (int c = 0; c < 3; c++) {
             du[c] = cam.fx * (dxdx * dxn[c] + dxdy * dyn[c]);
             dv[c] = cam.fy * (dydx * dxn[c] + dydy * dyn[c]);
         }
+#pragma unroll
         for (int k = 0; k < 3; k++) {
             double dX[3] = {dR[k][0] * X + dR[k][1] * Y + dR[k][2] * Z, dR[k][3] * X + dR[k][4] * Y + dR[k][5] * Z,
                             dR[k][6] * X + dR[k][7] * Y + dR[k][8] * Z};
@@ -650,6 +662,46 @@ AB_HD bool solve6(double A[6][6], double* b) {
         double s = b[i];
         for (int c = i + 1; c < 6; c++) s -= A[i][c] * b[c];
         b[i] = s / A[i][i];
+    }
+    return true;
+}
+
+// A x = b for the symmetric positive definite 6x6 system of a damped Gauss-Newton step (J^T J with its diagonal scaled by
+// 1 + lambda): Cholesky with every index known at compile time, so the factor lives in registers (the pivoting LU above
+// indexes its rows dynamically, which puts the matrix into local memory: one L1 round trip per access in the middle of the
+// dependent chain of a Levenberg-Marquardt iteration).  Only the upper triangle of A is read.  Returns false when a pivot
+// is not positive (degenerate geometry); the caller then falls back to the pivoting solver.
+AB_HD bool solve6_spd(const double A[6][6], double* b) {
+    double L[6][6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        double d = A[j][j];
+#pragma unroll
+        for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k];
+        if (!(d > 0.0)) return false;
+        const double inv = 1.0 / sqrt(d);
+        L[j][j] = inv;  // the reciprocal of the diagonal entry
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+            double v = A[j][i];
+#pragma unroll
+            for (int k = 0; k < j; k++) v -= L[i][k] * L[j][k];
+            L[i][j] = v * inv;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) {  // L y = b
+        double v = b[i];
+#pragma unroll
+        for (int k = 0; k < i; k++) v -= L[i][k] * b[k];
+        b[i] = v * L[i][i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {  // L^T x = y
+        double v = b[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; k++) v -= L[k][i] * b[k];
+        b[i] = v * L[i][i];
     }
     return true;
 }
@@ -712,15 +764,20 @@ AB_HD bool solve_pnp_marker(const Camera& cam, const float* corners, float size,
     double prevErrNorm = 0;
     pnp_residual_jacobian(cam, p, obj, m, err, J);
     for (;;) {
-        // state CALC_J
+        // state CALC_J (J^T J is symmetric: the upper triangle is computed, the lower mirrored)
+#pragma unroll
         for (int i = 0; i < 6; i++) {
             double s = 0;
+#pragma unroll
             for (int k = 0; k < 8; k++) s += J[k][i] * err[k];
             JtErr[i] = s;
-            for (int j = 0; j < 6; j++) {
+#pragma unroll
+            for (int j = i; j < 6; j++) {
                 double q = 0;
+#pragma unroll
                 for (int k = 0; k < 8; k++) q += J[k][i] * J[k][j];
                 JtJ[i][j] = q;
+                JtJ[j][i] = q;
             }
             prev[i] = p[i];
         }
@@ -733,13 +790,23 @@ AB_HD bool solve_pnp_marker(const Camera& cam, const float* corners, float size,
         for (;;) {
             double lambda = exp(lambdaLg10 * 2.302585092994046);
             double A[6][6], d[6];
+#pragma unroll
             for (int i = 0; i < 6; i++) {
+#pragma unroll
                 for (int j = 0; j < 6; j++) A[i][j] = JtJ[i][j];
                 A[i][i] *= 1. + lambda;
                 d[i] = JtErr[i];
             }
-            if (!solve6(A, d))
-                for (int i = 0; i < 6; i++) d[i] = 0;
+            if (!solve6_spd(A, d)) {  // cold path: its dynamically indexed copy keeps `A` itself in registers
+                double A2[6][6];
+                for (int i = 0; i < 6; i++) {
+                    for (int j = 0; j < 6; j++) A2[i][j] = JtJ[i][j];
+                    A2[i][i] *= 1. + lambda;
+                    d[i] = JtErr[i];
+                }
+                if (!solve6(A2, d))
+                    for (int i = 0; i < 6; i++) d[i] = 0;
+            }
             for (int i = 0; i < 6; i++) p[i] = prev[i] - d[i];
             // state CHECK_ERR
             pnp_residual(cam, p, obj, m, err);
@@ -1000,13 +1067,19 @@ AB_HD bool solve_pnp_planar(const Camera& cam, const float* obj, const float* im
         for (;;) {
             double lambda = exp(lambdaLg10 * 2.302585092994046);
             double A[6][6], d[6];
+#pragma unroll
             for (int i = 0; i < 6; i++) {
+#pragma unroll
                 for (int j = 0; j < 6; j++) A[i][j] = JtJ[i][j];
                 A[i][i] *= 1. + lambda;
                 d[i] = JtErr[i];
             }
-            if (!solve6(A, d))
-                for (int i = 0; i < 6; i++) d[i] = 0;
+            if (!solve6_spd(A, d)) {
+#pragma unroll
+                for (int i = 0; i < 6; i++) d[i] = JtErr[i];
+                if (!solve6(A, d))
+                    for (int i = 0; i < 6; i++) d[i] = 0;
+            }
             for (int i = 0; i < 6; i++) p[i] = prev[i] - d[i];
             errNorm = sqrt(pnp_accumulate(cam, p, obj, img, N, false, nullptr, nullptr));
             if (errNorm > prevErrNorm && ++lambdaLg10 <= 16) continue;

@@ -14,6 +14,7 @@
 //
 // Directions (image y grows downwards):  0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE.
 #pragma once
+#include <stdio.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -31,6 +32,20 @@ namespace ab {
 // it straddles a tile edge) and stays there for ~32 steps.
 // One zero word column left and >= 1 right of every row, one zero row above and >= 1 below, so a 3x3 neighbourhood
 // never needs a bounds test.
+// -DAB_DEBUG_BOUNDS: in-kernel index asserts (compute-sanitizer is closed on the GPU pool).  A violated bound prints its
+// source position and traps: the launch fails with an error instead of silently writing out of range.
+#if defined(AB_DEBUG_BOUNDS) && defined(__CUDA_ARCH__)
+#define AB_BOUND(cond)                                                             \
+    do {                                                                           \
+        if (!(cond)) {                                                             \
+            printf("AB_DEBUG_BOUNDS violated: %s (%s:%d)\n", #cond, __FILE__, __LINE__); \
+            __trap();                                                              \
+        }                                                                          \
+    } while (0)
+#else
+#define AB_BOUND(cond) ((void)0)
+#endif
+
 constexpr int BIT_PAD = 1;     // zero word columns left of the image
 constexpr int BIT_TILE = 32;   // rows (= words) per tile
 AB_HD int bit_words_per_row(int W) { return ((W + 31) >> 5) + BIT_PAD + 1; }  // word columns incl. padding
@@ -55,6 +70,7 @@ struct BitImage {
 AB_HD uint32_t window9(const BitImage& im, int x, int y) {
     const int p = x - 1 + 32 * BIT_PAD;  // pixel x lives at padded bit x + 32*BIT_PAD
     const int sh = p & 31, yr = (y + 1) & 31;
+    AB_BOUND(x >= 0 && x < im.W && y >= 0 && y < im.H);  // a walker never leaves the image
     const uint32_t* r1 = im.word(p >> 5, y);
     const int jump = im.wpr * BIT_TILE - (BIT_TILE - 1);  // to the same column of the next tile row, minus 31
     const uint32_t* r0 = r1 - (yr == 0 ? jump : 1);

@@ -91,12 +91,14 @@ __global__ void __launch_bounds__(256) k_scan_starts(Batch b) {
             while (m) {
                 int j = __ffs((int)m) - 1;
                 m &= m - 1;
+                AB_BOUND(o < b.cap_starts);
                 b.starts[o++] = make_uint2((uint32_t)f, (xb + j) | (y << 16));
             }
             m = hole[k];
             while (m) {
                 int j = __ffs((int)m) - 1;
                 m &= m - 1;
+                AB_BOUND(o < b.cap_starts);
                 b.starts[o++] = make_uint2((uint32_t)f | 0x80000000u, (xb + j) | (y << 16));
             }
         }
@@ -276,7 +278,9 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                             e.dirs = sb | ((f2 ? ((cpd >> 3) & 7u) : sb) << 3) | ((f1 ? (cpd & 7u) : sb) << 6) | ((uint32_t)fw.b << 9) |
                                      ((g1 ? ((cpd >> 6) & 7u) : sb) << 12) | ((g2 ? ((cpd >> 9) & 7u) : sb) << 15);
                             e.pad = 0;
-                            b.emitq[atomicAdd(&b.cnt->n_emit_long, 1u)] = e;  // at most one per parked walk: fits cap_long
+                            const unsigned int ei = atomicAdd(&b.cnt->n_emit_long, 1u);  // at most one per parked walk: fits cap_long
+                            AB_BOUND(ei < b.cap_long);
+                            b.emitq[ei] = e;
                         }
                     }
                     active = false;
@@ -299,6 +303,7 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                     q.dirs = (uint32_t)fw.b | ((uint32_t)bw.b << 4) | ((uint32_t)st.b << 8);
                     q.nf = (uint32_t)nf;
                     q.ng = (uint32_t)ng;
+                    AB_BOUND(qi < b.cap_long);
                     b.longq[qi] = q;
                     active = false;
                 } else {
@@ -369,6 +374,7 @@ __global__ void __launch_bounds__(128) k_emit(Batch b) {
         if (active) {
             if (!backward) {
                 for (int r = 0; r < STEPS; r++) {
+                    AB_BOUND(out >= b.pool && out < b.pool + b.cap_pool);
                     *out++ = (uint32_t)w.x | ((uint32_t)w.y << 16);
                     if (--remaining == 0) {
                         active = false;
@@ -380,6 +386,7 @@ __global__ void __launch_bounds__(128) k_emit(Batch b) {
             } else {
                 for (int r = 0; r < STEPS; r++) {
                     walk_backward(im, w);
+                    AB_BOUND(out >= b.pool && out < b.pool + b.cap_pool);
                     *out-- = (uint32_t)w.x | ((uint32_t)w.y << 16);
                     if (--remaining == 0) {
                         active = false;
@@ -449,6 +456,7 @@ __global__ void __launch_bounds__(128) k_emit_long(Batch b) {
         if (active) {
             if (!backward) {
                 for (int r = 0; r < STEPS; r++) {
+                    AB_BOUND(out >= b.pool && out < b.pool + b.cap_pool);
                     *out++ = (uint32_t)w.x | ((uint32_t)w.y << 16);
                     if (--remaining == 0) {
                         active = false;
@@ -460,6 +468,7 @@ __global__ void __launch_bounds__(128) k_emit_long(Batch b) {
             } else {
                 for (int r = 0; r < STEPS; r++) {
                     walk_backward(im, w);
+                    AB_BOUND(out >= b.pool && out < b.pool + b.cap_pool);
                     *out-- = (uint32_t)w.x | ((uint32_t)w.y << 16);
                     if (--remaining == 0) {
                         active = false;

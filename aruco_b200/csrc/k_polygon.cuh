@@ -29,7 +29,9 @@ __global__ void __launch_bounds__(128) k_polygon(Batch b) {
     unsigned int ncont = b.cnt->n_contours;
     if (ncont > b.cap_contours) ncont = b.cap_contours;
     for (unsigned int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < ncont; ci += nwarps) {
+        AB_BOUND((unsigned)ci < b.cap_contours);
         ContourRec rec = b.contours[ci];
+        AB_BOUND((unsigned long long)rec.off + rec.n <= b.cap_pool);
         rec.frame &= CONTOUR_FRAME_MASK;  // bits 31/30 = border type / long contour, used by the emit kernels only
         const int n = (int)rec.n;
         if (n < 4) continue;
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(128) k_polygon(Batch b) {
                     }
                     qr.key = ((uint32_t)(b.n_t - 1 - (int)tt) << 28) | rec.key;
                     qr.contour = ci;
+                    AB_BOUND((int)q < b.cap_q && rf * (unsigned)b.n_t < (unsigned)b.B);
                     b.quads[(size_t)rf * b.cap_q + q] = qr;
                 }
             }
