@@ -144,8 +144,18 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
     TraceStart st{0, 0, 0, 0};
     WalkState fw{0, 0, 0}, bw{0, 0, 0};
     uint32_t e_fw = 0, type_bit = 0;  // e_fw: forward table entry of the current forward state
+#ifdef AB_TRACE_SMEM_LUT
+    // variant study: the two 4 KB step tables in shared memory instead of L1-cached global memory
+    __shared__ __align__(16) uint8_t s_lut[2 * WALK_LUT_SIZE];
+    for (int i = threadIdx.x; i < 2 * WALK_LUT_SIZE / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(s_lut)[i] = reinterpret_cast<const uint4*>(b.walk_lut)[i];
+    __syncthreads();
+    const uint8_t* lut_fw = s_lut;
+    const uint8_t* lut_bw = s_lut + WALK_LUT_SIZE;
+#else
     const uint8_t* __restrict__ lut_fw = b.walk_lut;
     const uint8_t* __restrict__ lut_bw = b.walk_lut + WALK_LUT_SIZE;
+#endif
     int nf = 0, ng = 0, frame = 0;
     // LONG only: walker states at the last two power-of-two step counts (pixels, back-directions, step count);
     // they cut the finished contour into segments that k_emit_long writes in parallel

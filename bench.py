@@ -623,7 +623,10 @@ def measure_config(name, args, rank, local, world, torch, dist, full):
                # pinned H2D copies alone (same buffer, same chunking, no kernels), per rank, measured one rank after the
                # other's e2e leg but concurrently across ranks: the host-side ceiling of e2e
                "h2d_only_gbs": h2d, "h2d_gbs_in_e2e": e2e_fps * W * H / 1e9,
-               "frac_of_h2d_ceiling": (e2e_fps * W * H / 1e9) / max(sum(h2d), 1e-9)}
+               # the ceiling in the same max-over-ranks convention as `value`: every rank moves the same bytes, the slowest
+               # rank's link decides (on the 8-GPU boxes of this pool GPUs 0-3 and 4-7 sit behind host bridges of different speed)
+               "h2d_ceiling_gbs": world * min(h2d), "frac_of_h2d_ceiling": (e2e_fps * W * H / 1e9) / max(world * min(h2d), 1e-9),
+               "per_rank_frac_of_own_h2d": [B * n_e * W * H / (m / 1e3) / 1e9 / max(g, 1e-9) for m, g in zip(per_rank2, h2d)]}
     res["e2e"] = e2e
     return res
 
