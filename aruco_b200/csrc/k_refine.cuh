@@ -47,11 +47,19 @@ __device__ __forceinline__ void refine_lines_cta(const uint32_t* pts, int n, boo
     uint32_t ck[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) ck[k] = (uint32_t)(int)c[2 * k] | ((uint32_t)(int)c[2 * k + 1] << 16);
-    for (int j = t; j < n; j += blockDim.x) {
-        uint32_t p = rev ? pts[n - 1 - j] : pts[j];
+    // four contour words in flight per thread (the pool was written kernels ago: these are L2 round trips)
+    for (int j0 = t; j0 < n; j0 += 4 * blockDim.x) {
+        uint32_t p[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (p == ck[k]) atomicMax(&s_ci[k], j);  // last match wins (:935-941)
+        for (int u = 0; u < 4; u++) {
+            const int j = j0 + u * blockDim.x;
+            p[u] = j < n ? (rev ? pts[n - 1 - j] : pts[j]) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (p[u] == ck[k]) atomicMax(&s_ci[k], j0 + u * (int)blockDim.x);  // last match wins (:935-941)
     }
     __syncthreads();
     const int c0 = s_ci[0], c1 = s_ci[1], c2 = s_ci[2], c3 = s_ci[3];
@@ -90,6 +98,7 @@ __device__ __forceinline__ void refine_lines_cta(const uint32_t* pts, int n, boo
         // pass 0: bounding box decides the parametrisation; column sums of both candidates
         float mnx = 3.0e38f, mxx = -3.0e38f, mny = 3.0e38f, mxy = -3.0e38f;
         double Sx = 0, Sy = 0, Sxx = 0, Syy = 0;
+#pragma unroll 4
         for (int i = lane; i < m2; i += 32) {
             float x, y;
             fetch(i, x, y);

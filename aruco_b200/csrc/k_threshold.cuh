@@ -148,12 +148,14 @@ __device__ __forceinline__ uint32_t bits4_to_bytes(uint32_t n) {  // bit j of th
     return (((n & 15u) * 0x00204081u) & 0x01010101u) * 0xFFu;
 }
 __global__ void k_erode(const uint32_t* in, uint32_t* out, uint8_t* thres, size_t bits_words, int W, int H, int wpr, int B) {
+    // two threads per 32-pixel word, each writing the 16 bytes of its half: consecutive lanes write consecutive 16-byte
+    // pieces (one thread per word put two half-filled 32-byte sectors per lane on the wire: 0.63 ms per 64 4K frames, r2i)
     const int ww = (W + 31) >> 5;
-    const size_t total = (size_t)ww * H * B;
+    const size_t total = 2 * (size_t)ww * H * B;
     const bool vec = (W & 15) == 0 && (((uintptr_t)thres) & 15) == 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const unsigned line = (unsigned)(i / (unsigned)ww);  // f * H + y < 2^32
-        const int w = (int)(i - (size_t)line * ww);
+        const unsigned line = (unsigned)(i / (unsigned)(2 * ww));  // f * H + y < 2^32
+        const int hw = (int)(i - (size_t)line * (2 * ww)), w = hw >> 1, half = hw & 1;
         const int f = (int)(line / (unsigned)H), y = (int)(line - (unsigned)f * H);
         const uint32_t* base = in + (size_t)f * bits_words;
         const int nvalid = min(32, W - 32 * w);
@@ -174,15 +176,14 @@ __global__ void k_erode(const uint32_t* in, uint32_t* out, uint8_t* thres, size_
             acc &= cur & ((cur << 1) | (prv >> 31)) & ((cur >> 1) | (nxt << 31));
         }
         acc &= vmask;
-        out[(size_t)f * bits_words + bit_word_index(wpr, BIT_PAD + w, y)] = acc;
-        uint8_t* orow = thres + ((size_t)f * H + y) * W + 32 * w;
-        if (vec && nvalid >= 16) {
-            *reinterpret_cast<uint4*>(orow) = make_uint4(bits4_to_bytes(acc), bits4_to_bytes(acc >> 4), bits4_to_bytes(acc >> 8), bits4_to_bytes(acc >> 12));
-            if (nvalid == 32)
-                *reinterpret_cast<uint4*>(orow + 16) =
-                    make_uint4(bits4_to_bytes(acc >> 16), bits4_to_bytes(acc >> 20), bits4_to_bytes(acc >> 24), bits4_to_bytes(acc >> 28));
+        if (half == 0) out[(size_t)f * bits_words + bit_word_index(wpr, BIT_PAD + w, y)] = acc;
+        uint8_t* orow = thres + ((size_t)f * H + y) * W + 32 * w + 16 * half;
+        const uint32_t h16 = acc >> (16 * half);
+        const int nv = nvalid - 16 * half;  // valid pixels of this half
+        if (vec && nv >= 16) {
+            *reinterpret_cast<uint4*>(orow) = make_uint4(bits4_to_bytes(h16), bits4_to_bytes(h16 >> 4), bits4_to_bytes(h16 >> 8), bits4_to_bytes(h16 >> 12));
         } else {
-            for (int j = 0; j < nvalid; j++) orow[j] = (acc >> j) & 1u ? 255 : 0;
+            for (int j = 0; j < nv && j < 16; j++) orow[j] = (h16 >> j) & 1u ? 255 : 0;
         }
     }
 }

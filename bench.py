@@ -56,6 +56,10 @@ CONFIGS = {
                params=dict(p1=21, p2=7, warp_size=64, min_size=0.005, decoder=1, erosion=True)),
     "C4s4": dict(workload="C4s4: C4 at noise sigma 4 (contour storm: ~10x the border pixels of sigma 2)",
                  W=3840, H=2160, batch=64, n=100, sigma=4.0, params={}),
+    # the round-1 generator (175 px markers: ~5 % of them fall below the detector's minimum contour length and are rejected,
+    # 33 % fewer kept contour points) -- kept so that round-1 and round-2 numbers can be compared on the same frames
+    "C4r1": dict(workload="C4r1: C4 with the round-1 marker size (175 px, 94.8 detectable markers/frame)",
+                 W=3840, H=2160, batch=256, n=100, sigma=2.0, marker_px=175, params={}),
 }
 METRIC = {"C4": "frames_per_s_4k_100markers"}
 
@@ -700,7 +704,7 @@ def main():
     others = None
     if world == 1 and not args.skip_others and args.config == "C4" and not args.batch:
         others = {}
-        for name in ("C1", "C2", "C3", "C5", "C4s4"):
+        for name in ("C1", "C2", "C3", "C5", "C4s4", "C4r1"):
             try:
                 r = measure_config(name, args, 0, local, 1, torch, dist, full=False)
                 rf = roofline_of(r, 1, peak, peak_src)
