@@ -150,12 +150,13 @@ __device__ __forceinline__ uint32_t bits4_to_bytes(uint32_t n) {  // bit j of th
 __global__ void k_erode(const uint32_t* in, uint32_t* out, uint8_t* thres, size_t bits_words, int W, int H, int wpr, int B) {
     // two threads per 32-pixel word, each writing the 16 bytes of its half: consecutive lanes write consecutive 16-byte
     // pieces (one thread per word put two half-filled 32-byte sectors per lane on the wire: 0.63 ms per 64 4K frames, r2i)
+    // a CTA takes whole image rows (one 32-bit division per row, none per pixel group)
     const int ww = (W + 31) >> 5;
-    const size_t total = 2 * (size_t)ww * H * B;
+    const unsigned lines = (unsigned)H * (unsigned)B;  // f * H + y < 2^32
     const bool vec = (W & 15) == 0 && (((uintptr_t)thres) & 15) == 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const unsigned line = (unsigned)(i / (unsigned)(2 * ww));  // f * H + y < 2^32
-        const int hw = (int)(i - (size_t)line * (2 * ww)), w = hw >> 1, half = hw & 1;
+    for (unsigned line = blockIdx.x; line < lines; line += gridDim.x)
+    for (int hw = threadIdx.x; hw < 2 * ww; hw += blockDim.x) {
+        const int w = hw >> 1, half = hw & 1;
         const int f = (int)(line / (unsigned)H), y = (int)(line - (unsigned)f * H);
         const uint32_t* base = in + (size_t)f * bits_words;
         const int nvalid = min(32, W - 32 * w);
