@@ -37,6 +37,9 @@
 #ifndef AB_THT_PREF_TO
 #define AB_THT_PREF_TO 96
 #endif
+#ifndef AB_THT_PIPE
+#define AB_THT_PIPE 0  // 1: split arrive / wait (finish the rows of pair p while the barrier of pair p+1 fills): correct, no gain (r2k: 1.276 vs 1.282 ms)
+#endif
 
 namespace ab {
 
@@ -45,6 +48,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -87,6 +93,13 @@ __global__ void __launch_bounds__(TO + 32, AB_THT_MINB) k_threshold_tma(const __
     constexpr int RH = (AB_THT_RH / GR) * GR;  // output rows per CTA
     constexpr int RPB = AB_THT_RPB ? AB_THT_RPB : K;  // rows published per CTA barrier
     constexpr bool OWN = AB_THT_OWN && RPB == 2 && R4 == 4;
+    // PIPE: ncu r2i -- the CTA barrier between publishing the column sums of a row pair and reading the neighbours' was the
+    // top stall (2.7 of 7.8 cycles per issued instruction).  An mbarrier splits it: a thread ARRIVES after publishing row
+    // pair p+1, then finishes the output rows of pair p (whose sums became visible at the previous wait), and only then
+    // WAITS for pair p+1.  Three column-sum buffers, because a fast thread publishes pair p+2 while a slow one still reads
+    // pair p.  The centre-row ring slots of pair p survive the two ring steps of pair p+1 for K >= 7.
+    constexpr bool PIPE = AB_THT_PIPE && RPB == 2 && K >= 7;
+    constexpr int NBUF = PIPE ? 3 : 2;
     static_assert(GR % RPB == 0, "rows per barrier must divide the group");
     static_assert(ROWB % 16 == 0 && R4 <= 8, "TMA box: inner extent must be a multiple of 16 bytes");
     // dynamic shared memory: staged rows (groups, then the 2R priming rows) | 4 column-sum rows (two buffers of two) | barriers
@@ -94,7 +107,7 @@ __global__ void __launch_bounds__(TO + 32, AB_THT_MINB) k_threshold_tma(const __
     constexpr int STAGE_BYTES = (NG * GR + 2 * R) * ROWP;
     uint8_t* stage = tht_smem;
     uint32_t* cs = reinterpret_cast<uint32_t*>(tht_smem + STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tht_smem + STAGE_BYTES + 2 * RPB * BUF_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tht_smem + STAGE_BYTES + NBUF * RPB * BUF_BYTES);  // NG groups, priming, phases
     const int t = threadIdx.x;
     const int X0 = blockIdx.x * TW, y0 = blockIdx.y * RH, f = blockIdx.z;
     const int nout = min(RH, a.H - y0);
@@ -113,6 +126,7 @@ __global__ void __launch_bounds__(TO + 32, AB_THT_MINB) k_threshold_tma(const __
     if (t == 0) {
 #pragma unroll
         for (int i = 0; i <= NG; i++) mbar_init(s_bars + 8u * i, 1);
+        mbar_init(s_bars + 8u * (NG + 1), NT);  // PIPE: every working thread arrives once per row pair
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // priming rows y0-R .. y0+R-1, then the first groups
         const uint32_t pbar = s_bars + 8u * NG;
@@ -243,14 +257,55 @@ __global__ void __launch_bounds__(TO + 32, AB_THT_MINB) k_threshold_tma(const __
             boff = RPB * BUF_BYTES - boff;
         }
     };
-    for (int g = 0; g < ngroups; g++) {
-        const int slot = g % NG;
-        mbar_wait(s_bars + 8u * (uint32_t)slot, (uint32_t)((g / NG) & 1));
-        const uint32_t gbase = s_stage + (uint32_t)(slot * GR * ROWP);
-        if ((g + 1) * GR <= nout) body(gbase, g * GR, std::false_type{});
-        else body(gbase, g * GR, std::true_type{});
-        // every thread is past its last read of this slot (the body ends behind a CTA barrier): refill it
-        if (t == 0 && g + NG < ngroups) issue_group(g + NG);
+    if (!PIPE) {
+        for (int g = 0; g < ngroups; g++) {
+            const int slot = g % NG;
+            mbar_wait(s_bars + 8u * (uint32_t)slot, (uint32_t)((g / NG) & 1));
+            const uint32_t gbase = s_stage + (uint32_t)(slot * GR * ROWP);
+            if ((g + 1) * GR <= nout) body(gbase, g * GR, std::false_type{});
+            else body(gbase, g * GR, std::true_type{});
+            // every thread is past its last read of this slot (the body ends behind a CTA barrier): refill it
+            if (t == 0 && g + NG < ngroups) issue_group(g + NG);
+        }
+    } else {
+        const uint32_t phbar = s_bars + 8u * (NG + 1);
+        uint32_t wr = 0, rd = 0, parity = 0;  // column-sum buffer written by the current pair / read for the previous pair
+        uint32_t oa[4] = {0u, 0u, 0u, 0u}, ob[4] = {0u, 0u, 0u, 0u};  // own sums of the pair that is finished next
+        int orow_i = 0;                                                // first output row of that pair
+        for (int g = 0; g < ngroups; g++) {
+            const int slot = g % NG;
+            mbar_wait(s_bars + 8u * (uint32_t)slot, (uint32_t)((g / NG) & 1));
+            const uint32_t gbase = s_stage + (uint32_t)(slot * GR * ROWP);
+#pragma unroll
+            for (int jj = 0; jj < GR; jj += 2) {
+                accumulate(gbase + (uint32_t)(jj * ROWP), ring[(2 * R + jj) % K], false);
+                sts128(s_wr + wr, V0, V1, V2, V3);
+                const uint32_t na[4] = {V0, V1, V2, V3};
+                accumulate(gbase + (uint32_t)((jj + 1) * ROWP), ring[(2 * R + jj + 1) % K], false);
+                sts128(s_wr + wr + BUF_BYTES, V0, V1, V2, V3);
+                const uint32_t nb[4] = {V0, V1, V2, V3};
+                mbar_arrive(phbar);
+                if (is_out && (jj > 0 || g > 0)) {  // the previous pair: its sums became visible at the last wait
+                    const int pj = (jj + GR - 2) % GR;
+                    emit_row(s_rd + rd, ring[(R + pj) % K], orow_i < nout, oa);
+                    emit_row(s_rd + rd + BUF_BYTES, ring[(R + pj + 1) % K], orow_i + 1 < nout, ob);
+                    orow_i += 2;
+                }
+                mbar_wait(phbar, parity);
+                parity ^= 1u;
+                rd = wr;
+                wr = wr == 2 * 2 * BUF_BYTES ? 0u : wr + 2 * BUF_BYTES;
+#pragma unroll
+                for (int q = 0; q < 4; q++) oa[q] = na[q], ob[q] = nb[q];
+            }
+            // every thread has passed the wait behind its last read of this slot: refill it
+            if (t == 0 && g + NG < ngroups) issue_group(g + NG);
+        }
+        if (is_out) {  // the last pair
+            constexpr int pj = GR - 2;
+            emit_row(s_rd + rd, ring[(R + pj) % K], orow_i < nout, oa);
+            emit_row(s_rd + rd + BUF_BYTES, ring[(R + pj + 1) % K], orow_i + 1 < nout, ob);
+        }
     }
 }
 
@@ -279,7 +334,8 @@ inline int threshold_tma_tile(int W) {
 constexpr size_t threshold_tma_smem(int K, int TO) {
     const int R = K / 2, R4 = (R + 3) & ~3, HO = 4 * TO, TW = 2 * HO, CSW = HO + 2 * R4;
     const int RPB = AB_THT_RPB ? AB_THT_RPB : K;
-    return (size_t)(AB_THT_NG * 2 * K + 2 * R) * (size_t)((TW + 32 + 127) & ~127) + 2 * RPB * (size_t)CSW * 4 + 8 * (AB_THT_NG + 1);
+    const int NBUF = (AB_THT_PIPE && RPB == 2 && K >= 7) ? 3 : 2;
+    return (size_t)(AB_THT_NG * 2 * K + 2 * R) * (size_t)((TW + 32 + 127) & ~127) + NBUF * RPB * (size_t)CSW * 4 + 8 * (AB_THT_NG + 2);
 }
 template <class KERNEL>
 inline void threshold_tma_launch(KERNEL kern, dim3 grid, int threads, size_t smem, cudaStream_t st, const CUtensorMap& map, const ThrTmaArgs& ta) {
