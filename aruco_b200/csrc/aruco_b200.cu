@@ -105,6 +105,9 @@ struct ab_context {
     int n_pending = 0;
     int cur = 0;                   // which of the two the state getters read (last enqueued or fetched)
     bool worker_call = false;      // inside ab_threshold (thresHold never erodes: the u8 image must be written)
+    void* d_scratch = nullptr;     // grow-only device scratch of the small per-call workers (board pose)
+    size_t scratch_bytes = 0;
+    double* h_scratch = nullptr;   // pinned result slot of those workers
     cudaEvent_t ev_in = nullptr;   // orders the twin's stream after the caller's stream at enqueue time
     // capacities the caller chose in ab_reserve (0 = defaults); kept across automatic re-reservations
     int userQ = 0, userC = 0;
@@ -146,6 +149,18 @@ static int set_err(ab_context* c, int code, const char* fmt, ...) {
         if (e_ != cudaSuccess)                                                                           \
             return set_err(ctx, AB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+static int ensure_scratch(ab_context* ctx, size_t bytes) {
+    if (!ctx->h_scratch) CK(cudaMallocHost(&ctx->h_scratch, 64 * sizeof(double)));
+    if (ctx->scratch_bytes >= bytes) return AB_OK;
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    ctx->d_scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    bytes = (bytes + 4095) & ~(size_t)4095;
+    CK(cudaMalloc(&ctx->d_scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return AB_OK;
+}
 
 static void free_buffers(ab_context* c) {
     auto F = [](auto*& p) {
@@ -285,6 +300,8 @@ void ab_destroy(ab_context* ctx) {
         F(ctx->d_dict_tree);
     }
     if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
     for (int i = 0; i < 6; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 12; i++)
@@ -1615,20 +1632,22 @@ int ab_detect_board(ab_context* ctx, const ab_marker* markers, int n, const ab_b
         return AB_OK;
     }
     int N = 4 * nb;
-    DevBuf d_obj, d_img, d_obj2, d_img2, d_out;
-    CK(d_obj.alloc(sizeof(float) * 3 * N));
-    CK(d_img.alloc(sizeof(float) * 2 * N));
-    CK(d_obj2.alloc(sizeof(float) * 3 * N));
-    CK(d_img2.alloc(sizeof(float) * 2 * N));
-    CK(d_out.alloc(sizeof(double) * 8));
-    CK(cudaMemcpyAsync(d_obj.p, obj.data(), sizeof(float) * 3 * N, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_img.p, img.data(), sizeof(float) * 2 * N, cudaMemcpyHostToDevice, ctx->stream));
+    // one grow-only scratch block (obj | img | obj2 | img2 | out) and a pinned result slot: no allocation per call
+    const size_t nf3 = sizeof(float) * 3 * (size_t)N, nf2 = sizeof(float) * 2 * (size_t)N;
+    const size_t off_img = (nf3 + 15) & ~(size_t)15, off_obj2 = off_img + ((nf2 + 15) & ~(size_t)15),
+                 off_img2 = off_obj2 + ((nf3 + 15) & ~(size_t)15), off_out = off_img2 + ((nf2 + 15) & ~(size_t)15);
+    int rcs = ensure_scratch(ctx, off_out + 8 * sizeof(double));
+    if (rcs) return rcs;
+    uint8_t* base = (uint8_t*)ctx->d_scratch;
+    float *d_obj = (float*)base, *d_img = (float*)(base + off_img), *d_obj2 = (float*)(base + off_obj2), *d_img2 = (float*)(base + off_img2);
+    double* d_out = (double*)(base + off_out);
+    CK(cudaMemcpyAsync(d_obj, obj.data(), nf3, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_img, img.data(), nf2, cudaMemcpyHostToDevice, ctx->stream));
     float zeros[5] = {0, 0, 0, 0, 0};
-    k_board_pose<<<1, 32, 0, ctx->stream>>>(d_obj.as<float>(), d_img.as<float>(), N, make_camera(K, D ? D : zeros), repj_err_thres,
-                                            set_y_perp, d_obj2.as<float>(), d_img2.as<float>(), d_out.as<double>());
+    k_board_pose<<<1, 32, 0, ctx->stream>>>(d_obj, d_img, N, make_camera(K, D ? D : zeros), repj_err_thres, set_y_perp, d_obj2, d_img2, d_out);
     CK(cudaGetLastError());
-    double res[8];
-    CK(cudaMemcpyAsync(res, d_out.p, sizeof(res), cudaMemcpyDeviceToHost, ctx->stream));
+    double* res = ctx->h_scratch;
+    CK(cudaMemcpyAsync(res, d_out, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     out->has_pose = res[6] != 0.;
     for (int i = 0; i < 3; i++) {
