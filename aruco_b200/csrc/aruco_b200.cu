@@ -43,7 +43,7 @@ struct ab_context {
     cudaStream_t sub_stream[MAX_SUB] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
     int n_sub_streams = 1;  // measured on B200: no gain from 2-4 sub-batches (full grids leave no room to co-schedule)
-    int grid_trace = 8, grid_long = 8, grid_emit = 8;  // CTAs per SM of the persistent walker grids
+    int grid_trace = 8, grid_long = 8, grid_emit = 4;  // CTAs per SM of the persistent walker grids (r2l sweep: emit 0.57 -> 0.52 ms at 4)
     int last_nsub = 1;
     ab_params params;
     std::string err;

@@ -44,7 +44,10 @@ enum { AB_CORNER_NONE = 0, AB_CORNER_HARRIS = 1, AB_CORNER_SUBPIX = 2, AB_CORNER
  * device, anything else is called back on the host with the canonical images */
 enum { AB_DECODER_FIDUCIDAL = 0, AB_DECODER_HRM = 1, AB_DECODER_HOST_CALLBACK = 2 };
 
-/* Private state of MarkerDetector (markerdetector.h:288-311); defaults = ctor (markerdetector.cpp:235-249). */
+/* Private state of MarkerDetector (markerdetector.h:288-311); defaults = ctor (markerdetector.cpp:235-249).
+ * Limits of this implementation that the reference does not have (ab_set_params / the detect calls return AB_E_INVALID):
+ * thres_param1_range <= 7 (2r+1 <= 15 threshold images per frame), adaptive block size (thres_param1 made odd, >= 3) <= 63,
+ * SUBPIX / locked-corner window (int)thres_param1 in 1..24, warp_size <= 128, frames 8..16384 pixels per side.            */
 typedef struct ab_params {
     int32_t thres_method;        /* _thresMethod      (setThresholdMethod, h:129)            */
     double thres_param1;         /* _thresParam1      (setThresholdParams, h:140)            */

@@ -59,6 +59,38 @@ def test_threshold_worker_bit_exact(det, frames, method, p1, p2):
         assert (got == ref).all()
 
 
+@pytest.mark.parametrize("W", [320, 512, 640, 768, 960, 1024, 1280, 1536, 1920, 3840])
+def test_tma_threshold_tiles_and_borders_bit_exact(det, W):
+    """The TMA-staged kernel over every tile width it dispatches to (8*TO in 768 / 960 / 640 / 512 / 320: one tile, several
+    tiles, box wider than the image), block sizes 3..11, heights that are not a multiple of the row group (a single partial
+    group, 1 row), noise and hard edges at all four image borders -- binarised image AND the packed copy (through erosion,
+    which reads the packed image and writes the u8 image) bit-exact against the oracle."""
+    import ctypes as C
+    from oracle import native
+    lib = native.load()
+    rng = np.random.default_rng(W)
+    for H, k, delta in ((1, 7, 7), (13, 3, 2), (126, 5, 7), (127, 7, 7), (300, 9, -3), (253, 11, 7)):
+        img = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        img[:, :2] = 255 * (H & 1)            # hard edges on the left / right / top / bottom borders
+        img[:, -3:] = 0
+        img[0, :] = 200
+        img[-1, W // 3:] = 17
+        got = det.thresHold(1, img, k, delta)
+        ref = np.empty_like(img)
+        lib.orc_threshold(img.ctypes.data_as(C.c_void_p), W, H, 1, float(k), float(delta), ref.ctypes.data_as(C.c_void_p))
+        assert (got == ref).all(), (W, H, k)
+    # the packed copy and the erosion that follows it (threshold kernel without its u8 store + k_erode)
+    from oracle.cv2_oracle import Params
+    img = rng.integers(0, 256, (139, W), dtype=np.uint8)
+    det.enableErosion(True)
+    try:
+        det.detect(img)
+        ref = native.detect(img, Params(erosion=True))
+        assert (det.getThresholdedImage(0) == ref["thres"]).all()
+    finally:
+        det.enableErosion(False)
+
+
 def test_detect_rectangles_and_warp_workers(det, frames):
     from oracle import native
     from oracle.cv2_oracle import Params
