@@ -37,6 +37,9 @@
 #ifndef AB_THT_PREF_TO
 #define AB_THT_PREF_TO 96
 #endif
+#ifndef AB_THT_SHFL
+#define AB_THT_SHFL 0  // 1: the neighbours' column sums come by warp shuffle; shared memory only carries them across warp edges
+#endif
 #ifndef AB_THT_PIPE
 #define AB_THT_PIPE 0  // 1: split arrive / wait (finish the rows of pair p while the barrier of pair p+1 fills): correct, no gain (r2k: 1.276 vs 1.282 ms)
 #endif
@@ -98,6 +101,7 @@ __global__ void __launch_bounds__(TO + 32, AB_THT_MINB) k_threshold_tma(const __
     // pair p+1, then finishes the output rows of pair p (whose sums became visible at the previous wait), and only then
     // WAITS for pair p+1.  Three column-sum buffers, because a fast thread publishes pair p+2 while a slow one still reads
     // pair p.  The centre-row ring slots of pair p survive the two ring steps of pair p+1 for K >= 7.
+    constexpr bool SHFL = AB_THT_SHFL && OWN && !AB_THT_PIPE;
     constexpr bool PIPE = AB_THT_PIPE && RPB == 2 && K >= 7;
     constexpr int NBUF = PIPE ? 3 : 2;
     static_assert(GR % RPB == 0, "rows per barrier must divide the group");
@@ -166,6 +170,11 @@ __global__ void __launch_bounds__(TO + 32, AB_THT_MINB) k_threshold_tma(const __
     const uint32_t s_wr = s_base + 4u * ci, s_rd = s_base + 4u * (ci - R4);
     const int nib_shift = 4 * (t & 3);
     uint32_t boff = 0;
+    // SHFL: who publishes its sums to shared memory (the lanes at warp edges and the halo threads) and who reads a
+    // neighbour's from there (the others get them by shuffle)
+    const int lane_id = t & 31;
+    const bool pub = lane_id == 0 || lane_id == 31 || !is_out || t == TO - 1;
+    const bool need_l = lane_id == 0, need_r = lane_id == 31 || t == TO - 1;
 
     uint32_t ring[K][4];
     uint32_t V0 = 0u, V1 = 0u, V2 = 0u, V3 = 0u;
@@ -197,7 +206,21 @@ __global__ void __launch_bounds__(TO + 32, AB_THT_MINB) k_threshold_tma(const __
     // horizontal window sums, comparison and stores of one output row whose column sums sit at shared offset `rd`
     auto emit_row = [&](uint32_t rd, const uint32_t* c, bool row_ok, const uint32_t* own) {
         uint32_t w[NV];
-        if (OWN) {  // the middle four entries are this thread's own sums
+        if (SHFL) {
+            w[4] = own[0], w[5] = own[1], w[6] = own[2], w[7] = own[3];
+            w[0] = 0u;
+            w[11] = 0u;
+#pragma unroll
+            for (int q = 1; q < 4; q++) w[q] = __shfl_up_sync(out_mask, own[q], 1);        // left neighbour's sums 1..3
+#pragma unroll
+            for (int q = 0; q < 3; q++) w[8 + q] = __shfl_down_sync(out_mask, own[q], 1);  // right neighbour's sums 0..2
+            if (R == 4) {
+                w[0] = __shfl_up_sync(out_mask, own[0], 1);
+                w[11] = __shfl_down_sync(out_mask, own[3], 1);
+            }
+            if (need_l) lds128(rd, w[0], w[1], w[2], w[3]);
+            if (need_r) lds128(rd + 32u, w[8], w[9], w[10], w[11]);
+        } else if (OWN) {  // the middle four entries are this thread's own sums
             lds128(rd, w[0], w[1], w[2], w[3]);
             w[4] = own[0], w[5] = own[1], w[6] = own[2], w[7] = own[3];
             lds128(rd + 32u, w[8], w[9], w[10], w[11]);
@@ -244,7 +267,7 @@ __global__ void __launch_bounds__(TO + 32, AB_THT_MINB) k_threshold_tma(const __
 #pragma unroll
             for (int q = 0; q < RPB; q++) {
                 accumulate(gbase + (uint32_t)((jj + q) * ROWP), ring[(2 * R + jj + q) % K], false);
-                sts128(s_wr + boff + q * BUF_BYTES, V0, V1, V2, V3);
+                if (!SHFL || pub) sts128(s_wr + boff + q * BUF_BYTES, V0, V1, V2, V3);
                 if (OWN && q == 0) own[0] = V0, own[1] = V1, own[2] = V2, own[3] = V3;
             }
             __syncthreads();
