@@ -147,44 +147,78 @@ __global__ void k_threshold_fixed(const uint8_t* grey, size_t grey_row, size_t g
 __device__ __forceinline__ uint32_t bits4_to_bytes(uint32_t n) {  // bit j of the nibble -> byte j = 0x00 / 0xFF
     return (((n & 15u) * 0x00204081u) & 0x01010101u) * 0xFFu;
 }
-__global__ void k_erode(const uint32_t* in, uint32_t* out, uint8_t* thres, size_t bits_words, int W, int H, int wpr, int B) {
-    // two threads per 32-pixel word, each writing the 16 bytes of its half: consecutive lanes write consecutive 16-byte
-    // pieces (one thread per word put two half-filled 32-byte sectors per lane on the wire: 0.63 ms per 64 4K frames, r2i)
-    // a CTA takes whole image rows (one 32-bit division per row, none per pixel group)
-    const int ww = (W + 31) >> 5;
-    const unsigned lines = (unsigned)H * (unsigned)B;  // f * H + y < 2^32
+constexpr int ERODE_CH = 128;             // word columns per shared-memory chunk
+constexpr int ERODE_PITCH = ERODE_CH + 3;  // odd multiple: rows of a tile land in different banks
+__global__ void __launch_bounds__(256) k_erode(const uint32_t* in, uint32_t* out, uint8_t* thres, size_t bits_words, int W, int H, int wpr, int B) {
+    // The packed image is stored in tiles of 32 rows x one word column (one 128-byte line, ab_trace.cuh), so a row-wise
+    // reader touches one line per word (r2m: 0.62 ms per 64 4K frames).  A CTA therefore takes a strip of one tile row:
+    // (1) its tiles go to shared memory line by line (lane = row of the tile), with a one-word / one-row apron in which
+    // everything outside the image counts as 255; (2) the 3x3 AND per word, lane = word column; (3) the eroded words go back
+    // tile by tile and the u8 rows go out as consecutive 16-byte pieces.
+    __shared__ uint32_t s_in[34][ERODE_PITCH];
+    __shared__ uint32_t s_out[32][ERODE_PITCH];
+    const int ww = (W + 31) >> 5, ntr = (H + 2 + BIT_TILE - 1) / BIT_TILE;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = blockDim.x >> 5;
     const bool vec = (W & 15) == 0 && (((uintptr_t)thres) & 15) == 0;
-    for (unsigned line = blockIdx.x; line < lines; line += gridDim.x)
-    for (int hw = threadIdx.x; hw < 2 * ww; hw += blockDim.x) {
-        const int w = hw >> 1, half = hw & 1;
-        const int f = (int)(line / (unsigned)H), y = (int)(line - (unsigned)f * H);
+    for (int strip = blockIdx.x; strip < ntr * B; strip += gridDim.x) {
+        const int f = strip / ntr, tr = strip - f * ntr;
         const uint32_t* base = in + (size_t)f * bits_words;
-        const int nvalid = min(32, W - 32 * w);
-        const uint32_t vmask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
-        uint32_t acc = 0xFFFFFFFFu;
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy++) {
-            const int yy = y + dy;
-            if (yy < 0 || yy >= H) continue;  // rows outside the image count as 255
-            const uint32_t* row = base + bit_word_index(wpr, BIT_PAD + w, yy);
-            const uint32_t cur = row[0] | ~vmask;                          // pixels beyond W count as 255
-            const uint32_t prv = (w == 0) ? 0xFFFFFFFFu : row[-BIT_TILE];  // pixels left of 0 count as 255
-            uint32_t nxt = (w == ww - 1) ? 0xFFFFFFFFu : row[BIT_TILE];
-            if (w == ww - 2) {
-                const int nv2 = W - 32 * (w + 1);
-                if (nv2 < 32) nxt |= ~((1u << nv2) - 1u);
+        uint32_t* obase = out + (size_t)f * bits_words;
+        for (int c0 = 0; c0 < ww; c0 += ERODE_CH) {
+            const int nc = min(ERODE_CH, ww - c0);
+            // (1) columns c0-1 .. c0+nc of padded rows 32 tr - 1 .. 32 tr + 32
+            for (int cc = warp; cc < nc + 2; cc += nwarp) {
+                const int c = c0 - 1 + cc;
+                const bool col_ok = c >= 0 && c < ww;
+                const uint32_t colmask = col_ok ? (c == ww - 1 && (W & 31) ? ((1u << (W & 31)) - 1u) : 0xFFFFFFFFu) : 0u;
+                {   // the tile itself: lane = row in tile, image row y = 32 tr + lane - 1
+                    const int y = 32 * tr + lane - 1;
+                    uint32_t v = 0xFFFFFFFFu;
+                    if (col_ok && y >= 0 && y < H) v = base[((size_t)tr * wpr + BIT_PAD + c) * BIT_TILE + lane] | ~colmask;
+                    s_in[lane + 1][cc] = v;
+                }
+                if (lane < 2) {  // the rows above and below the tile
+                    const int y = lane == 0 ? 32 * tr - 2 : 32 * tr + 31;
+                    uint32_t v = 0xFFFFFFFFu;
+                    if (col_ok && y >= 0 && y < H) v = base[bit_word_index(wpr, BIT_PAD + c, y)] | ~colmask;
+                    s_in[lane == 0 ? 0 : 33][cc] = v;
+                }
             }
-            acc &= cur & ((cur << 1) | (prv >> 31)) & ((cur >> 1) | (nxt << 31));
-        }
-        acc &= vmask;
-        if (half == 0) out[(size_t)f * bits_words + bit_word_index(wpr, BIT_PAD + w, y)] = acc;
-        uint8_t* orow = thres + ((size_t)f * H + y) * W + 32 * w + 16 * half;
-        const uint32_t h16 = acc >> (16 * half);
-        const int nv = nvalid - 16 * half;  // valid pixels of this half
-        if (vec && nv >= 16) {
-            *reinterpret_cast<uint4*>(orow) = make_uint4(bits4_to_bytes(h16), bits4_to_bytes(h16 >> 4), bits4_to_bytes(h16 >> 8), bits4_to_bytes(h16 >> 12));
-        } else {
-            for (int j = 0; j < nv && j < 16; j++) orow[j] = (h16 >> j) & 1u ? 255 : 0;
+            __syncthreads();
+            // (2) eroded word of (row r, column c0 + cc): lane = column
+            for (int i = t; i < 32 * nc; i += blockDim.x) {
+                const int r = i / nc, cc = i - r * nc;
+                uint32_t acc = 0xFFFFFFFFu;
+#pragma unroll
+                for (int dy = 0; dy < 3; dy++) {
+                    const uint32_t prv = s_in[r + dy][cc], cur = s_in[r + dy][cc + 1], nxt = s_in[r + dy][cc + 2];
+                    acc &= cur & ((cur << 1) | (prv >> 31)) & ((cur >> 1) | (nxt << 31));
+                }
+                if (c0 + cc == ww - 1 && (W & 31)) acc &= (1u << (W & 31)) - 1u;
+                s_out[r][cc] = acc;
+            }
+            __syncthreads();
+            // (3a) packed image, tile by tile (rows outside the image stay zero: the frame of the padded buffer)
+            for (int cc = warp; cc < nc; cc += nwarp) {
+                const int y = 32 * tr + lane - 1;
+                if (y >= 0 && y < H) obase[((size_t)tr * wpr + BIT_PAD + c0 + cc) * BIT_TILE + lane] = s_out[lane][cc];
+            }
+            // (3b) u8 image: 16 bytes per thread, consecutive threads consecutive pieces of a row
+            for (int i = t; i < 32 * 2 * nc; i += blockDim.x) {
+                const int r = i / (2 * nc), hw = i - r * (2 * nc), cc = hw >> 1, half = hw & 1;
+                const int y = 32 * tr + r - 1;
+                if (y < 0 || y >= H) continue;
+                const int x0 = 32 * (c0 + cc) + 16 * half, nv = min(16, W - x0);
+                if (nv <= 0) continue;
+                const uint32_t h16 = s_out[r][cc] >> (16 * half);
+                uint8_t* orow = thres + ((size_t)f * H + y) * W + x0;
+                if (vec && nv == 16) {
+                    *reinterpret_cast<uint4*>(orow) = make_uint4(bits4_to_bytes(h16), bits4_to_bytes(h16 >> 4), bits4_to_bytes(h16 >> 8), bits4_to_bytes(h16 >> 12));
+                } else {
+                    for (int j = 0; j < nv; j++) orow[j] = (h16 >> j) & 1u ? 255 : 0;
+                }
+            }
+            __syncthreads();
         }
     }
 }

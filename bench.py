@@ -411,19 +411,31 @@ class Workload:
         return {"checked_frames": len(idx), "ids_exact": bool(ok), "corners_within_px": 0.01, "poses_within_1e-4": "%d/%d" % (pose_ok, poses)}, counts
 
     def run_steps(self, n, flush=False):
-        """n steps with two batches in flight inside the ONE context: batch i+1 is enqueued before batch i is fetched."""
-        det, total, pending = self.det, 0, 0
+        """n steps with two batches in flight inside the ONE context: batch i+1 is enqueued before batch i is fetched.  The
+        host side of a step is two C-ABI calls on preallocated buffers (no per-step allocation: a slow host thread would
+        show up as idle gaps on the device)."""
+        from aruco_b200._lib import ab_marker
+        det, lib, total, pending = self.det, self.det._lib, 0, 0
+        if getattr(self, "_out", None) is None:
+            self._out = (ab_marker * (self.B * self.cap))()
+            self._cnt = (C.c_int32 * self.B)()
+            self._Kf = np.ascontiguousarray(np.asarray(self.K, np.float32).reshape(9))
+            self._Df = np.ascontiguousarray(np.asarray(self.D, np.float32).reshape(-1)[:5])
+        Kp, Dp = self._Kf.ctypes.data_as(C.c_void_p), self._Df.ctypes.data_as(C.c_void_p)
+        ptr = C.c_void_p(self.frames.data_ptr())
         for _ in range(n):
             if pending == 2:
-                total += sum(det.fetch(self.B, self.cap, raw=True)[1])
+                det._check(lib.ab_fetch_results(det._h, self._out, self.cap, self._cnt))
+                total += sum(self._cnt)
                 pending -= 1
             if flush and self.flush is not None:
                 with self.torch.cuda.stream(self.stream):
                     self.flush.fill_(1)
-            det.enqueue_device(self.frames.data_ptr(), self.W, self.H, self.B, self.K, self.D, self.size)
+            det._check(lib.ab_enqueue_batch_device(det._h, ptr, self.W, self.H, self.W, self.W * self.H, self.B, Kp, Dp, self.size))
             pending += 1
         while pending:
-            total += sum(det.fetch(self.B, self.cap, raw=True)[1])
+            det._check(lib.ab_fetch_results(det._h, self._out, self.cap, self._cnt))
+            total += sum(self._cnt)
             pending -= 1
         return total
 
