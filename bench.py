@@ -494,19 +494,29 @@ class Workload:
         out = (ab_marker * (B * cap))()
         cnts = (C.c_int32 * B)()
         Kf, Df = np.ascontiguousarray(self.K.reshape(9)), np.ascontiguousarray(self.D)
-        bd = None
+        board_call = None
         if self.board is not None:
-            from aruco_b200.board import BoardDetector
-            bd = BoardDetector(detector=det)
+            # BoardDetector::detect (boarddetector.cpp:90-204) through the C ABI on the markers just found: ab_detect_board takes
+            # the ab_marker array as ab_detect_batch wrote it (the Python mirror's per-marker marshalling is not timed)
+            from aruco_b200._lib import ab_board, ab_board_config
+            ids = np.ascontiguousarray(np.array(self.board.ids, np.int32))
+            pts = np.ascontiguousarray(self.board.objPoints.astype(np.float32).reshape(-1))
+            cfgb = ab_board_config(len(ids), self.board.mInfoType, ids.ctypes.data, pts.ctypes.data)
+            outm, resb = (ab_marker * cap)(), ab_board()
+
+            def board_call():
+                for f in range(B):
+                    frame_markers = (ab_marker * cap).from_buffer(out, f * cap * C.sizeof(ab_marker))
+                    det._check(det._lib.ab_detect_board(det._h, frame_markers, cnts[f], C.byref(cfgb), Kf.ctypes.data_as(C.c_void_p),
+                                                        Df.ctypes.data_as(C.c_void_p), float(self.size), -1.0, 0, outm, C.byref(resb)))
+                    assert resb.has_pose and resb.prob > 0.5
 
         def one():
             rc = det._lib.ab_detect_batch(det._h, C.c_void_p(host.data_ptr()), W, H, W, W * H, B, Kf.ctypes.data_as(C.c_void_p),
                                           Df.ctypes.data_as(C.c_void_p), self.size, out, cap, cnts)
             det._check(rc)
-            if bd is not None:  # BoardDetector::detect per frame on the markers just found (boarddetector.cpp:90-204)
-                for ms in det._markers(out, list(cnts), cap):
-                    prob, board = bd.detect(ms, self.board, self.K, self.D, self.size)
-                    assert board.Rvec is not None and prob > 0.5
+            if board_call is not None:
+                board_call()
 
         for _ in range(2):
             one()
