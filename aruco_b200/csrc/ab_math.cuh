@@ -904,7 +904,29 @@ AB_HD void jacobi_eigen9(double A[9][9], double V[9][9]) {
     }
 }
 
+// How the loops over the N stacked points run: one thread over all of them (the host check, and any single-thread caller),
+// or the 32 lanes of a warp over every 32nd point with butterfly sums that leave the same value in every lane (k_board_pose:
+// 96 points of a 24-marker board took 1.4 ms per solve in one thread).  Everything between the loops -- eigen decomposition,
+// Cholesky, the CvLevMarq control flow -- runs redundantly and identically in all lanes.
+struct PnpSerial {
+    AB_HD static int first() { return 0; }
+    AB_HD static int step() { return 1; }
+    AB_HD static double sum(double v) { return v; }
+};
+#if defined(__CUDACC__)
+struct PnpWarp {
+    __device__ static int first() { return (int)(threadIdx.x & 31u); }
+    __device__ static int step() { return 32; }
+    __device__ static double sum(double v) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        return v;
+    }
+};
+#endif
+
 // residual (and J^T J, J^T e) of all N points for pose p; returns |e|^2
+template <class PAR>
 AB_HD double pnp_accumulate(const Camera& cam, const double* p, const float* obj, const float* img, int N, bool with_jac,
                             double JtJ[6][6], double* JtErr) {
     double R[9], dR[3][9];
@@ -918,7 +940,7 @@ AB_HD double pnp_accumulate(const Camera& cam, const double* p, const float* obj
         rodrigues_to_mat(p, R);
     }
     double e2 = 0;
-    for (int n = 0; n < N; n++) {
+    for (int n = PAR::first(); n < N; n += PAR::step()) {
         double X = obj[3 * n], Y = obj[3 * n + 1], Z = obj[3 * n + 2];
         double x = R[0] * X + R[1] * Y + R[2] * Z + p[3];
         double y = R[3] * X + R[4] * Y + R[5] * Z + p[4];
@@ -953,43 +975,59 @@ AB_HD double pnp_accumulate(const Camera& cam, const double* p, const float* obj
         }
         for (int i = 0; i < 6; i++) {
             JtErr[i] += Ju[i] * eu + Jv[i] * ev;
-            for (int j = 0; j < 6; j++) JtJ[i][j] += Ju[i] * Ju[j] + Jv[i] * Jv[j];
+            for (int j = i; j < 6; j++) JtJ[i][j] += Ju[i] * Ju[j] + Jv[i] * Jv[j];
         }
     }
-    return e2;
+    if (with_jac) {
+        for (int i = 0; i < 6; i++) {
+            JtErr[i] = PAR::sum(JtErr[i]);
+            for (int j = i; j < 6; j++) {
+                JtJ[i][j] = PAR::sum(JtJ[i][j]);
+                JtJ[j][i] = JtJ[i][j];
+            }
+        }
+    }
+    return PAR::sum(e2);
 }
 
 // obj: N x 3 (a z = const plane), img: N x 2 pixels.  Returns false for degenerate input.
-AB_HD bool solve_pnp_planar(const Camera& cam, const float* obj, const float* img, int N, double* rvec, double* tvec) {
+template <class PAR>
+AB_HD bool solve_pnp_planar_t(const Camera& cam, const float* obj, const float* img, int N, double* rvec, double* tvec) {
     if (N < 4) return false;
     // object centroid; the board must lie in a z = const plane (every reference board configuration does)
     double Mc[3] = {0, 0, 0};
-    for (int n = 0; n < N; n++)
+    for (int n = PAR::first(); n < N; n += PAR::step())
         for (int c = 0; c < 3; c++) Mc[c] += obj[3 * n + c];
-    for (int c = 0; c < 3; c++) Mc[c] /= N;
+    for (int c = 0; c < 3; c++) Mc[c] = PAR::sum(Mc[c]) / N;
     double spread = 0, zdev = 0;
-    for (int n = 0; n < N; n++) {
+    for (int n = PAR::first(); n < N; n += PAR::step()) {
         spread += fabs(obj[3 * n] - Mc[0]) + fabs(obj[3 * n + 1] - Mc[1]);
         zdev += fabs(obj[3 * n + 2] - Mc[2]);
     }
+    spread = PAR::sum(spread);
+    zdev = PAR::sum(zdev);
     if (!(spread > 0) || zdev > 1e-6 * spread) return false;
     // normalised DLT (cv::findHomography, method 0): object (X,Y) -> normalised image (x,y)
     double cM[2] = {Mc[0], Mc[1]}, cm[2] = {0, 0}, sM[2] = {0, 0}, sm[2] = {0, 0};
-    for (int n = 0; n < N; n++) {
+    for (int n = PAR::first(); n < N; n += PAR::step()) {
         double xn, yn;
         undistort_point_norm(cam, img[2 * n], img[2 * n + 1], &xn, &yn);
         cm[0] += xn;
         cm[1] += yn;
     }
-    cm[0] /= N;
-    cm[1] /= N;
-    for (int n = 0; n < N; n++) {
+    cm[0] = PAR::sum(cm[0]) / N;
+    cm[1] = PAR::sum(cm[1]) / N;
+    for (int n = PAR::first(); n < N; n += PAR::step()) {
         double xn, yn;
         undistort_point_norm(cam, img[2 * n], img[2 * n + 1], &xn, &yn);
         sm[0] += fabs(xn - cm[0]);
         sm[1] += fabs(yn - cm[1]);
         sM[0] += fabs(obj[3 * n] - cM[0]);
         sM[1] += fabs(obj[3 * n + 1] - cM[1]);
+    }
+    for (int c = 0; c < 2; c++) {
+        sm[c] = PAR::sum(sm[c]);
+        sM[c] = PAR::sum(sM[c]);
     }
     if (fabs(sM[0]) < DBL_EPSILON || fabs(sM[1]) < DBL_EPSILON || fabs(sm[0]) < DBL_EPSILON || fabs(sm[1]) < DBL_EPSILON) return false;
     sm[0] = N / sm[0];
@@ -999,7 +1037,7 @@ AB_HD bool solve_pnp_planar(const Camera& cam, const float* obj, const float* im
     double LtL[9][9], V[9][9];
     for (int i = 0; i < 9; i++)
         for (int j = 0; j < 9; j++) LtL[i][j] = 0;
-    for (int n = 0; n < N; n++) {
+    for (int n = PAR::first(); n < N; n += PAR::step()) {
         double xn, yn;
         undistort_point_norm(cam, img[2 * n], img[2 * n + 1], &xn, &yn);
         double x = (xn - cm[0]) * sm[0], y = (yn - cm[1]) * sm[1];
@@ -1008,6 +1046,8 @@ AB_HD bool solve_pnp_planar(const Camera& cam, const float* obj, const float* im
         for (int j = 0; j < 9; j++)
             for (int k = j; k < 9; k++) LtL[j][k] += Lx[j] * Lx[k] + Ly[j] * Ly[k];
     }
+    for (int j = 0; j < 9; j++)
+        for (int k = j; k < 9; k++) LtL[j][k] = PAR::sum(LtL[j][k]);
     for (int j = 0; j < 9; j++)
         for (int k = 0; k < j; k++) LtL[j][k] = LtL[k][j];
     jacobi_eigen9(LtL, V);
@@ -1070,7 +1110,7 @@ AB_HD bool solve_pnp_planar(const Camera& cam, const float* obj, const float* im
     // CvLevMarq schedule (see solve_pnp_marker)
     double JtJ[6][6], JtErr[6], prev[6];
     int lambdaLg10 = -3, iters = 0;
-    double prevErrNorm = sqrt(pnp_accumulate(cam, p, obj, img, N, true, JtJ, JtErr));
+    double prevErrNorm = sqrt(pnp_accumulate<PAR>(cam, p, obj, img, N, true, JtJ, JtErr));
     for (;;) {
         for (int i = 0; i < 6; i++) prev[i] = p[i];
         double errNorm = 0;
@@ -1091,7 +1131,7 @@ AB_HD bool solve_pnp_planar(const Camera& cam, const float* obj, const float* im
                     for (int i = 0; i < 6; i++) d[i] = 0;
             }
             for (int i = 0; i < 6; i++) p[i] = prev[i] - d[i];
-            errNorm = sqrt(pnp_accumulate(cam, p, obj, img, N, false, nullptr, nullptr));
+            errNorm = sqrt(pnp_accumulate<PAR>(cam, p, obj, img, N, false, nullptr, nullptr));
             if (errNorm > prevErrNorm && ++lambdaLg10 <= 16) continue;
             break;
         }
@@ -1103,13 +1143,16 @@ AB_HD bool solve_pnp_planar(const Camera& cam, const float* obj, const float* im
         }
         if (++iters >= 20 || sqrt(dn) / sqrt(pn) < FLT_EPSILON) break;
         prevErrNorm = errNorm;
-        pnp_accumulate(cam, p, obj, img, N, true, JtJ, JtErr);
+        pnp_accumulate<PAR>(cam, p, obj, img, N, true, JtJ, JtErr);
     }
     for (int i = 0; i < 3; i++) {
         rvec[i] = p[i];
         tvec[i] = p[3 + i];
     }
     return true;
+}
+AB_HD bool solve_pnp_planar(const Camera& cam, const float* obj, const float* img, int N, double* rvec, double* tvec) {
+    return solve_pnp_planar_t<PnpSerial>(cam, obj, img, N, rvec, tvec);
 }
 
 }  // namespace ab

@@ -140,19 +140,20 @@ __global__ void k_extrinsics(ab_marker* m, int n, Camera cam, float size, int se
     m[i].ssize = size;
 }
 
-// BoardDetector::detect pose part (src/boarddetector.cpp:157-199): one thread, N stacked corners.
+// BoardDetector::detect pose part (src/boarddetector.cpp:157-199): ONE WARP over the N stacked corners (the point loops run
+// lane-strided with butterfly sums, see PnpWarp; everything else is computed identically by all lanes).
 // out[0..2] = rvec, out[3..5] = tvec, out[6] = ok, out[7] = points used by the final solve
-__global__ void k_board_pose(const float* obj, const float* img, int N, Camera cam, float repj_thres, int set_y_perp,
-                             float* obj2, float* img2, double* out) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+__global__ void __launch_bounds__(32) k_board_pose(const float* obj, const float* img, int N, Camera cam, float repj_thres, int set_y_perp,
+                                                   float* obj2, float* img2, double* out) {
+    const int lane = threadIdx.x;
     double r[3] = {0, 0, 0}, t[3] = {0, 0, 0};
-    bool ok = solve_pnp_planar(cam, obj, img, N, r, t);
+    bool ok = solve_pnp_planar_t<PnpWarp>(cam, obj, img, N, r, t);
     int used = N;
     if (ok && repj_thres > 0) {
         double R[9];
         rodrigues_to_mat(r, R);
         int m = 0;
-        for (int n = 0; n < N; n++) {
+        for (int n = 0; n < N; n++) {  // order-preserving compaction of the inliers: every lane counts, lane 0 writes
             double X = obj[3 * n], Y = obj[3 * n + 1], Z = obj[3 * n + 2];
             double x = R[0] * X + R[1] * Y + R[2] * Z + t[0], y = R[3] * X + R[4] * Y + R[5] * Z + t[1], z = R[6] * X + R[7] * Y + R[8] * Z + t[2];
             z = z ? 1. / z : 1.;
@@ -161,22 +162,27 @@ __global__ void k_board_pose(const float* obj, const float* img, int N, Camera c
             float du = (float)u - img[2 * n], dv = (float)v - img[2 * n + 1];  // projectPoints writes Point2f
             float err = (float)sqrt((double)du * du + (double)dv * dv);
             if (err < repj_thres) {
-                for (int c = 0; c < 3; c++) obj2[3 * m + c] = obj[3 * n + c];
-                img2[2 * m] = img[2 * n];
-                img2[2 * m + 1] = img[2 * n + 1];
+                if (lane == 0) {
+                    for (int c = 0; c < 3; c++) obj2[3 * m + c] = obj[3 * n + c];
+                    img2[2 * m] = img[2 * n];
+                    img2[2 * m + 1] = img[2 * n + 1];
+                }
                 m++;
             }
         }
+        __syncwarp();
         used = m;
-        ok = solve_pnp_planar(cam, obj2, img2, m, r, t);
+        ok = solve_pnp_planar_t<PnpWarp>(cam, obj2, img2, m, r, t);
     }
     if (ok && set_y_perp) rotate_x_axis(r);
-    for (int i = 0; i < 3; i++) {
-        out[i] = r[i];
-        out[3 + i] = t[i];
+    if (lane == 0) {
+        for (int i = 0; i < 3; i++) {
+            out[i] = r[i];
+            out[3 + i] = t[i];
+        }
+        out[6] = ok ? 1. : 0.;
+        out[7] = (double)used;
     }
-    out[6] = ok ? 1. : 0.;
-    out[7] = (double)used;
 }
 
 }  // namespace ab
