@@ -324,7 +324,8 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "mpix_per_s": fps * px / 1e6,
-            "config": config_dict(cfg, B, {"reference_sample": "first %d frames of the batch per step (%s)" % (sample, "generated on the GPU: identical to the GPU arm's" if on_gpu else "no GPU: CPU generator, other noise realisations")}),
+            "config": config_dict(cfg, B),  # the same dict as the GPU arm's: same workload, same frame generator and seeds
+            "reference_sample": "first %d frames of the batch per step (%s)" % (sample, "generated on the GPU: identical to the GPU arm's" if on_gpu else "no GPU: CPU generator, other noise realisations"),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": "%d frames/step x %d steps, oracle/aruco_oracle.cpp OpenMP frame-parallel (reference C++ "
                                        "unbuildable: no OpenCV C++)" % (sample, args.steps)},
@@ -752,8 +753,9 @@ def main():
     line = {"metric": METRIC.get(args.config, "frames_per_s_" + args.config), "value": res["fps"], "unit": "frames/s", "n_gpus": world,
             "steps": res["steps"], "warmup": args.warmup, "ms_per_step": res["ms_total"] / res["steps"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "mpix_per_s": res["fps"] * W * H / 1e6,
-            "config": config_dict(CONFIGS[args.config], B, {"pipelining": "2 batches in flight per GPU inside ONE library context "
-                                                            "(ab_enqueue_batch_device twice before ab_fetch_results); every step enqueues one batch and fetches its markers"}),
+            "config": config_dict(CONFIGS[args.config], B),
+            "pipelining": "2 batches in flight per GPU inside ONE library context (ab_enqueue_batch_device twice before "
+                          "ab_fetch_results); every step enqueues one batch and fetches its markers",
             "markers_per_frame": res["markers_per_frame"], "parity": res["parity"], "clocks": res["clocks"], "e2e": res["e2e"],
             "per_rank_ms": res["per_rank_ms"], "host": host_info,
             "gpu_launches": n_launch * res["steps"], "roofline": roofline, "cpu_baseline": cpu, "other_configs": others,
