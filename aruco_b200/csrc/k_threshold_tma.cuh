@@ -221,9 +221,23 @@ __global__ void __launch_bounds__(TO + 32, AB_THT_MINB) k_threshold_tma(const __
             if (need_l) lds128(rd, w[0], w[1], w[2], w[3]);
             if (need_r) lds128(rd + 32u, w[8], w[9], w[10], w[11]);
         } else if (OWN) {  // the middle four entries are this thread's own sums
-            lds128(rd, w[0], w[1], w[2], w[3]);
+#if defined(AB_THT_MINLDS)
+            // variant study: only the six neighbour entries a 7-wide window needs (two 8-byte + two 4-byte loads: 6 wavefronts
+            // per warp instead of 8)
+            if (R <= 3) {
+                w[0] = 0u;
+                w[11] = 0u;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[1]) : "r"(rd + 4u) : "memory");
+                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w[2]), "=r"(w[3]) : "r"(rd + 8u) : "memory");
+                asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w[8]), "=r"(w[9]) : "r"(rd + 32u) : "memory");
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[10]) : "r"(rd + 40u) : "memory");
+            } else
+#endif
+            {
+                lds128(rd, w[0], w[1], w[2], w[3]);
+                lds128(rd + 32u, w[8], w[9], w[10], w[11]);
+            }
             w[4] = own[0], w[5] = own[1], w[6] = own[2], w[7] = own[3];
-            lds128(rd + 32u, w[8], w[9], w[10], w[11]);
         } else {
 #pragma unroll
             for (int q = 0; q < NV / 4; q++) lds128(rd + 16u * q, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
