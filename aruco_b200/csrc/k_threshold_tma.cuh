@@ -346,6 +346,183 @@ __global__ void __launch_bounds__(TO + 32, AB_THT_MINB) k_threshold_tma(const __
     }
 }
 
+// ---- block sizes 13 .. 21 ---------------------------------------------------------------------------------------
+// The window sums of K >= 13 do not fit the 16-bit lanes (K^2 * 255 >= 2^15) and a register ring of K packed rows per
+// column pair does not fit the register file, so the round-1 fallback k_threshold_fast<K> spent 27 instructions per pixel
+// (it was 40 % of config C5, ADPT 21/7).  Same TMA staging as above with three changes:
+//   * no register ring: the staged tile keeps the last K + 31 source rows, and the row that leaves the vertical window
+//     (and the centre row of the mean test) is read from it again and unpacked;
+//   * the vertical sums stay lane-paired 16-bit (K * 255 < 2^13); the horizontal window is added in packed chunks that
+//     cannot overflow (floor(65535 / (255 K)) terms) and continued in two 32-bit accumulators per pixel pair;
+//   * the mean test is a 32-bit comparison per pixel: S - cst - K^2 * src >= 0.
+template <int K, int TO, bool U8>
+__global__ void __launch_bounds__(TO + 32, 1) k_threshold_tma_wide(const __grid_constant__ CUtensorMap src_map, ThrTmaArgs a) {
+    constexpr int R = K / 2, R4 = (R + 3) & ~3, HT = R4 / 4, NV = 4 + 2 * R4, HO = 4 * TO, TW = 2 * HO, CSW = HO + 2 * R4, K2 = K * K;
+    constexpr uint32_t BUF_BYTES = CSW * 4;
+    constexpr int NT = TO + 2 * HT;
+    constexpr int GR = 14;                     // rows per TMA group = one unrolled body
+    constexpr int NS = K + 31;                 // staged rows (ring); row NS is a row of zeros
+    constexpr int ROWB = TW + 32, ROWP = (ROWB + 127) & ~127;
+    constexpr int RH = (AB_THT_RH / GR) * GR;
+    constexpr int CH = 65535 / (255 * K);      // packed terms that cannot overflow a 16-bit lane
+    static_assert(R4 <= 16 && K >= 13, "halo of the staged tile is 16 columns");
+    extern __shared__ __align__(128) uint8_t tht_smem[];
+    constexpr int STAGE_BYTES = (NS + 1) * ROWP;
+    uint8_t* stage = tht_smem;
+    uint32_t* cs = reinterpret_cast<uint32_t*>(tht_smem + STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tht_smem + STAGE_BYTES + 4 * BUF_BYTES);  // 3 group slots + priming
+    const int t = threadIdx.x;
+    const int X0 = blockIdx.x * TW, y0 = blockIdx.y * RH, f = blockIdx.z;
+    const int nout = min(RH, a.H - y0);
+    const int ngroups = (nout + GR - 1) / GR;
+    const uint32_t s_stage = (uint32_t)__cvta_generic_to_shared(stage);
+    const uint32_t s_bars = (uint32_t)__cvta_generic_to_shared(&bars[0]);
+    // stream row s = image row y0 - R + s (clamped: replicated border) lives in ring slot s % NS
+    auto issue_rows = [&](int s0, int n, uint32_t bar) {
+        mbar_expect_tx(bar, (uint32_t)(n * ROWB));
+#pragma unroll 1
+        for (int r = 0; r < n; r++) {
+            const int srow = s0 + r;
+            tma_load_row(s_stage + (uint32_t)((srow % NS) * ROWP), &src_map, (X0 - 16) >> 2, min(max(y0 - R + srow, 0), a.H - 1), f, bar);
+        }
+    };
+    for (int i = 4 * t; i < ROWP; i += 4 * (int)blockDim.x) *reinterpret_cast<uint32_t*>(stage + (size_t)NS * ROWP + i) = 0u;
+    if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) mbar_init(s_bars + 8u * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issue_rows(0, 2 * R, s_bars + 8u * 3);  // priming rows
+        for (int g = 0; g < 2 && g < ngroups; g++) issue_rows(2 * R + g * GR, GR, s_bars + 8u * (uint32_t)g);
+    }
+    __syncthreads();
+    const bool is_out = t < TO;
+    const unsigned out_mask = __ballot_sync(0xFFFFFFFFu, is_out);
+    if (t >= NT) return;
+    const int ci = is_out ? R4 + 4 * t : (t < TO + HT ? 4 * (t - TO) : R4 + HO + 4 * (t - TO - HT));
+    const int ca = X0 - R4 + ci, cb = ca + HO;
+    uint32_t sel[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t ja = ca < 0 ? 0u : (ca >= a.W ? 3u : (uint32_t)j), jb = 4u + (cb >= a.W ? 3u : (uint32_t)j);
+        sel[j] = ja | (ja << 4) | (jb << 8) | (jb << 12);
+    }
+    const uint32_t offA = s_stage + (uint32_t)(min(max(ca, 0), a.W - 4) - X0 + 16), offB = s_stage + (uint32_t)(min(cb, a.W - 4) - X0 + 16);
+    const size_t fo = (size_t)f * a.out_mul + a.out_off;
+    uint8_t* orow = a.thres + fo * a.W * a.H + (size_t)y0 * a.W + ca;
+    uint32_t* brow = a.bits + fo * a.bits_words + bit_word_index(a.wpr, BIT_PAD + (X0 >> 5) + (t >> 3), y0);
+    int btr = (y0 + 1) & 31;
+    const int bjump = a.wpr * BIT_TILE - (BIT_TILE - 1);
+    const bool word_t = is_out && (t & 7) == 0;
+    const int cst = K2 * a.idelta - (K2 - 1) / 2;  // S >= K2*src + cst  <=>  src - mean <= -idelta
+    const uint32_t M = 0x00FF00FFu;
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(cs);
+    const uint32_t s_wr = s_base + 4u * ci, s_rd = s_base + 4u * (ci - R4);
+    const int nib_shift = 4 * (t & 3);
+    uint32_t boff = 0;
+    uint32_t V0 = 0u, V1 = 0u, V2 = 0u, V3 = 0u;
+    // the four packed pixel pairs of this thread in the staged row at byte offset `row`
+    auto unpack = [&](uint32_t row, uint32_t* P) {
+        uint32_t pa, pb;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pa) : "r"(offA + row) : "memory");
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pb) : "r"(offB + row) : "memory");
+#pragma unroll
+        for (int j = 0; j < 4; j++) P[j] = prmt_r(pa, pb, sel[j]) & M;
+    };
+    constexpr uint32_t RING_BYTES = (uint32_t)NS * ROWP;
+    auto adv = [&](uint32_t& off) { off = off + ROWP >= RING_BYTES ? 0u : off + ROWP; };
+    mbar_wait(s_bars + 8u * 3, 0);
+#pragma unroll 4
+    for (int srow = 0; srow < 2 * R; srow++) {
+        uint32_t P[4];
+        unpack((uint32_t)(srow * ROWP), P);
+        V0 += P[0], V1 += P[1], V2 += P[2], V3 += P[3];
+    }
+    uint32_t off_new = (uint32_t)(2 * R * ROWP), off_old = RING_BYTES /* the zero row: nothing leaves the window yet */,
+             off_c = (uint32_t)(R * ROWP);
+    auto accumulate = [&]() {
+        uint32_t P[4], Q[4];
+        unpack(off_new, P);
+        unpack(off_old, Q);
+        V0 = V0 + P[0] - Q[0];
+        V1 = V1 + P[1] - Q[1];
+        V2 = V2 + P[2] - Q[2];
+        V3 = V3 + P[3] - Q[3];
+        adv(off_new);
+        adv(off_old);  // from the zero row (offset RING_BYTES) this wraps to slot 0 = stream row 0
+    };
+    auto emit_row = [&](uint32_t rd, bool row_ok, const uint32_t* own) {
+        uint32_t c[4];
+        unpack(off_c, c);
+        adv(off_c);
+        uint32_t w[NV];
+#pragma unroll
+        for (int q = 0; q < R4 / 4; q++) {
+            lds128(rd + 16u * q, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+            lds128(rd + 16u * (R4 / 4 + 1 + q), w[R4 + 4 + 4 * q], w[R4 + 5 + 4 * q], w[R4 + 6 + 4 * q], w[R4 + 7 + 4 * q]);
+        }
+        w[R4] = own[0], w[R4 + 1] = own[1], w[R4 + 2] = own[2], w[R4 + 3] = own[3];
+        // window of pixel 0: packed chunk sums, widened to one 32-bit accumulator per half
+        int32_t Sa = -cst, Sb = -cst;
+#pragma unroll
+        for (int c0 = 0; c0 < K; c0 += CH) {
+            uint32_t g = 0u;
+#pragma unroll
+            for (int d = c0; d < c0 + CH && d < K; d++) g += w[R4 - R + d];
+            Sa += (int32_t)(g & 0xFFFFu);
+            Sb += (int32_t)(g >> 16);
+        }
+        uint32_t nib_a = 0u, nib_b = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (j > 0) {  // slide the window one column
+                const uint32_t wo = w[R4 - R + j - 1], wi = w[R4 + R + j];
+                Sa += (int32_t)(wi & 0xFFFFu) - (int32_t)(wo & 0xFFFFu);
+                Sb += (int32_t)(wi >> 16) - (int32_t)(wo >> 16);
+            }
+            const int32_t Da = Sa - K2 * (int32_t)(c[j] & 0xFFFFu), Db = Sb - K2 * (int32_t)(c[j] >> 16);
+            nib_a |= ((uint32_t)~Da >> 31) << j;  // foreground <=> D >= 0
+            nib_b |= ((uint32_t)~Db >> 31) << j;
+        }
+        if (U8 && row_ok) {
+            *reinterpret_cast<uint32_t*>(orow) = bits4_to_bytes(nib_a);
+            *reinterpret_cast<uint32_t*>(orow + HO) = bits4_to_bytes(nib_b);
+        }
+        uint32_t x = (nib_a | (nib_b << 16)) << nib_shift;
+        x |= __shfl_xor_sync(out_mask, x, 1);
+        x |= __shfl_xor_sync(out_mask, x, 2);
+        const uint32_t y = __shfl_xor_sync(out_mask, x, 4);
+        if (word_t && row_ok) {
+            brow[0] = prmt<0x5410>(x, y);
+            brow[(HO / 32) * BIT_TILE] = prmt<0x7632>(x, y);
+        }
+        if (U8) orow += a.W;
+        brow += btr == 31 ? bjump : 1;
+        btr = (btr + 1) & 31;
+    };
+    int o = 0;
+    for (int g = 0; g < ngroups; g++) {
+        mbar_wait(s_bars + 8u * (uint32_t)(g % 3), (uint32_t)((g / 3) & 1));
+#pragma unroll
+        for (int jj = 0; jj < GR; jj += 2) {
+            accumulate();
+            sts128(s_wr + boff, V0, V1, V2, V3);
+            const uint32_t own_a[4] = {V0, V1, V2, V3};
+            accumulate();
+            sts128(s_wr + boff + BUF_BYTES, V0, V1, V2, V3);
+            __syncthreads();
+            if (is_out) {
+                const uint32_t own_b[4] = {V0, V1, V2, V3};
+                emit_row(s_rd + boff, o < nout, own_a);
+                emit_row(s_rd + boff + BUF_BYTES, o + 1 < nout, own_b);
+            }
+            o += 2;
+            boff = 2 * BUF_BYTES - boff;
+        }
+        // group g+2 overwrites stream rows <= 14 g + 9; the centre rows still being read are >= R + 14 g + 12
+        if (t == 0 && g + 2 < ngroups) issue_rows(2 * R + (g + 2) * GR, GR, s_bars + 8u * (uint32_t)((g + 2) % 3));
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 typedef CUresult (*ab_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -368,6 +545,10 @@ inline int threshold_tma_tile(int W) {
     return 0;
 }
 
+constexpr size_t threshold_tma_wide_smem(int K, int TO) {
+    const int R = K / 2, R4 = (R + 3) & ~3, HO = 4 * TO, TW = 2 * HO, CSW = HO + 2 * R4;
+    return (size_t)(K + 32) * (size_t)((TW + 32 + 127) & ~127) + 4 * (size_t)CSW * 4 + 8 * 4;
+}
 constexpr size_t threshold_tma_smem(int K, int TO) {
     const int R = K / 2, R4 = (R + 3) & ~3, HO = 4 * TO, TW = 2 * HO, CSW = HO + 2 * R4;
     const int RPB = AB_THT_RPB ? AB_THT_RPB : K;
@@ -397,8 +578,9 @@ inline bool launch_threshold_tma(const ThrArgs& a, int B, cudaStream_t st) {
     if (disabled) return false;
     const int K2 = a.k * a.k;
     const long long cst = (long long)K2 * a.idelta - (K2 - 1) / 2;
-    if (a.k < 3 || a.k > 11 || !(a.k & 1) || (a.W & 3)) return false;
-    if (K2 * 255LL + (cst < 0 ? -cst : cst) >= 0x8000) return false;
+    if (a.k < 3 || a.k > 21 || !(a.k & 1) || (a.W & 3)) return false;
+    const bool wide = a.k >= 13 || K2 * 255LL + (cst < 0 ? -cst : cst) >= 0x8000;  // the window sums leave the 16-bit lanes
+    if (wide && a.k < 13) return false;
     if ((((uintptr_t)a.grey) | a.grey_row | a.grey_frame) & 15) return false;  // TMA: 16-byte aligned base and strides
     const int to = threshold_tma_tile(a.W);
     ab_encode_tiled_fn enc = tensor_map_encoder();
@@ -412,8 +594,31 @@ inline bool launch_threshold_tma(const ThrArgs& a, int B, cudaStream_t st) {
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return false;
     ThrTmaArgs ta{a.thres, a.bits, a.bits_words, a.W, a.H, a.wpr, a.idelta, a.out_mul, a.out_off};
-    const int rh = (AB_THT_RH / (2 * a.k)) * (2 * a.k);
+    const int rh = wide ? (AB_THT_RH / 14) * 14 : (AB_THT_RH / (2 * a.k)) * (2 * a.k);
     dim3 grid(a.W / tw, (a.H + rh - 1) / rh, B);
+    if (wide) {
+#define AB_THW_TO(KK, TT)                                                                                                \
+    if (to == TT) {                                                                                                      \
+        const size_t smem = threshold_tma_wide_smem(KK, TT);                                                             \
+        if (a.skip_u8) threshold_tma_launch(k_threshold_tma_wide<KK, TT, false>, grid, TT + 32, smem, st, map, ta);      \
+        else threshold_tma_launch(k_threshold_tma_wide<KK, TT, true>, grid, TT + 32, smem, st, map, ta);                 \
+        return true;                                                                                                     \
+    }
+#define AB_THW_CASE(KK) \
+    case KK:            \
+        AB_THW_TO(KK, 96) AB_THW_TO(KK, 120) AB_THW_TO(KK, 80) AB_THW_TO(KK, 40) return false;
+        switch (a.k) {
+            AB_THW_CASE(13)
+            AB_THW_CASE(15)
+            AB_THW_CASE(17)
+            AB_THW_CASE(19)
+            AB_THW_CASE(21)
+            default:
+                return false;
+        }
+#undef AB_THW_CASE
+#undef AB_THW_TO
+    }
 #define AB_THT_TO(KK, TT)                                                                        \
     if (to == TT) {                                                                              \
         const size_t smem = threshold_tma_smem(KK, TT);                                          \

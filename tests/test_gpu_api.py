@@ -62,14 +62,16 @@ def test_threshold_worker_bit_exact(det, frames, method, p1, p2):
 @pytest.mark.parametrize("W", [320, 512, 640, 768, 960, 1024, 1280, 1536, 1920, 3840])
 def test_tma_threshold_tiles_and_borders_bit_exact(det, W):
     """The TMA-staged kernel over every tile width it dispatches to (8*TO in 768 / 960 / 640 / 512 / 320: one tile, several
-    tiles, box wider than the image), block sizes 3..11, heights that are not a multiple of the row group (a single partial
+    tiles, box wider than the image), block sizes 3..21, heights that are not a multiple of the row group (a single partial
     group, 1 row), noise and hard edges at all four image borders -- binarised image AND the packed copy (through erosion,
     which reads the packed image and writes the u8 image) bit-exact against the oracle."""
     import ctypes as C
     from oracle import native
     lib = native.load()
     rng = np.random.default_rng(W)
-    for H, k, delta in ((1, 7, 7), (13, 3, 2), (126, 5, 7), (127, 7, 7), (300, 9, -3), (253, 11, 7)):
+    for H, k, delta in ((1, 7, 7), (13, 3, 2), (126, 5, 7), (127, 7, 7), (300, 9, -3), (253, 11, 7),
+                        # the wide kernel (K >= 13: staged ring instead of the register ring, 32-bit window sums)
+                        (1, 13, 7), (40, 15, 0), (127, 17, -2), (126, 19, 7), (260, 21, 7), (33, 21, 300)):
         img = rng.integers(0, 256, (H, W), dtype=np.uint8)
         img[:, :2] = 255 * (H & 1)            # hard edges on the left / right / top / bottom borders
         img[:, -3:] = 0
