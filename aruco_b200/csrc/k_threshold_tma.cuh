@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(TO + 32, 1) k_threshold_tma_wide(const __grid_
     constexpr int ROWB = TW + 32, ROWP = (ROWB + 127) & ~127;
     constexpr int RH = (AB_THT_RH / GR) * GR;
     constexpr int CH = 65535 / (255 * K);      // packed terms that cannot overflow a 16-bit lane
-    static_assert(R4 <= 16 && K >= 13, "halo of the staged tile is 16 columns");
+    static_assert(R4 <= 16, "halo of the staged tile is 16 columns");
     extern __shared__ __align__(128) uint8_t tht_smem[];
     constexpr int STAGE_BYTES = (NS + 1) * ROWP;
     uint8_t* stage = tht_smem;
@@ -579,8 +579,12 @@ inline bool launch_threshold_tma(const ThrArgs& a, int B, cudaStream_t st) {
     const int K2 = a.k * a.k;
     const long long cst = (long long)K2 * a.idelta - (K2 - 1) / 2;
     if (a.k < 3 || a.k > 21 || !(a.k & 1) || (a.W & 3)) return false;
+#ifdef AB_THT_FORCE_WIDE7
+    const bool wide = a.k >= 13 || a.k == 7;  // variant study: the ring-less kernel for the default block size
+#else
     const bool wide = a.k >= 13 || K2 * 255LL + (cst < 0 ? -cst : cst) >= 0x8000;  // the window sums leave the 16-bit lanes
     if (wide && a.k < 13) return false;
+#endif
     if ((((uintptr_t)a.grey) | a.grey_row | a.grey_frame) & 15) return false;  // TMA: 16-byte aligned base and strides
     const int to = threshold_tma_tile(a.W);
     ab_encode_tiled_fn enc = tensor_map_encoder();
@@ -608,6 +612,9 @@ inline bool launch_threshold_tma(const ThrArgs& a, int B, cudaStream_t st) {
     case KK:            \
         AB_THW_TO(KK, 96) AB_THW_TO(KK, 120) AB_THW_TO(KK, 80) AB_THW_TO(KK, 40) return false;
         switch (a.k) {
+#ifdef AB_THT_FORCE_WIDE7
+            AB_THW_CASE(7)
+#endif
             AB_THW_CASE(13)
             AB_THW_CASE(15)
             AB_THW_CASE(17)
