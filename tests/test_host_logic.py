@@ -102,3 +102,21 @@ def test_two_rank_sharding_gives_the_unsharded_result(built):
         g, _ = synth.render_frame(640, 480, 6, seed=f, sigma=1.0, marker_px=70)
         ref.append(sorted(m["id"] for m in native.detect(g, Params(), debug=False)["markers"]))
     assert full == ref and sum(len(r) for r in ref) >= 20
+
+
+def test_bench_reference_arm_runs_without_a_gpu(built):
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm) on the single-frame config: one JSON line
+    with the contract's keys, the same metric / config dict the GPU arm would emit, no GPU launches."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "C1", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["gpu_launches"] == 0 and d["higher_is_better"] is True and d["unit"] == "frames/s"
+    assert d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["markers_per_frame"] == 6.0 and d["config"]["workload"].startswith("C1")
