@@ -37,6 +37,9 @@
 #ifndef AB_THT_PREF_TO
 #define AB_THT_PREF_TO 96
 #endif
+#ifndef AB_THW_GR
+#define AB_THW_GR 8  // wide kernel: rows per TMA group (r2q, K = 21: 8 -> 0.56 ms, 10 -> 0.61, 14 -> 0.62 per 64 frames; 43 instead of 54 KB per CTA)
+#endif
 #ifndef AB_THT_SHFL
 #define AB_THT_SHFL 0  // 1: the neighbours' column sums come by warp shuffle; shared memory only carries them across warp edges
 #endif
@@ -350,7 +353,7 @@ __global__ void __launch_bounds__(TO + 32, AB_THT_MINB) k_threshold_tma(const __
 // The window sums of K >= 13 do not fit the 16-bit lanes (K^2 * 255 >= 2^15) and a register ring of K packed rows per
 // column pair does not fit the register file, so the round-1 fallback k_threshold_fast<K> spent 27 instructions per pixel
 // (it was 40 % of config C5, ADPT 21/7).  Same TMA staging as above with three changes:
-//   * no register ring: the staged tile keeps the last K + 31 source rows, and the row that leaves the vertical window
+//   * no register ring: the staged tile keeps the last K + 2 GR + 3 source rows, and the row that leaves the vertical window
 //     (and the centre row of the mean test) is read from it again and unpacked;
 //   * the vertical sums stay lane-paired 16-bit (K * 255 < 2^13); the horizontal window is added in packed chunks that
 //     cannot overflow (floor(65535 / (255 K)) terms) and continued in two 32-bit accumulators per pixel pair;
@@ -360,8 +363,8 @@ __global__ void __launch_bounds__(TO + 32, 1) k_threshold_tma_wide(const __grid_
     constexpr int R = K / 2, R4 = (R + 3) & ~3, HT = R4 / 4, NV = 4 + 2 * R4, HO = 4 * TO, TW = 2 * HO, CSW = HO + 2 * R4, K2 = K * K;
     constexpr uint32_t BUF_BYTES = CSW * 4;
     constexpr int NT = TO + 2 * HT;
-    constexpr int GR = 14;                     // rows per TMA group = one unrolled body
-    constexpr int NS = K + 31;                 // staged rows (ring); row NS is a row of zeros
+    constexpr int GR = AB_THW_GR;              // rows per TMA group = one unrolled body
+    constexpr int NS = K + 2 * GR + 3;         // staged rows (ring); row NS is a row of zeros
     constexpr int ROWB = TW + 32, ROWP = (ROWB + 127) & ~127;
     constexpr int RH = (AB_THT_RH / GR) * GR;
     constexpr int CH = 65535 / (255 * K);      // packed terms that cannot overflow a 16-bit lane
@@ -518,7 +521,7 @@ __global__ void __launch_bounds__(TO + 32, 1) k_threshold_tma_wide(const __grid_
             o += 2;
             boff = 2 * BUF_BYTES - boff;
         }
-        // group g+2 overwrites stream rows <= 14 g + 9; the centre rows still being read are >= R + 14 g + 12
+        // group g+2 overwrites stream rows <= GR g + GR - 5; the centre rows still being read are >= R + GR g + GR - 2
         if (t == 0 && g + 2 < ngroups) issue_rows(2 * R + (g + 2) * GR, GR, s_bars + 8u * (uint32_t)((g + 2) % 3));
     }
 }
@@ -547,7 +550,7 @@ inline int threshold_tma_tile(int W) {
 
 constexpr size_t threshold_tma_wide_smem(int K, int TO) {
     const int R = K / 2, R4 = (R + 3) & ~3, HO = 4 * TO, TW = 2 * HO, CSW = HO + 2 * R4;
-    return (size_t)(K + 32) * (size_t)((TW + 32 + 127) & ~127) + 4 * (size_t)CSW * 4 + 8 * 4;
+    return (size_t)(K + 2 * AB_THW_GR + 4) * (size_t)((TW + 32 + 127) & ~127) + 4 * (size_t)CSW * 4 + 8 * 4;
 }
 constexpr size_t threshold_tma_smem(int K, int TO) {
     const int R = K / 2, R4 = (R + 3) & ~3, HO = 4 * TO, TW = 2 * HO, CSW = HO + 2 * R4;
@@ -598,7 +601,7 @@ inline bool launch_threshold_tma(const ThrArgs& a, int B, cudaStream_t st) {
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return false;
     ThrTmaArgs ta{a.thres, a.bits, a.bits_words, a.W, a.H, a.wpr, a.idelta, a.out_mul, a.out_off};
-    const int rh = wide ? (AB_THT_RH / 14) * 14 : (AB_THT_RH / (2 * a.k)) * (2 * a.k);
+    const int rh = wide ? (AB_THT_RH / AB_THW_GR) * AB_THW_GR : (AB_THT_RH / (2 * a.k)) * (2 * a.k);
     dim3 grid(a.W / tw, (a.H + rh - 1) / rh, B);
     if (wide) {
 #define AB_THW_TO(KK, TT)                                                                                                \
