@@ -877,6 +877,11 @@ static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t f
     // too-near filter removes again (cpp:322-334, :592-627), so one image gives the same result.
     const int n_t = n_thres_images(P);
     if (n * n_t > ctx->maxB) return set_err(ctx, AB_E_STATE, "internal: %d virtual frames > reserved %d", n * n_t, ctx->maxB);
+    {   // k_scan_starts indexes its work items with 32 bits
+        const unsigned long long items = 8ull * (unsigned long long)((ctx->W + 31) >> 5) * (unsigned long long)((ctx->H + 2 + BIT_TILE - 1) / BIT_TILE) *
+                                         (unsigned long long)(n * n_t);
+        if (items >= (1ull << 32)) return set_err(ctx, AB_E_INVALID, "batch of %d frames %dx%d is too large for one launch: split it", n, ctx->W, ctx->H);
+    }
     Batch b;
     fill_batch(ctx, b, dgrey, row, frame, n, K, D, marker_size);
     b.n_t = n_t;

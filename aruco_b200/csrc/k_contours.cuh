@@ -28,12 +28,15 @@ __global__ void __launch_bounds__(256) k_scan_starts(Batch b) {
         uint32_t outer[4] = {0, 0, 0, 0}, hole[4] = {0, 0, 0, 0};
         int wcl = 0, y0 = 0, f = 0, cnt = 0;
         if (i < total) {
-            const int g = (int)(i & 7ull);
-            unsigned long long r = i >> 3;
-            wcl = (int)(r % (unsigned)ww);
-            r /= (unsigned)ww;
-            const int ty = (int)(r % (unsigned)trows);
-            f = (int)(r / (unsigned)trows);
+            // 32-bit index arithmetic (the host checks total < 2^32): four 64-bit divisions per item were ~half of this
+            // kernel's instructions
+            const unsigned i32 = (unsigned)i, row_items = 8u * (unsigned)ww, frame_items = row_items * (unsigned)trows;
+            f = (int)(i32 / frame_items);
+            const unsigned rem = i32 - (unsigned)f * frame_items;
+            const int ty = (int)(rem / row_items);
+            const unsigned r2 = rem - (unsigned)ty * row_items;
+            const int g = (int)(r2 & 7u);
+            wcl = (int)(r2 >> 3);
             y0 = ty * BIT_TILE + 4 * g - 1;  // image row of the first of the 4 rows (padded row - 1)
             const uint32_t* tile = b.bits + (size_t)f * b.bits_words + ((size_t)ty * b.wpr + (wcl + BIT_PAD)) * BIT_TILE;
             const uint4 c4 = *reinterpret_cast<const uint4*>(tile + 4 * g);
