@@ -39,8 +39,8 @@ constexpr int LINES_SIDE_CAP = 512;  // points of a side staged in shared memory
 // cv::undistortPoints when UNDIST, :957-959) in shared memory; the later passes read them from there.
 template <bool UNDIST>
 __device__ __forceinline__ void refine_lines_cta(const uint32_t* pts, int n, bool rev, const float* c, const Camera& cam,
-                                                 float2 (*s_side)[LINES_SIDE_CAP], int* s_ci, float (*s_line)[3], float* refined,
-                                                 unsigned int* err) {
+                                                 float2 (*s_side)[LINES_SIDE_CAP], int* s_ci, float (*s_line)[3], float2 (*s_rot)[LINES_MAX_SWEEPS],
+                                                 float* refined, unsigned int* err) {
     const int t = threadIdx.x, lane = t & 31, l = t >> 5;
     if (t < 4) s_ci[t] = -1;
     __syncthreads();
@@ -120,7 +120,10 @@ __device__ __forceinline__ void refine_lines_cta(const uint32_t* pts, int n, boo
         const bool along_x = mxx - mnx > mxy - mny;  // y = a x + c (:103-115), else x = b y + c (:116-128)
         double W2[2] = {warp_sum_d(along_x ? Sxx : Syy), (double)m2};
         double p = warp_sum_d(along_x ? Sx : Sy);
-        float rc[LINES_MAX_SWEEPS], rs[LINES_MAX_SWEEPS];
+        // the rotations done so far (cos, sin) live in shared memory: replaying them is a loop over `ns` entries (ncu r2s: an
+        // unrolled, predicated replay of all LINES_MAX_SWEEPS slots made this kernel issue bound at 14 k warp-instructions
+        // per marker)
+        float2* rot = s_rot[l];
         float Vt[2][2] = {{1.f, 0.f}, {0.f, 1.f}};
         int ns = 0;
         const int max_iter = max(m2, 30);
@@ -132,12 +135,8 @@ __device__ __forceinline__ void refine_lines_cta(const uint32_t* pts, int n, boo
             }
             float cc, ss;
             jacobi_rotation_f32(W2[0], W2[1], p, &cc, &ss);
-#pragma unroll
-            for (int k = 0; k < LINES_MAX_SWEEPS; k++)
-                if (k == ns) {
-                    rc[k] = cc;
-                    rs[k] = ss;
-                }
+            if (lane == 0) rot[ns] = make_float2(cc, ss);
+            __syncwarp();
             ns++;
 #pragma unroll
             for (int k = 0; k < 2; k++) {
@@ -150,13 +149,13 @@ __device__ __forceinline__ void refine_lines_cta(const uint32_t* pts, int n, boo
                 float x, y;
                 point(i, x, y);
                 float t0 = along_x ? x : y, t1 = 1.f;
-#pragma unroll
-                for (int k = 0; k < LINES_MAX_SWEEPS; k++)
-                    if (k < ns) {
-                        float n0 = rc[k] * t0 + rs[k] * t1, n1 = -rs[k] * t0 + rc[k] * t1;
-                        t0 = n0;
-                        t1 = n1;
-                    }
+#pragma unroll 1
+                for (int k = 0; k < ns; k++) {
+                    const float2 cs2 = rot[k];
+                    float n0 = cs2.x * t0 + cs2.y * t1, n1 = -cs2.y * t0 + cs2.x * t1;
+                    t0 = n0;
+                    t1 = n1;
+                }
                 a += (double)t0 * t0;
                 bb += (double)t1 * t1;
                 pn += (double)t0 * t1;
@@ -173,13 +172,13 @@ __device__ __forceinline__ void refine_lines_cta(const uint32_t* pts, int n, boo
             point(i, x, y);
             float t0 = along_x ? x : y, t1 = 1.f;
             const float rhs = along_x ? y : x;
-#pragma unroll
-            for (int k = 0; k < LINES_MAX_SWEEPS; k++)
-                if (k < ns) {
-                    float n0 = rc[k] * t0 + rs[k] * t1, n1 = -rs[k] * t0 + rc[k] * t1;
-                    t0 = n0;
-                    t1 = n1;
-                }
+#pragma unroll 1
+            for (int k = 0; k < ns; k++) {
+                const float2 cs2 = rot[k];
+                float n0 = cs2.x * t0 + cs2.y * t1, n1 = -cs2.y * t0 + cs2.x * t1;
+                t0 = n0;
+                t1 = n1;
+            }
             ub[0] += (double)((t0 * sc[0]) * rhs);
             ub[1] += (double)((t1 * sc[1]) * rhs);
         }
@@ -216,6 +215,7 @@ constexpr int LINES_CTAS_PER_FRAME = 64;
 template <bool UNDIST>
 __global__ void __launch_bounds__(128) k_refine_lines(Batch b) {
     __shared__ float2 s_side[4][LINES_SIDE_CAP];
+    __shared__ float2 s_rot[4][LINES_MAX_SWEEPS];
     __shared__ int s_ci[4];
     __shared__ float s_line[4][3];
     const int f = blockIdx.y, nc = min((int)b.n_cands[f], b.cap_c);
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(128) k_refine_lines(Batch b) {
         if (cand->id < 0) continue;
         const ContourRec rec = b.contours[cand->contour];
         // the reference reverses the contour of swapped candidates (:622-625)
-        refine_lines_cta<UNDIST>(b.pool + rec.off, (int)rec.n, cand->swapped != 0, cand->c, b.cam, s_side, s_ci, s_line, cand->refined,
+        refine_lines_cta<UNDIST>(b.pool + rec.off, (int)rec.n, cand->swapped != 0, cand->c, b.cam, s_side, s_ci, s_line, s_rot, cand->refined,
                                  &b.cnt->err);
         __syncthreads();  // s_ci / s_line / s_side are reused by the next candidate
     }
@@ -235,9 +235,10 @@ template <bool UNDIST>
 __global__ void __launch_bounds__(128) k_refine_lines_single(const uint32_t* pts, int n, const float* corners, Camera cam, float* out,
                                                              unsigned int* err) {
     __shared__ float2 s_side[4][LINES_SIDE_CAP];
+    __shared__ float2 s_rot[4][LINES_MAX_SWEEPS];
     __shared__ int s_ci[4];
     __shared__ float s_line[4][3];
-    refine_lines_cta<UNDIST>(pts, n, false, corners, cam, s_side, s_ci, s_line, out, err);
+    refine_lines_cta<UNDIST>(pts, n, false, corners, cam, s_side, s_ci, s_line, s_rot, out, err);
 }
 
 // bilinear getRectSubPix sample with replicated border, f32 arithmetic in OpenCV's order
