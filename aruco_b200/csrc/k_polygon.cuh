@@ -45,18 +45,21 @@ __global__ void __launch_bounds__(128) k_polygon(Batch b) {
             p0 = (p0 + rs) % n;
             uint32_t sp = pts[p0];
             int sx = (int)(sp & 0xFFFFu), sy = (int)(sp >> 16);
-            unsigned long long best = 0;  // (dist << 32) | ~j : larger dist wins, then smaller j
+            // per lane: first strict maximum (j ascends, so `>` keeps the smallest j of equal distances); coordinates are
+            // < 2^14, the squared distance fits 32 bits.  The 64-bit key (dist << 32) | ~j is only built for the warp reduction.
+            unsigned bestd = 0u, bestj = 0u;
             for (int j = 1 + lane; j < n; j += 32) {
                 int q = p0 + j;
                 if (q >= n) q -= n;
                 uint32_t pp = pts[q];
                 int dx = (int)(pp & 0xFFFFu) - sx, dy = (int)(pp >> 16) - sy;
-                unsigned long long d = (unsigned long long)(dx * dx + dy * dy);
-                if (d > 0) {
-                    unsigned long long key = (d << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)j);
-                    if (key > best) best = key;
+                const unsigned d = (unsigned)(dx * dx + dy * dy);
+                if (d > bestd) {
+                    bestd = d;
+                    bestj = (unsigned)j;
                 }
             }
+            unsigned long long best = bestd ? ((unsigned long long)bestd << 32) | (unsigned long long)(0xFFFFFFFFu - bestj) : 0ull;
             best = warp_max_u64(best);
             maxd = (long long)(best >> 32);
             if (best) rs = (int)(0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFu));
