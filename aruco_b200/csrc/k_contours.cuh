@@ -119,7 +119,19 @@ __global__ void __launch_bounds__(256) k_scan_starts(Batch b) {
 // (full walker state) and its lane is refilled; k_trace<true> then runs the parked walks to completion in
 // densely populated warps.  Without this, the long walks end up one or two per warp and the kernel spends
 // most of its time issuing instructions for ~9 of 32 lanes (ncu r1e).
-constexpr int TRACE_LONG_T = 48;
+#ifndef AB_TRACE_LONG_T
+#define AB_TRACE_LONG_T 48
+#endif
+#ifndef AB_TRACE_STEPS
+#define AB_TRACE_STEPS 8
+#endif
+#ifndef AB_TRACE_STEPS_LONG
+#define AB_TRACE_STEPS_LONG 8
+#endif
+#ifndef AB_EMIT_STEPS
+#define AB_EMIT_STEPS 16
+#endif
+constexpr int TRACE_LONG_T = AB_TRACE_LONG_T;
 
 // `s` is the start state of a start candidate (table flags e): does its trigger scan before key0?
 // (raster positions fit 32 bits: W, H <= 16384)
@@ -130,7 +142,7 @@ __device__ __forceinline__ bool smaller_trigger(uint32_t e, const WalkState& s, 
 
 template <bool LONG>
 __global__ void __launch_bounds__(128) k_trace(Batch b) {
-    constexpr int STEPS = 8;
+    constexpr int STEPS = LONG ? AB_TRACE_STEPS_LONG : AB_TRACE_STEPS;
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     unsigned long long n_items;
@@ -415,7 +427,7 @@ __global__ void __launch_bounds__(128) k_emit(Batch b) {
 // ends.  The longest dependent chain of the stage drops from n/2 to about n/8 neighbourhood loads (the walkers are
 // latency bound: one L2/DRAM round trip per step).  Items are ordered so that a warp holds one kind of walker.
 __global__ void __launch_bounds__(128) k_emit_long(Batch b) {
-    constexpr int STEPS = 16;
+    constexpr int STEPS = AB_EMIT_STEPS;
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     unsigned int nrec = b.cnt->n_emit_long;
