@@ -37,6 +37,9 @@
 #ifndef AB_THT_PREF_TO
 #define AB_THT_PREF_TO 96
 #endif
+#ifndef AB_THT_PRIME_IN_SLOT
+#define AB_THT_PRIME_IN_SLOT 1  // 1: the 2R priming rows borrow the last group slot (its group is issued after they are consumed)
+#endif
 #ifndef AB_THW_GR
 #define AB_THW_GR 8  // wide kernel: rows per TMA group (r2q, K = 21: 8 -> 0.56 ms, 10 -> 0.61, 14 -> 0.62 per 64 frames; 43 instead of 54 KB per CTA)
 #endif
@@ -111,7 +114,9 @@ __global__ void __launch_bounds__(TO + 32, AB_THT_MINB) k_threshold_tma(const __
     static_assert(ROWB % 16 == 0 && R4 <= 8, "TMA box: inner extent must be a multiple of 16 bytes");
     // dynamic shared memory: staged rows (groups, then the 2R priming rows) | 4 column-sum rows (two buffers of two) | barriers
     extern __shared__ __align__(128) uint8_t tht_smem[];
-    constexpr int STAGE_BYTES = (NG * GR + 2 * R) * ROWP;
+    constexpr bool PSLOT = AB_THT_PRIME_IN_SLOT && NG >= 2 && 2 * R <= GR;
+    constexpr int PRIME_ROW0 = PSLOT ? (NG - 1) * GR : NG * GR;
+    constexpr int STAGE_BYTES = (PSLOT ? NG * GR : NG * GR + 2 * R) * ROWP;
     uint8_t* stage = tht_smem;
     uint32_t* cs = reinterpret_cast<uint32_t*>(tht_smem + STAGE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(tht_smem + STAGE_BYTES + NBUF * RPB * BUF_BYTES);  // NG groups, priming, phases
@@ -139,8 +144,8 @@ __global__ void __launch_bounds__(TO + 32, AB_THT_MINB) k_threshold_tma(const __
         const uint32_t pbar = s_bars + 8u * NG;
         mbar_expect_tx(pbar, 2 * R * ROWB);
         for (int r = 0; r < 2 * R; r++)
-            tma_load_row(s_stage + (uint32_t)((NG * GR + r) * ROWP), &src_map, (X0 - 16) >> 2, min(max(y0 - R + r, 0), a.H - 1), f, pbar);
-        for (int g = 0; g < NG && g < ngroups; g++) issue_group(g);
+            tma_load_row(s_stage + (uint32_t)((PRIME_ROW0 + r) * ROWP), &src_map, (X0 - 16) >> 2, min(max(y0 - R + r, 0), a.H - 1), f, pbar);
+        for (int g = 0; g < (PSLOT ? NG - 1 : NG) && g < ngroups; g++) issue_group(g);
     }
     __syncthreads();  // barrier words initialised before anybody polls them
     const bool is_out = t < TO;
@@ -203,7 +208,11 @@ __global__ void __launch_bounds__(TO + 32, AB_THT_MINB) k_threshold_tma(const __
     };
     mbar_wait(s_bars + 8u * NG, 0);
 #pragma unroll
-    for (int j = 0; j < 2 * R; j++) accumulate(s_stage + (uint32_t)((NG * GR + j) * ROWP), ring[j], true);
+    for (int j = 0; j < 2 * R; j++) accumulate(s_stage + (uint32_t)((PRIME_ROW0 + j) * ROWP), ring[j], true);
+    if (PSLOT) {  // the borrowed slot is free again
+        __syncthreads();
+        if (t == 0 && NG - 1 < ngroups) issue_group(NG - 1);
+    }
 #pragma unroll
     for (int j = 2 * R; j < K; j++) ring[j][0] = ring[j][1] = ring[j][2] = ring[j][3] = 0u;
     // horizontal window sums, comparison and stores of one output row whose column sums sit at shared offset `rd`
@@ -556,7 +565,8 @@ constexpr size_t threshold_tma_smem(int K, int TO) {
     const int R = K / 2, R4 = (R + 3) & ~3, HO = 4 * TO, TW = 2 * HO, CSW = HO + 2 * R4;
     const int RPB = AB_THT_RPB ? AB_THT_RPB : K;
     const int NBUF = (AB_THT_PIPE && RPB == 2 && K >= 7) ? 3 : 2;
-    return (size_t)(AB_THT_NG * 2 * K + 2 * R) * (size_t)((TW + 32 + 127) & ~127) + NBUF * RPB * (size_t)CSW * 4 + 8 * (AB_THT_NG + 2);
+    const bool PSLOT = AB_THT_PRIME_IN_SLOT && AB_THT_NG >= 2;  // 2R <= 2K always
+    return (size_t)(AB_THT_NG * 2 * K + (PSLOT ? 0 : 2 * R)) * (size_t)((TW + 32 + 127) & ~127) + NBUF * RPB * (size_t)CSW * 4 + 8 * (AB_THT_NG + 2);
 }
 template <class KERNEL>
 inline void threshold_tma_launch(KERNEL kern, dim3 grid, int threads, size_t smem, cudaStream_t st, const CUtensorMap& map, const ThrTmaArgs& ta) {
