@@ -18,7 +18,8 @@ enum : unsigned {
 constexpr int MAX_QUADS = 1024;  // hard upper bound of quads per frame handled by the per-frame filter
 constexpr int MAX_CANDS = 1024;   // hard upper bound of candidates per frame
 
-// frame: bit 31 = border type (outer/hole), bit 30 = long contour (points written by k_emit_long, not k_emit)
+// frame: bit 31 = border type (outer/hole), bit 30 = long contour (closed by k_trace<true>, which copied the points it
+// recorded while walking into the pool; k_emit only adds the TRACE_PARK_N steps walked before the walk was parked)
 constexpr uint32_t CONTOUR_LONG = 0x40000000u, CONTOUR_FRAME_MASK = 0x3FFFFFFFu;
 struct ContourRec {
     uint32_t frame;
@@ -34,17 +35,6 @@ struct LongRec {
     uint32_t sxy, fxy, bxy;  // start / forward walker / backward walker pixel (x | y << 16)
     uint32_t dirs;           // fw.b | bw.b << 4 | start.b << 8
     uint32_t nf, ng;
-};
-
-// a long contour closed by k_trace<true>: the walkers' checkpoints cut it into 6 segments with known end states, so
-// k_emit_long writes it with 12 walkers instead of 2 (states S0..S5 at indices 0, a[0..4]; S6 = S0 at index n)
-struct EmitRec {
-    uint32_t frame;   // bit 31 = border type
-    uint32_t off, n;  // slice of the point pool
-    uint32_t a[5];    // segment boundaries: p/2, p, nf, n-q, n-q/2
-    uint32_t xy[6];   // pixels of S0..S5 (x | y << 16)
-    uint32_t dirs;    // back-directions of S0..S5, 3 bits each
-    uint32_t pad;
 };
 
 struct QuadRec {
@@ -78,8 +68,7 @@ struct Counters {
     unsigned int err;
     unsigned int emit_work;
     unsigned int n_long, long_work;
-    unsigned int canny_changed, n_emit_long;
-    unsigned int emit_long_work, pad3;
+    unsigned int canny_changed, pad3;
     unsigned long long n_quads_total, n_cands_total, n_markers_total;
 };
 
@@ -113,7 +102,8 @@ struct Batch {
     LongRec* longq;
     unsigned int cap_long;
     const uint8_t* walk_lut;  // WALK_LUT_FW then WALK_LUT_BW (ab_trace.cuh)
-    EmitRec* emitq;  // long contours (at most one per parked walk: capacity cap_long)
+    uint2* trace_rec;       // k_trace<true>: per-lane record of the pixels visited (forward, backward) since the walk was resumed
+    unsigned int rec_half;  // entries per lane (max_len / 2 + 2)
     QuadRec* quads;  // [B][cap_q]
     int cap_q;
     CandRec* cands;  // [B][cap_c]

@@ -43,7 +43,11 @@ struct ab_context {
     cudaStream_t sub_stream[MAX_SUB] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
     int n_sub_streams = 1;  // measured on B200: no gain from 2-4 sub-batches (full grids leave no room to co-schedule)
-    int grid_trace = 8, grid_long = 8, grid_emit = 4;  // CTAs per SM of the persistent walker grids (r2l sweep: emit 0.57 -> 0.52 ms at 4)
+    int grid_trace = 8, grid_long = 8;  // CTAs per SM of the persistent walker grids
+    uint2* d_trace_rec = nullptr;       // strips of k_trace<true>'s lanes (k_contours.cuh), grown on demand
+    size_t trace_rec_bytes = 0, rec_sub_bytes = 0;
+    unsigned rec_ctas = 0, rec_half = 0;
+    size_t trace_rec_budget = (size_t)6 << 30;  // more lanes than this pays for are not launched
     int last_nsub = 1;
     ab_params params;
     std::string err;
@@ -62,7 +66,6 @@ struct ab_context {
     ContourRec* d_contours = nullptr;
     uint32_t* d_pool = nullptr;
     LongRec* d_longq = nullptr;
-    EmitRec* d_emitq = nullptr;
     uint8_t* d_walk_lut = nullptr;
     unsigned capLongPF = 8192;
     QuadRec* d_quads = nullptr;
@@ -177,7 +180,8 @@ static void free_buffers(ab_context* c) {
     F(c->d_contours);
     F(c->d_pool);
     F(c->d_longq);
-    F(c->d_emitq);
+    F(c->d_trace_rec);
+    c->trace_rec_bytes = 0;
     F(c->d_quads);
     F(c->d_cands);
     F(c->d_canon);
@@ -267,7 +271,7 @@ int ab_create(int device, ab_context** out) {
     if (const char* e = getenv("ARUCO_B200_CAP_LONG")) ctx->capLongPF = (unsigned)std::max(1, atoi(e));
     if (const char* e = getenv("ARUCO_B200_GRID_TRACE")) ctx->grid_trace = std::max(1, atoi(e));
     if (const char* e = getenv("ARUCO_B200_GRID_LONG")) ctx->grid_long = std::max(1, atoi(e));
-    if (const char* e = getenv("ARUCO_B200_GRID_EMIT")) ctx->grid_emit = std::max(1, atoi(e));
+    if (const char* e = getenv("ARUCO_B200_TRACE_REC_MB")) ctx->trace_rec_budget = (size_t)std::max(1, atoi(e)) << 20;
     for (int i = 0; i < 6; i++) cudaEventCreate(&ctx->ev[i]);
     for (int i = 0; i < 12; i++) cudaEventCreate(&ctx->kev[i]);
     for (int i = 0; i < 2; i++) {
@@ -474,7 +478,6 @@ static int reserve_impl(ab_context* ctx, int width, int height, int max_batch) {
     A(&ctx->d_contours, B * ctx->capContoursPF * sizeof(ContourRec));
     A(&ctx->d_pool, B * capP * 4);
     A(&ctx->d_longq, B * ctx->capLongPF * sizeof(LongRec));
-    A(&ctx->d_emitq, B * ctx->capLongPF * sizeof(EmitRec));
     A(&ctx->d_quads, B * capQ * sizeof(QuadRec));
     A(&ctx->d_cands, B * capC * sizeof(CandRec));
     A(&ctx->d_canon, B * capC * (size_t)S_alloc * S_alloc);
@@ -675,7 +678,6 @@ static int fill_batch(ab_context* ctx, Batch& b, const uint8_t* dgrey, size_t ro
     b.cap_contours = ctx->capContoursPF * (unsigned)n;
     b.longq = ctx->d_longq;
     b.cap_long = ctx->capLongPF * (unsigned)n;
-    b.emitq = ctx->d_emitq;
     b.walk_lut = ctx->d_walk_lut;
     b.pool = ctx->d_pool;
     b.cap_pool = (unsigned long long)ctx->capPoolPF * n;
@@ -734,7 +736,6 @@ static Batch sub_view(ab_context* ctx, const Batch& w, int f0, int nf, int s) {
     v.cap_pool = (unsigned long long)ctx->capPoolPF * vt * nf;
     v.longq = w.longq + (size_t)ctx->capLongPF * vt * f0;
     v.cap_long = ctx->capLongPF * (unsigned)(vt * nf);
-    v.emitq = w.emitq + (size_t)ctx->capLongPF * vt * f0;
     v.quads = w.quads + (size_t)f0 * w.cap_q;
     v.cands = w.cands + (size_t)f0 * w.cap_c;
     v.canon = w.canon + (size_t)f0 * w.cap_c * (size_t)(w.S * w.S);
@@ -756,8 +757,39 @@ static void launch_refine_lines(const Batch& b, cudaStream_t st) {
     else k_refine_lines<false><<<grid, 128, 0, st>>>(b);
 }
 
+// k_trace<true>: every lane of the persistent grid owns a strip of max_len / 2 + 2 recorded pixel pairs (30 KB at 4K), so the
+// grid is as large as the parked walks can use, the configured CTAs per SM allow and the strip budget pays for.  Concurrent
+// sub-batches share the grid and the strips evenly.  Called once per batch, before its first launch.
+static int plan_trace_long(ab_context* ctx, int max_len, unsigned cap_long_sub, int nsub) {
+    const size_t half = ((size_t)(std::max(max_len, 0) / 2 + 2) + 1) & ~(size_t)1;  // even: 16-byte aligned strips
+    size_t ctas = (size_t)ctx->sm_count * (size_t)std::max(1, ctx->grid_long / nsub);
+    ctas = std::min(ctas, ((size_t)cap_long_sub + 127) / 128);
+    ctas = std::max<size_t>(1, std::min(ctas, ctx->trace_rec_budget / nsub / (half * 128 * sizeof(uint2))));
+    const size_t sub_bytes = ctas * 128 * half * sizeof(uint2), need = sub_bytes * nsub;
+    if (need > ctx->trace_rec_bytes) {  // grows only when the geometry or the maximum contour size grew
+        if (ctx->d_trace_rec) cudaFree(ctx->d_trace_rec);
+        ctx->d_trace_rec = nullptr;
+        ctx->trace_rec_bytes = 0;
+        cudaError_t e = cudaMalloc(&ctx->d_trace_rec, need);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return set_err(ctx, AB_E_CUDA, "walker strips (%zu MB): %s", need >> 20, cudaGetErrorString(e));
+        }
+        ctx->trace_rec_bytes = need;
+    }
+    ctx->rec_ctas = (unsigned)ctas;
+    ctx->rec_half = (unsigned)half;
+    ctx->rec_sub_bytes = sub_bytes;
+    return AB_OK;
+}
+static void launch_trace_long(ab_context* ctx, Batch& bv, cudaStream_t st, int sub) {
+    bv.trace_rec = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(ctx->d_trace_rec) + ctx->rec_sub_bytes * sub);
+    bv.rec_half = ctx->rec_half;
+    k_trace<true><<<ctx->rec_ctas, 128, 0, st>>>(bv);
+}
+
 // one sub-batch (a view of the batch buffers) on one stream: every stage of the path
-static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
+static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing, int sub = 0) {
     const ab_params& P = ctx->params;
     const int n = b.B, n_t = b.n_t;
     const int sms = ctx->sm_count;
@@ -781,9 +813,8 @@ static int run_sub(ab_context* ctx, Batch b, cudaStream_t st, bool timing) {
     if (timing) cudaEventRecord(ctx->kev[2], st);
     k_trace<false><<<sms * ctx->grid_trace, 128, 0, st>>>(bv);
     if (timing) cudaEventRecord(ctx->kev[3], st);
-    k_trace<true><<<sms * ctx->grid_long, 128, 0, st>>>(bv);
+    launch_trace_long(ctx, bv, st, sub);
     if (timing) cudaEventRecord(ctx->kev[4], st);
-    k_emit_long<<<sms * ctx->grid_emit, 128, 0, st>>>(bv);
     k_emit<<<sms * 8, 128, 0, st>>>(bv);
     if (timing) cudaEventRecord(ctx->kev[5], st);
     k_polygon<<<sms * 8, 128, 0, st>>>(bv);
@@ -901,10 +932,11 @@ static int run_batch(ab_context* ctx, const uint8_t* dgrey, size_t row, size_t f
         CK(cudaEventRecord(ctx->ev_fork, st));
         for (int s = 0; s < nsub; s++) CK(cudaStreamWaitEvent(ctx->sub_stream[s], ctx->ev_fork, 0));
     }
+    if (int rc = plan_trace_long(ctx, b.max_len, ctx->capLongPF * (unsigned)(b.n_t * (n / nsub)), nsub)) return rc;
     for (int s = 0; s < nsub; s++) {
         const int f0 = (int)((long long)s * n / nsub), nf = (int)((long long)(s + 1) * n / nsub) - f0;
         Batch v = sub_view(ctx, b, f0, nf, s);
-        int rc = run_sub(ctx, v, nsub > 1 ? ctx->sub_stream[s] : st, ctx->timing && nsub == 1);
+        int rc = run_sub(ctx, v, nsub > 1 ? ctx->sub_stream[s] : st, ctx->timing && nsub == 1, s);
         if (rc) return rc;
     }
     if (nsub > 1) {
@@ -1345,8 +1377,9 @@ int ab_detect_rectangles(ab_context* ctx, const uint8_t* thres, int width, int h
                                                           b.wpr, 0, 1, 1, 1, 0);
     k_scan_starts<<<ctx->sm_count * 8, 256, 0, st>>>(b);
     k_trace<false><<<ctx->sm_count * 8, 128, 0, st>>>(b);
-    k_trace<true><<<ctx->sm_count * 4, 128, 0, st>>>(b);
-    k_emit_long<<<ctx->sm_count * 8, 128, 0, st>>>(b);
+    rc = plan_trace_long(ctx, b.max_len, b.cap_long, 1);
+    if (rc) return rc;
+    launch_trace_long(ctx, b, st, 0);
     k_emit<<<ctx->sm_count * 8, 128, 0, st>>>(b);
     k_polygon<<<ctx->sm_count * 4, 128, 0, st>>>(b);
     k_frame_filter<<<1, 256, 0, st>>>(b);

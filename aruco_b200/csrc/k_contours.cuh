@@ -2,9 +2,11 @@
 // src/markerdetector.cpp:510-511, and the length filter at :517).  See ab_trace.cuh for the algorithm.
 //   k_scan_starts:  bitwise scan of the tiled packed image for start candidates (one thread per word column x 4 rows)
 //   k_trace<false>: one lane per candidate walks its border cycle in both directions; walks alive after 48 iterations
-//                   are parked.  k_trace<true> finishes the parked walks.  The Suzuki start of every border with
-//                   min_len < n < max_len reserves its slice of the point pool and leaves a contour record.
-//   k_emit_long / k_emit: re-walk the kept contours and write their ordered points (12 / 2 walkers per contour).
+//                   are parked.  k_trace<true> finishes the parked walks and RECORDS the pixels it visits in a per-lane
+//                   strip; the Suzuki start of every border with min_len < n < max_len reserves its slice of the point
+//                   pool and leaves a contour record, and the warp copies the winner's strip into the slice.
+//   k_emit:         re-walks what is not recorded: contours closed by k_trace<false> (2 walkers per contour) and the
+//                   first TRACE_PARK_N steps in either direction of the long ones.
 #pragma once
 #include "ab_device.cuh"
 
@@ -132,6 +134,10 @@ __global__ void __launch_bounds__(256) k_scan_starts(Batch b) {
 #define AB_EMIT_STEPS 16
 #endif
 constexpr int TRACE_LONG_T = AB_TRACE_LONG_T;
+// iterations a walk has made when k_trace<false> parks it: lanes are refilled only between rounds of AB_TRACE_STEPS
+// iterations, so the count is the first multiple of the round length that reaches the parking threshold
+constexpr int TRACE_PARK_N = (AB_TRACE_LONG_T + AB_TRACE_STEPS - 1) / AB_TRACE_STEPS * AB_TRACE_STEPS;
+static_assert(TRACE_PARK_N % 2 == 0 && AB_TRACE_STEPS_LONG % 2 == 0, "paired strip stores need even rounds");
 
 // `s` is the start state of a start candidate (table flags e): does its trigger scan before key0?
 // (raster positions fit 32 bits: W, H <= 16384)
@@ -172,10 +178,15 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
     const uint8_t* __restrict__ lut_bw = b.walk_lut + WALK_LUT_SIZE;
 #endif
     int nf = 0, ng = 0, frame = 0;
-    // LONG only: walker states at the last two power-of-two step counts (pixels, back-directions, step count);
-    // they cut the finished contour into segments that k_emit_long writes in parallel
-    uint32_t cpF1 = 0, cpF2 = 0, cpB1 = 0, cpB2 = 0, cpd = 0;
-    int pF = 0, qB = 0;
+    // LONG only: entry k of the lane's strip = (pixel of the forward walker after TRACE_PARK_N + 1 + k steps, pixel of the
+    // backward walker after as many) = points TRACE_PARK_N + 1 + k and n - TRACE_PARK_N - 1 - k of the contour.  Losers
+    // record for nothing (8 bytes per iteration); winners save the second walk over the border that k_emit_long used to
+    // make (one dependent L1/L2 round trip per point, 0.5 ms per 256 4K frames).
+    const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint2* const rec = LONG ? b.trace_rec + (size_t)gid * b.rec_half : nullptr;
+    uint32_t cp_off = 0;
+    uint2 rec_prev = make_uint2(0u, 0u);
+    int cp_len = 0;  // > 0: this lane's walk closed a kept contour whose strip is still to be copied
     for (;;) {
         unsigned idle = __ballot_sync(FULL, !active && !exhausted);
         if (idle) {
@@ -200,9 +211,8 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                     bw = WalkState{(int)(q.bxy & 0xFFFFu), (int)(q.bxy >> 16), (int)((q.dirs >> 4) & 7u)};
                     nf = (int)q.nf;
                     ng = (int)q.ng;
+                    AB_BOUND(nf == TRACE_PARK_N && ng == TRACE_PARK_N);
                     e_fw = lut_fw[window9(im, fw.x, fw.y) | ((uint32_t)fw.b << 9)];
-                    cpF1 = cpF2 = cpB1 = cpB2 = cpd = 0;
-                    pF = qB = 0;
                     active = true;
                 } else {
                     uint2 rec = b.starts[i];
@@ -239,17 +249,21 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                 }
                 const uint32_t w_f = window9(im, fw.x, fw.y);
                 WalkState bw1{bw0.x + step_dx(bw0.b), bw0.y + step_dy(bw0.b), 0};
+                if (LONG) {  // both pixels are known before the step tables answer: the store is off the dependent chain
+                    AB_BOUND(nf >= TRACE_PARK_N && (unsigned)(nf - TRACE_PARK_N) < b.rec_half);
+                    // two iterations per 16-byte store (one 8-byte store per iteration: k_trace<true> 0.93 instead of 0.77 ms):
+                    // a round starts at an even entry (TRACE_PARK_N and the round length are even), so the parity of r is
+                    // the parity of the entry; a walk that closes on an even entry flushes its half below.  Plain stores
+                    // and plain loads: st.cg / ld.cg were measured and are no faster or much slower (profiles/README.md)
+                    const uint2 cur = make_uint2((uint32_t)fw.x | ((uint32_t)fw.y << 16), (uint32_t)bw1.x | ((uint32_t)bw1.y << 16));
+                    if (r & 1) *reinterpret_cast<uint4*>(rec + (nf - TRACE_PARK_N - 1)) = make_uint4(rec_prev.x, rec_prev.y, cur.x, cur.y);
+                    else rec_prev = cur;
+                }
                 const uint32_t w_q = window9(im, bw1.x, bw1.y);
                 e_fw = lut_fw[w_f | ((uint32_t)fw.b << 9)];
                 const uint32_t e_bw = lut_bw[w_q | ((uint32_t)((bw0.b + 4) & 7) << 9)];
                 bw1.b = (int)(e_bw & 7u);
                 nf++;
-                if (LONG && (nf & (nf - 1)) == 0) {  // parked walks arrive with nf < 64: the first checkpoint is step 64
-                    cpF2 = cpF1;
-                    cpF1 = (uint32_t)fw.x | ((uint32_t)fw.y << 16);
-                    cpd = (cpd & ~0x3Fu) | ((cpd & 7u) << 3) | (uint32_t)fw.b;
-                    pF = nf;
-                }
                 if (same_state(fw, bw0)) {
                     closed = true;
                 } else if ((e_fw & (WALK_TRIG_OUTER | WALK_TRIG_HOLE)) && smaller_trigger(e_fw, fw, im.W, st.key)) {
@@ -257,12 +271,6 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                 } else {
                     bw = bw1;
                     ng++;
-                    if (LONG && (ng & (ng - 1)) == 0) {
-                        cpB2 = cpB1;
-                        cpB1 = (uint32_t)bw.x | ((uint32_t)bw.y << 16);
-                        cpd = (cpd & ~0xFC0u) | (((cpd >> 6) & 7u) << 9) | ((uint32_t)bw.b << 6);
-                        qB = ng;
-                    }
                     if (same_state(fw, bw)) closed = true;
                     else if ((e_bw & (WALK_TRIG_OUTER | WALK_TRIG_HOLE)) && smaller_trigger(e_bw, bw, im.W, st.key)) dead = true;
                     else if (nf + ng >= b.max_len) dead = true;  // too long: dropped by :517 anyway
@@ -281,31 +289,9 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                             b.contours[ci] = ContourRec{(uint32_t)frame | type_bit, (uint32_t)off, (uint32_t)len, (uint32_t)st.key};
                         } else {
                             b.contours[ci] = ContourRec{(uint32_t)frame | type_bit | CONTOUR_LONG, (uint32_t)off, (uint32_t)len, (uint32_t)st.key};
-                            // boundaries 0 <= p/2 <= p <= nf <= n-q <= n-q/2 <= n; a missing checkpoint collapses its
-                            // segment onto the start state.  The second-last checkpoint exists iff the last one is >= 128.
-                            const uint32_t sxy = (uint32_t)st.x | ((uint32_t)st.y << 16), sb = (uint32_t)st.b;
-                            const bool f1 = pF > 0, f2 = pF >= 128, g1 = qB > 0, g2 = qB >= 128;
-                            EmitRec e;
-                            e.frame = (uint32_t)frame | type_bit;
-                            e.off = (uint32_t)off;
-                            e.n = (uint32_t)len;
-                            e.a[0] = f2 ? (uint32_t)(pF >> 1) : 0u;
-                            e.a[1] = f1 ? (uint32_t)pF : 0u;
-                            e.a[2] = (uint32_t)nf;
-                            e.a[3] = (uint32_t)(len - (g1 ? qB : 0));
-                            e.a[4] = (uint32_t)(len - (g2 ? (qB >> 1) : 0));
-                            e.xy[0] = sxy;
-                            e.xy[1] = f2 ? cpF2 : sxy;
-                            e.xy[2] = f1 ? cpF1 : sxy;
-                            e.xy[3] = (uint32_t)fw.x | ((uint32_t)fw.y << 16);
-                            e.xy[4] = g1 ? cpB1 : sxy;
-                            e.xy[5] = g2 ? cpB2 : sxy;
-                            e.dirs = sb | ((f2 ? ((cpd >> 3) & 7u) : sb) << 3) | ((f1 ? (cpd & 7u) : sb) << 6) | ((uint32_t)fw.b << 9) |
-                                     ((g1 ? ((cpd >> 6) & 7u) : sb) << 12) | ((g2 ? ((cpd >> 9) & 7u) : sb) << 15);
-                            e.pad = 0;
-                            const unsigned int ei = atomicAdd(&b.cnt->n_emit_long, 1u);  // at most one per parked walk: fits cap_long
-                            AB_BOUND(ei < b.cap_long);
-                            b.emitq[ei] = e;
+                            cp_off = (uint32_t)off;
+                            cp_len = len;
+                            if (!(r & 1)) rec[nf - 1 - TRACE_PARK_N] = rec_prev;
                         }
                     }
                     active = false;
@@ -335,6 +321,35 @@ __global__ void __launch_bounds__(128) k_trace(Batch b) {
                     nodefer = true;  // queue full: finish this walk in place (correct, just slower)
                 }
             }
+        }
+        if (LONG) {  // winners of this round: the warp copies each strip into its slice of the pool, 32 points at a time
+            __syncwarp();  // the strips were written by their own lanes
+            unsigned cpm = __ballot_sync(FULL, cp_len > 0);
+            while (cpm) {
+                const int s = __ffs((int)cpm) - 1;
+                cpm &= cpm - 1;
+                const int n = __shfl_sync(FULL, cp_len, s);
+                const int f = __shfl_sync(FULL, nf, s) - TRACE_PARK_N, g = __shfl_sync(FULL, ng, s) - TRACE_PARK_N;
+                uint32_t* dst = b.pool + __shfl_sync(FULL, cp_off, s);
+                const uint2* src = b.trace_rec + (size_t)(gid - (unsigned)lane + (unsigned)s) * b.rec_half;
+                AB_BOUND(f >= 1 && g >= 0 && g <= f && n == f + g + 2 * TRACE_PARK_N);
+                constexpr int CU = 8;  // loads in flight per lane: the copy holds up the other 31 walks of the warp
+                for (int k0 = lane; k0 < f; k0 += 32 * CU) {
+                    uint2 v[CU];
+#pragma unroll
+                    for (int u = 0; u < CU; u++)
+                        if (k0 + 32 * u < f) v[u] = src[k0 + 32 * u];
+#pragma unroll
+                    for (int u = 0; u < CU; u++) {
+                        const int k = k0 + 32 * u;
+                        if (k < f) {
+                            dst[TRACE_PARK_N + 1 + k] = v[u].x;
+                            if (k < g) dst[n - TRACE_PARK_N - 1 - k] = v[u].y;
+                        }
+                    }
+                }
+            }
+            cp_len = 0;
         }
     }
 }
@@ -372,105 +387,26 @@ __global__ void __launch_bounds__(128) k_emit(Batch b) {
                     // costs one dependent load round trip instead of two (forward lanes, then backward lanes)
                     const ContourRec rec = b.contours[i < ncont ? i : i - ncont];
                     const int n = (int)rec.n;
-                    if (n > 0 && !(rec.frame & CONTOUR_LONG)) {  // long contours: k_emit_long
+                    if (n > 0) {
                         im = b.bit_image((int)(rec.frame & CONTOUR_FRAME_MASK));
                         TraceStart st;
                         make_start(im, (int)(rec.frame >> 31), (int)(rec.key % (uint32_t)b.W), (int)(rec.key / (uint32_t)b.W), st);
                         w = WalkState{st.x, st.y, st.b};
-                        const int h0 = (n + 1) >> 1;
+                        // a long contour (n > 2 TRACE_PARK_N) only lacks the points walked before it was parked: 0 .. PARK_N
+                        // and n-1 .. n-PARK_N; the others are walked whole, half from either end
+                        const bool lng = (rec.frame & CONTOUR_LONG) != 0u;
+                        const int h0 = lng ? TRACE_PARK_N + 1 : (n + 1) >> 1;
                         backward = i >= ncont;
                         if (!backward) {
                             out = b.pool + rec.off;  // positions 0 .. h0-1, ascending
                             remaining = h0;
                             nb = neighbours8(im, w.x, w.y);
                         } else {
-                            out = b.pool + rec.off + n - 1;  // positions n-1 .. h0, descending
-                            remaining = n - h0;
+                            out = b.pool + rec.off + n - 1;  // positions n-1 .. h0 (long: n - PARK_N), descending
+                            remaining = lng ? TRACE_PARK_N : n - h0;
                         }
                         active = remaining > 0;
                     }
-                }
-            }
-        }
-        if (__ballot_sync(FULL, active) == 0) {
-            if (__ballot_sync(FULL, !exhausted) == 0) break;
-            continue;
-        }
-        if (active) {
-            if (!backward) {
-                for (int r = 0; r < STEPS; r++) {
-                    AB_BOUND(out >= b.pool && out < b.pool + b.cap_pool);
-                    *out++ = (uint32_t)w.x | ((uint32_t)w.y << 16);
-                    if (--remaining == 0) {
-                        active = false;
-                        break;
-                    }
-                    walk_forward(w, nb);
-                    nb = neighbours8(im, w.x, w.y);
-                }
-            } else {
-                for (int r = 0; r < STEPS; r++) {
-                    walk_backward(im, w);
-                    AB_BOUND(out >= b.pool && out < b.pool + b.cap_pool);
-                    *out-- = (uint32_t)w.x | ((uint32_t)w.y << 16);
-                    if (--remaining == 0) {
-                        active = false;
-                        break;
-                    }
-                }
-            }
-        }
-    }
-}
-
-// Long contours: 12 work items per EmitRec -- every segment between two known walker states is filled from both
-// ends.  The longest dependent chain of the stage drops from n/2 to about n/8 neighbourhood loads (the walkers are
-// latency bound: one L2/DRAM round trip per step).  Items are ordered so that a warp holds one kind of walker.
-__global__ void __launch_bounds__(128) k_emit_long(Batch b) {
-    constexpr int STEPS = AB_EMIT_STEPS;
-    const unsigned FULL = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31;
-    unsigned int nrec = b.cnt->n_emit_long;
-    if (nrec > b.cap_long) nrec = b.cap_long;
-    const unsigned int n_items = 12u * nrec;
-    bool active = false, exhausted = false, backward = false;
-    BitImage im = b.bit_image(0);
-    WalkState w{0, 0, 0};
-    uint32_t nb = 0;
-    int remaining = 0;
-    uint32_t* out = nullptr;
-    for (;;) {
-        unsigned idle = __ballot_sync(FULL, !active && !exhausted);
-        if (idle) {
-            unsigned base = 0;
-            int leader = __ffs((int)idle) - 1;
-            if (lane == leader) base = atomicAdd(&b.cnt->emit_long_work, (unsigned)__popc(idle));
-            base = __shfl_sync(FULL, base, leader);
-            if (!active && !exhausted) {
-                unsigned i = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
-                if (i >= n_items) {
-                    exhausted = true;
-                } else {
-                    backward = i >= 6u * nrec;
-                    const unsigned k = backward ? i - 6u * nrec : i;
-                    const unsigned seg = k / nrec;  // 0..5
-                    const EmitRec* e = b.emitq + (k - seg * nrec);
-                    const uint32_t n = e->n;
-                    const uint32_t a0 = seg == 0 ? 0u : e->a[seg - 1], a1 = seg == 5 ? n : e->a[seg];
-                    const int L = (int)(a1 - a0), h = (L + 1) >> 1;
-                    const unsigned s = backward ? (seg == 5 ? 0u : seg + 1u) : seg;  // state index (S6 = S0)
-                    const uint32_t xy = e->xy[s];
-                    im = b.bit_image((int)(e->frame & CONTOUR_FRAME_MASK));
-                    w = WalkState{(int)(xy & 0xFFFFu), (int)(xy >> 16), (int)((e->dirs >> (3 * s)) & 7u)};
-                    if (!backward) {
-                        out = b.pool + e->off + a0;  // positions a0 .. a0+h-1, ascending
-                        remaining = h;
-                        if (h > 0) nb = neighbours8(im, w.x, w.y);
-                    } else {
-                        out = b.pool + e->off + a1 - 1;  // positions a1-1 .. a0+h, descending
-                        remaining = L - h;
-                    }
-                    active = remaining > 0;
                 }
             }
         }

@@ -38,9 +38,9 @@ sys.path.insert(0, ROOT)
 
 MARKER_SIZE = 0.05
 N_BASE = 8  # distinct rendered scenes; every frame of a batch gets its own noise realisation
-# kernels launched per batch: threshold, scan_starts, trace, trace_long, emit_long, emit, polygon, frame_filter,
+# kernels launched per batch: threshold, scan_starts, trace, trace_long, emit, polygon, frame_filter,
 # homography, sample, otsu, identify, refine, finalize, pose (+ erode when erosion is on)
-KERNELS_PER_BATCH = 15
+KERNELS_PER_BATCH = 14
 
 CONFIGS = {
     "C1": dict(workload="C1: reference frame testdata/single 640x480 (tests/golden), Fiducidal, ADPT_THRES 7/7 + LINES + PnP, one frame per call",

@@ -301,7 +301,9 @@ def test_pose_sensitivity_to_the_lapack_line_fit(det):
 
 def test_parked_walk_queue_overflow_finishes_in_place(built, monkeypatch):
     """When the queue of parked long walks is full, k_trace<false> finishes the walk itself and k_emit (two walkers per
-    contour) writes it: same markers, same contours as with the default capacity (12-walker k_emit_long path)."""
+    contour) writes it: same markers, same contours as with the default capacity (where k_trace<true> records the points
+    of the walks it finishes and copies the winners' strips).  The same holds when the strip budget only pays for one CTA
+    of k_trace<true>."""
     from aruco_b200 import MarkerDetector, synth
     g, _ = synth.render_frame(1920, 1080, 50, 21, 2.0)
     K, D = synth.camera_for(1920, 1080)
@@ -314,6 +316,13 @@ def test_parked_walk_queue_overflow_finishes_in_place(built, monkeypatch):
     assert len(ref) >= 45 and [m.id for m in got] == [m.id for m in ref]
     assert all((a.corners == b.corners).all() and (a.Rvec == b.Rvec).all() for a, b in zip(got, ref))
     got_contours = [small.getContour(0, i) for i in range(len(small.getAllCandidates(0)[0]))]
+    assert len(got_contours) == len(ref_contours) and all((a == b).all() for a, b in zip(got_contours, ref_contours))
+    monkeypatch.delenv("ARUCO_B200_CAP_LONG")
+    monkeypatch.setenv("ARUCO_B200_TRACE_REC_MB", "1")
+    lean = MarkerDetector()
+    got = lean.detect(g, K, D, 0.05)
+    assert [m.id for m in got] == [m.id for m in ref] and all((a.corners == b.corners).all() for a, b in zip(got, ref))
+    got_contours = [lean.getContour(0, i) for i in range(len(lean.getAllCandidates(0)[0]))]
     assert len(got_contours) == len(ref_contours) and all((a == b).all() for a, b in zip(got_contours, ref_contours))
 
 
