@@ -95,7 +95,11 @@ AB_API int ab_load_hrm_dictionary(ab_context* ctx, int n, int count, const uint8
 AB_API int ab_set_decoder_callback(ab_context* ctx, ab_decoder_fn fn, void* user); /* h:243 (custom fn)  */
 /* Sizes device buffers. max_start_candidates / max_contour_points are per frame; <=0 picks defaults.  The capacities
  * are remembered: later automatic re-reservations (a larger batch, another warp size) keep them.  On failure the
- * context holds no buffers and the next call reserves again.                                                      */
+ * context holds no buffers and the next call reserves again.
+ * One buffer is sized at the first batch instead, because it depends on the maximum contour size in force then: the
+ * strips in which the border walkers record their pixels (4 * (max contour length + 4) bytes per walker lane; 4.7 GB per
+ * in-flight batch for 4K frames with the default sizes).  It never exceeds 6 GB unless the environment variable
+ * ARUCO_B200_TRACE_REC_MB says otherwise -- a smaller budget only means fewer walker lanes.                            */
 AB_API int ab_reserve(ab_context* ctx, int width, int height, int max_batch, int max_quads_per_frame,
                       int max_candidates_per_frame, int64_t max_start_candidates_per_frame,
                       int64_t max_contour_points_per_frame);
